@@ -1,0 +1,189 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.json from the UNMODIFIED reference (container-only).
+
+The reference holds no tests, fixtures or golden vectors,
+so parity is pinned on outputs of the reference itself, imported from
+/root/reference through oracle/ref_shim.py and run here:
+
+  G1  forward_trajectories.json   RateStateModel.evaluate()[1]  (RateStateModel.py:188)
+        Dc in {1,10,100,1000,1350,5000,10000} x RadiationDamping in {True, False},
+        plus a stiff case (Dc = 0.05) and the silent-failure case (Dc = 1e-4, q9).
+  G2  chain_list_priors.json / chain_dict_priors.json   MCMC.sample(False) (MCMC.py:391)
+        run with np.random.seed(...), with every random draw logged
+        (proposal, uniform, unit-scale gamma) plus accept flags, chain and std2.
+  G3  sse_grid.json   SSE(Dc) on a grid for the seeded data set (MCMC.py:387).
+
+Everything is written in the reference's own ``__ndarray__`` JSON wire format
+(json_save_load.py:37-38).  Versions of numpy/scipy are stamped into each file:
+the reference pins none, and SciPy's dop853 is part of the oracle's identity.
+
+Usage: python oracle/make_golden.py         (about two minutes)
+"""
+import contextlib
+import io
+import json
+import os
+import platform
+import sys
+import warnings
+
+import numpy as np
+import scipy
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.ref_shim import load_reference  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+STAMP = {"numpy": np.__version__, "scipy": scipy.__version__, "python": platform.python_version(),
+         "generator": "oracle/make_golden.py", "source": "unmodified reference via oracle/ref_shim.py"}
+
+
+def enc(o):
+    if isinstance(o, np.ndarray):
+        return {"__ndarray__": True, "data": o.tolist(), "shape": list(o.shape)}
+    if isinstance(o, (np.floating, np.integer, np.bool_)):
+        return o.item()
+    raise TypeError(type(o))
+
+
+def dump(name, obj):
+    obj = dict(obj)
+    obj["_stamp"] = STAMP
+    path = os.path.join(OUT, name)
+    with open(path, "w") as f:
+        json.dump(obj, f, default=enc)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def ref_forward(rsm, dc, damping=True, n=500):
+    m = rsm.RateStateModel(number_time_steps=n)
+    m.Dc = float(dc)
+    m.RadiationDamping = damping
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t, acc, _ = m.evaluate()
+    return t, acc
+
+
+def make_data(rsm, dc_true, seed, n=500):
+    """cfg-1 data set: seed immediately before evaluate(); keep acc_noise."""
+    m = rsm.RateStateModel(number_time_steps=n)
+    m.Dc = float(dc_true)
+    np.random.seed(seed)
+    t, acc, acc_noise = m.evaluate()
+    return acc_noise
+
+
+def record_chain(rsm, mcm, data, dc_true, qpriors, qstart, nsamples, seed):
+    """Run MCMC.sample(False) with all random draws logged."""
+    log = {"proposals": [], "V_used": [], "uniforms": [], "gammas_unit": [], "gammas_scaled": []}
+    real_mvn, real_rand, real_gamma = np.random.multivariate_normal, np.random.rand, mcm.gamma
+
+    def mvn(mean, cov, *a, **k):
+        x = real_mvn(mean, cov, *a, **k)
+        log["proposals"].append(float(np.ravel(x)[0]))
+        log["V_used"].append(float(np.ravel(cov)[0]))
+        return x
+
+    def rand(*a):
+        u = real_rand(*a)
+        log["uniforms"].append((len(log["proposals"]) - 1, float(np.ravel(u)[0])))
+        return u
+
+    class GammaProxy:
+        """scipy.stats.gamma.rvs(a, scale=s) == s * RandomState.standard_gamma(a)."""
+        @staticmethod
+        def rvs(aval, scale=1.0, size=1):
+            g0 = np.random.standard_gamma(aval, size)
+            log["gammas_unit"].append(float(g0[0]))
+            g = np.ravel(g0 * scale)          # scale arrives as a (1,1) array (SSq keeps dims)
+            log["gammas_scaled"].append(float(g[0]))
+            return g
+
+    def run(patched):
+        model = rsm.RateStateModel(number_time_steps=len(data))
+        np.random.seed(seed)
+        mc = mcm.MCMC(model, data, dc_true, qpriors, qstart, nsamples=nsamples)
+        if patched:
+            np.random.multivariate_normal, np.random.rand, mcm.gamma = mvn, rand, GammaProxy
+        try:
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                out = mc.sample(False)
+        finally:
+            np.random.multivariate_normal, np.random.rand, mcm.gamma = real_mvn, real_rand, real_gamma
+        # MCMC.py:503 prints "<isample> <accept>"; accept is a (1,1) bool array when the
+        # proposal was in bounds ("[[ True]]") and a numpy bool otherwise ("False")
+        accepts = ["True" in ln for ln in buf.getvalue().splitlines()
+                   if ln and ln.split()[0].isdigit() and ("True" in ln or "False" in ln)]
+        assert len(accepts) == nsamples
+        return out, np.asarray(mc.std2), np.asarray(mc.Vstart), accepts
+
+    plain = run(False)
+    rec = run(True)
+    # the logging wrappers must not change the chain
+    assert np.array_equal(plain[0], rec[0]) and np.array_equal(plain[1], rec[1]), "recorder changed the chain"
+    out, std2, vstart, accepts = rec
+    uni = np.full(nsamples, np.nan)
+    for i, u in log["uniforms"]:
+        uni[i] = u
+    return {
+        "seed": seed, "dc_true": dc_true, "qstart": qstart, "nsamples": nsamples,
+        "nburn": int(nsamples / 2),
+        "qpriors_form": "dict" if isinstance(qpriors, dict) else "list",
+        "lo": float(qpriors[1]), "hi": float(qpriors[2]), "n_prior_len": len(qpriors),
+        "data": np.asarray(data),
+        "proposals": np.array(log["proposals"]), "V_used": np.array(log["V_used"]),
+        "uniforms": uni, "gammas_unit": np.array(log["gammas_unit"]),
+        "accepts": np.array(accepts, dtype=np.int64),
+        "chain_post_burn": np.asarray(out), "std2_post_burn": std2, "Vstart": vstart,
+    }
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    rsm, mcm = load_reference()
+
+    # G1
+    g1 = {"cases": []}
+    for damping in (True, False):
+        for dc in (1.0, 10.0, 100.0, 1000.0, 1350.0, 5000.0, 10000.0):
+            t, acc = ref_forward(rsm, dc, damping)
+            g1["cases"].append({"Dc": dc, "RadiationDamping": damping, "N": 500, "acc": acc,
+                                "t_last": float(t[-1])})
+    t, acc = ref_forward(rsm, 0.05, True)
+    g1["cases"].append({"Dc": 0.05, "RadiationDamping": True, "N": 500, "acc": acc, "t_last": float(t[-1])})
+    t, acc = ref_forward(rsm, 1e-4, True)
+    g1["cases"].append({"Dc": 1e-4, "RadiationDamping": True, "N": 500, "acc": acc, "t_last": float(t[-1]),
+                        "filled": int(np.count_nonzero(t) + 1), "t1": float(t[1])})
+    # a different grid: N = 200 over [0, 30]
+    m = rsm.RateStateModel(number_time_steps=200, end_time=30.0)
+    m.Dc = 700.0
+    t, acc, _ = m.evaluate()
+    g1["cases"].append({"Dc": 700.0, "RadiationDamping": True, "N": 200, "end_time": 30.0, "acc": acc,
+                        "t_last": float(t[-1])})
+    dump("forward_trajectories.json", g1)
+
+    # G3 (and the data set used by G2)
+    data = make_data(rsm, 1350.0, 12345)
+    grid = np.array([300.0, 700.0, 1000.0, 1200.0, 1300.0, 1350.0, 1400.0, 1500.0, 2000.0, 4000.0, 9000.0])
+    sse = []
+    for dc in grid:
+        _, acc = ref_forward(rsm, dc, True)
+        sse.append(np.sum((acc.reshape(1, -1) - data) ** 2, axis=1).item())     # MCMC.py:387
+    dump("sse_grid.json", {"dc_true": 1350.0, "seed": 12345, "data": data, "grid": grid, "sse": np.array(sse)})
+
+    # G2
+    dump("chain_list_priors.json",
+         record_chain(rsm, mcm, data, 1350.0, ["Uniform", 0.0, 10000.0], 1000.0, nsamples=120, seed=2024))
+    dump("chain_dict_priors.json",
+         record_chain(rsm, mcm, data, 1350.0, {1: 0.0, 2: 10000.0}, 1000.0, nsamples=60, seed=7))
+    # a chain that starts near the upper bound so that out-of-bounds proposals occur (q10)
+    dump("chain_bounds.json",
+         record_chain(rsm, mcm, data, 1350.0, ["Uniform", 900.0, 1500.0], 1450.0, nsamples=60, seed=99))
+
+
+if __name__ == "__main__":
+    main()
