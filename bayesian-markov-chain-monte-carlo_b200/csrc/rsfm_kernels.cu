@@ -1,0 +1,825 @@
+// rsfm_kernels.cu -- CUDA kernels and the C ABI (include/rsfm.h) of the RSF-MCMC
+// hot path for B200 (sm_100a).  There is no CPU fallback: every entry point that
+// computes needs a compute-capability-10 device and fails loudly otherwise.
+//
+// Kernels
+//   rsf_forward_kernel   batched RateStateModel.evaluate() (+ SSE)      a9, a10, a11, a4
+//   rsf_init_kernel      compute_initial_covariance + first SSqcalc     a8
+//   rsf_mcmc_kernel      K fused iterations of MCMC.sample's loop       a1-a7
+//   suffstats_kernel     pooled (n, sum q, sum qq^T) over chains        8e
+//   chain_diag_kernel    per-chain mean / var / ESS                     8d (ESS/s)
+//   dfma_peak_kernel     FP64 roofline denominator
+// (a-numbers: SURVEY.md section 8a.)
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+#include <new>
+
+#include <cuda_runtime.h>
+
+#include "rsfm.h"
+#include "rsfm_device.cuh"
+#include "philox.cuh"
+
+using namespace rsfm;
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, const char *detail)
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail ? detail : "");
+    return code;
+}
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) return set_err(RSFM_ERR_CUDA, #expr ": %s", cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" int rsfm_abi_version(void) { return RSFM_ABI_VERSION; }
+extern "C" const char *rsfm_last_error(void) { return g_err; }
+
+extern "C" void rsfm_cfg_defaults(rsfm_cfg *c)
+{
+    memset(c, 0, sizeof(*c));
+    c->a = 0.011; c->b = 0.014; c->mu_ref = 0.6; c->V_ref = 1.0; c->k1 = 1.0e-7;     // RateStateModel.py:5-9
+    c->t_start = 0.0; c->t_final = 50.0;                                             // :10-11
+    c->delta_t = (c->t_final - c->t_start) / 500;                                    // :177
+    c->n_out = (int32_t)floor((c->t_final - c->t_start) / c->delta_t);               // :358
+    c->mu_t_zero = 0.6;
+    c->vstep_period = 1000.0; c->vstep_factor = 10.0;
+    c->rtol = 1e-6; c->atol = 1e-10; c->nmax = 500;                                  // :374, scipy nsteps
+    c->n0 = 0.01;                                                                    // MCMC.py:97
+    for (int i = 0; i < RSFM_MAX_PARAMS; i++) { c->lo[i] = 0.0; c->hi[i] = 10000.0; }
+    c->radiation_damping = 1;
+    c->loading = RSFM_LOAD_SINE_DECAY;
+    c->integ_mode = RSFM_INTEG_PARITY;
+    c->n_params = 1;
+    c->n_prior_len = 3;
+    c->adapt_interval = 10;
+    c->adapt_mode = RSFM_ADAPT_NONE;
+}
+
+extern "C" int rsfm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+static int require_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(RSFM_ERR_NO_DEVICE, "no CUDA device: librsfm has no CPU fallback%s", "");
+    }
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) {
+        cudaGetLastError();
+        return set_err(RSFM_ERR_NO_DEVICE, "current device is not sm_100 (B200): librsfm has no other code path%s", "");
+    }
+    return RSFM_OK;
+}
+
+static int check_cfg(const rsfm_cfg *c)
+{
+    if (!c) return set_err(RSFM_ERR_INVALID, "cfg is NULL%s", "");
+    if (c->n_out < 1 || c->nmax < 1 || !(c->delta_t > 0.0)) return set_err(RSFM_ERR_INVALID, "bad grid in cfg%s", "");
+    if (c->n_params != 1 && c->n_params != 3) return set_err(RSFM_ERR_INVALID, "n_params must be 1 or 3%s", "");
+    if (c->loading != RSFM_LOAD_SINE_DECAY && c->loading != RSFM_LOAD_VSTEP)
+        return set_err(RSFM_ERR_INVALID, "bad loading selector%s", "");
+    if (c->integ_mode != RSFM_INTEG_PARITY && c->integ_mode != RSFM_INTEG_CARRY)
+        return set_err(RSFM_ERR_INVALID, "bad integ_mode%s", "");
+    if (c->adapt_interval < 2 || c->adapt_interval > 64) return set_err(RSFM_ERR_INVALID, "adapt_interval must be in [2, 64]%s", "");
+    return RSFM_OK;
+}
+
+static ModelK make_model(const rsfm_cfg *c)
+{
+    ModelK M;
+    M.mu_ref = c->mu_ref; M.V_ref = c->V_ref; M.k1 = c->k1; M.t_start = c->t_start;
+    M.delta_t = c->delta_t; M.mu_t_zero = c->mu_t_zero;
+    M.rtol = c->rtol; M.atol = c->atol; M.vstep_period = c->vstep_period; M.vstep_factor = c->vstep_factor;
+    M.n_out = c->n_out; M.nmax = c->nmax; M.damping = c->radiation_damping; M.loading = c->loading;
+    M.integ_mode = c->integ_mode;
+    return M;
+}
+
+// chains per block: small batches are spread over more SMs (the kernel is latency
+// bound there), large batches use 128-thread blocks.
+static int pick_block(int C)
+{
+    if (C <= 148 * 32) return 32;
+    if (C <= 148 * 64 * 2) return 64;
+    return 128;
+}
+
+// ---------------------------------------------------------------------------
+// forward batch
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+rsf_forward_kernel(ModelK M, int C, double a0, double b0, const double *__restrict__ dc_in,
+                   const double *__restrict__ a_in, const double *__restrict__ b_in,
+                   const double *__restrict__ data, double *__restrict__ acc_out,
+                   double *__restrict__ t_out, double *__restrict__ sse_out, int32_t *__restrict__ status_out,
+                   int32_t *__restrict__ filled_out, unsigned long long *__restrict__ nrhs_out,
+                   unsigned long long *__restrict__ nstep_out)
+{
+    __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = c < C;
+    const int cc = active ? c : C - 1;
+    const double dc = dc_in[cc];
+    const double a = a_in ? a_in[cc] : a0;
+    const double b = b_in ? b_in[cc] : b0;
+    SeriesStage series;
+    series.begin(s_tile, s_bar, data, M.n_out);
+    series.start_solve();
+    SolveOut o = rsf_solve(M, a, b, dc, active, series, acc_out ? acc_out + cc : nullptr, nullptr, (size_t)C,
+                           1.0, nullptr, t_out ? t_out + cc : nullptr);
+    if (active) {
+        if (sse_out) sse_out[c] = o.sse;
+        if (status_out) status_out[c] = o.status;
+        if (filled_out) filled_out[c] = o.filled;
+        if (nrhs_out) nrhs_out[c] = o.nrhs;
+        if (nstep_out) nstep_out[c] = o.nstep;
+    }
+}
+
+extern "C" int rsfm_forward_batch(const rsfm_cfg *cfg, int32_t C, const double *dc_dev, const double *a_dev,
+                                  const double *b_dev, const double *data_dev, double *acc_out_dev,
+                                  double *t_out_dev, double *sse_out_dev, int32_t *status_dev, int32_t *filled_dev,
+                                  uint64_t *nrhs_dev, uint64_t *nstep_dev, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (C < 1 || !dc_dev) return set_err(RSFM_ERR_INVALID, "forward_batch: C < 1 or dc_dev NULL%s", "");
+    if (sse_out_dev && !data_dev) return set_err(RSFM_ERR_INVALID, "forward_batch: sse_out needs data%s", "");
+    if (data_dev && ((uintptr_t)data_dev & 15)) return set_err(RSFM_ERR_INVALID, "forward_batch: data_dev must be 16-byte aligned%s", "");
+    rc = require_device();
+    if (rc) return rc;
+    const int block = pick_block(C);
+    const int grid = (C + block - 1) / block;
+    rsf_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+        make_model(cfg), C, cfg->a, cfg->b, dc_dev, a_dev, b_dev, sse_out_dev ? data_dev : nullptr, acc_out_dev,
+        t_out_dev, sse_out_dev, status_dev, filled_dev, (unsigned long long *)nrhs_dev, (unsigned long long *)nstep_dev);
+    CUDA_TRY(cudaGetLastError());
+    return RSFM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// sampler state
+// ---------------------------------------------------------------------------
+struct SamplerDev {
+    double *q;          // [d][C]
+    double *sse;        // [C]
+    double *sigma2;     // [C]
+    double *chol;       // [d(d+1)/2][C]; d = 1: proposal variance (as the reference stores it)
+    double *ring;       // [adapt_interval][C] last samples, COMPAT adaptation (d = 1)
+    double *suff;       // [d + d(d+1)/2][C] per-chain sums for POOLED adaptation
+    double *data;       // [n_out] padded to an even count
+    unsigned int *accepted;        // [C]
+    int *status;                   // [C] sticky OR of RSFM_CHAIN_* of all solves
+    unsigned long long *nrhs;      // [C]
+    unsigned long long *nstep;     // [C]
+};
+
+struct rsfm_sampler {
+    rsfm_cfg cfg;
+    int C;
+    uint64_t seed, chain_id0;
+    int64_t iteration;
+    int64_t suff_count;            // iterations accumulated in suff
+    int initialised;
+    int device;
+    SamplerDev d;
+    double *scratch;               // [n_out][C] base trajectory for rsfm_init
+    double *reduce_out;            // [16] device scratch for suffstats
+};
+
+static int tri(int d) { return d * (d + 1) / 2; }
+
+extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t seed, uint64_t chain_id0)
+{
+    if (check_cfg(cfg)) return nullptr;
+    if (C < 1) { set_err(RSFM_ERR_INVALID, "rsfm_create: C < 1%s", ""); return nullptr; }
+    if (require_device()) return nullptr;
+    rsfm_sampler *s = new (std::nothrow) rsfm_sampler();
+    if (!s) { set_err(RSFM_ERR_INVALID, "rsfm_create: out of host memory%s", ""); return nullptr; }
+    memset(s, 0, sizeof(*s));
+    s->cfg = *cfg; s->C = C; s->seed = seed; s->chain_id0 = chain_id0;
+    cudaGetDevice(&s->device);
+    const int d = cfg->n_params;
+    const size_t Cz = (size_t)C;
+    bool ok = true;
+    auto alloc = [&](void **p, size_t bytes) {
+        if (!ok) return;
+        if (cudaMalloc(p, bytes) != cudaSuccess) { ok = false; return; }
+        if (cudaMemset(*p, 0, bytes) != cudaSuccess) ok = false;
+    };
+    alloc((void **)&s->d.q, sizeof(double) * d * Cz);
+    alloc((void **)&s->d.sse, sizeof(double) * Cz);
+    alloc((void **)&s->d.sigma2, sizeof(double) * Cz);
+    alloc((void **)&s->d.chol, sizeof(double) * tri(d) * Cz);
+    alloc((void **)&s->d.ring, sizeof(double) * cfg->adapt_interval * Cz);
+    alloc((void **)&s->d.suff, sizeof(double) * (d + tri(d)) * Cz);
+    alloc((void **)&s->d.data, sizeof(double) * ((size_t)cfg->n_out + 2));
+    alloc((void **)&s->d.accepted, sizeof(unsigned int) * Cz);
+    alloc((void **)&s->d.status, sizeof(int) * Cz);
+    alloc((void **)&s->d.nrhs, sizeof(unsigned long long) * Cz);
+    alloc((void **)&s->d.nstep, sizeof(unsigned long long) * Cz);
+    alloc((void **)&s->reduce_out, sizeof(double) * 16);
+    if (!ok) {
+        set_err(RSFM_ERR_CUDA, "rsfm_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rsfm_destroy(s);
+        return nullptr;
+    }
+    return s;
+}
+
+extern "C" void rsfm_destroy(rsfm_sampler *s)
+{
+    if (!s) return;
+    cudaFree(s->d.q); cudaFree(s->d.sse); cudaFree(s->d.sigma2); cudaFree(s->d.chol); cudaFree(s->d.ring);
+    cudaFree(s->d.suff); cudaFree(s->d.data); cudaFree(s->d.accepted); cudaFree(s->d.status);
+    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->scratch); cudaFree(s->reduce_out);
+    delete s;
+}
+
+extern "C" int64_t rsfm_iteration(const rsfm_sampler *s) { return s ? s->iteration : -1; }
+
+// ---------------------------------------------------------------------------
+// init: compute_initial_covariance + SSqcalc(qstart)   (MCMC.py:245-266, 468)
+// ---------------------------------------------------------------------------
+// pass 0: base solve at q0, trajectory to scratch, SSE -> sse, sigma2_0
+// pass j = 1..d: solve at q0 with parameter j-1 scaled by (1 + 1e-6); accumulates
+//                the column products needed for X'X.  d = 1 keeps everything in
+//                one pass; d = 3 stores the three sensitivity columns.
+template <int D>
+__global__ void __launch_bounds__(128)
+rsf_init_kernel(ModelK M, int C, int pass, double a0, double b0, int n_prior_len, SamplerDev S,
+                double *__restrict__ scratch /* [(1+ (D>1?D:0))][n_out][C] */)
+{
+    __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = c < C;
+    const int cc = active ? c : C - 1;
+    double q[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) q[j] = S.q[(size_t)j * C + cc];
+    double fd_den = 1.0;
+    if (pass > 0) {
+        q[pass - 1] *= (1 + 1e-6);                    // MCMC.py:251
+        fd_den = q[pass - 1] * 1e-6;                  // :264
+    }
+    const double a = (D == 3) ? q[0] : a0;
+    const double b = (D == 3) ? q[1] : b0;
+    const double dc = q[D - 1];
+    SeriesStage series;
+    series.begin(s_tile, s_bar, pass == 0 ? S.data : nullptr, M.n_out);
+    series.start_solve();
+    const size_t plane = (size_t)M.n_out * C;
+    double xtx = 0.0;
+    if (pass == 0) {
+        SolveOut o = rsf_solve(M, a, b, dc, active, series, scratch + cc, nullptr, (size_t)C, 1.0, nullptr);
+        if (active) {
+            S.sse[c] = o.sse;
+            S.sigma2[c] = o.sse / (double)(M.n_out - n_prior_len);     // :261
+            S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status;
+        }
+    } else if (D == 1) {
+        SolveOut o = rsf_solve(M, a, b, dc, active, series, nullptr, scratch + cc, (size_t)C, fd_den, &xtx);
+        if (active) {
+            S.chol[c] = S.sigma2[c] * (1.0 / xtx);                     // Vstart, :265-266
+            S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status;
+        }
+    } else {
+        // d = 3: write the perturbed trajectory; columns are combined by rsf_init_finish_kernel
+        SolveOut o = rsf_solve(M, a, b, dc, active, series, scratch + (size_t)pass * plane + cc, nullptr,
+                               (size_t)C, 1.0, nullptr);
+        if (active) { S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; }
+    }
+}
+
+// d = 3: X'X from the stored trajectories, Vstart = sigma2_0 (X'X)^-1, chol(Vstart)
+__global__ void rsf_init_finish_kernel(int C, int n_out, SamplerDev S, const double *__restrict__ scratch)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const size_t plane = (size_t)n_out * C;
+    double den[3];
+    for (int j = 0; j < 3; j++) den[j] = S.q[(size_t)j * C + c] * (1 + 1e-6) * 1e-6;
+    double g00 = 0, g10 = 0, g11 = 0, g20 = 0, g21 = 0, g22 = 0;
+    for (int k = 0; k < n_out; k++) {
+        const double base = scratch[(size_t)k * C + c];
+        const double x0 = (scratch[plane + (size_t)k * C + c] - base) / den[0];
+        const double x1 = (scratch[2 * plane + (size_t)k * C + c] - base) / den[1];
+        const double x2 = (scratch[3 * plane + (size_t)k * C + c] - base) / den[2];
+        g00 += x0 * x0; g10 += x1 * x0; g11 += x1 * x1; g20 += x2 * x0; g21 += x2 * x1; g22 += x2 * x2;
+    }
+    // Cholesky G = R R^T, then G^-1 = R^-T R^-1; V = s2 G^-1; L = chol(V)
+    const double s2 = S.sigma2[c];
+    double r00 = sqrt(g00), r10 = g10 / r00, r20 = g20 / r00;
+    double r11 = sqrt(g11 - r10 * r10), r21 = (g21 - r20 * r10) / r11;
+    double r22 = sqrt(g22 - r20 * r20 - r21 * r21);
+    // W = R^-1 (lower)
+    double w00 = 1 / r00, w11 = 1 / r11, w22 = 1 / r22;
+    double w10 = -r10 * w00 * w11, w21 = -r21 * w11 * w22;
+    double w20 = -(r20 * w00 + r21 * w10) * w22;
+    // V = s2 * W^T W
+    double v00 = s2 * (w00 * w00 + w10 * w10 + w20 * w20);
+    double v10 = s2 * (w10 * w11 + w20 * w21);
+    double v11 = s2 * (w11 * w11 + w21 * w21);
+    double v20 = s2 * (w20 * w22);
+    double v21 = s2 * (w21 * w22);
+    double v22 = s2 * (w22 * w22);
+    double l00 = sqrt(v00), l10 = v10 / l00, l20 = v20 / l00;
+    double l11 = sqrt(v11 - l10 * l10), l21 = (v21 - l20 * l10) / l11;
+    double l22 = sqrt(v22 - l20 * l20 - l21 * l21);
+    S.chol[0 * (size_t)C + c] = l00; S.chol[1 * (size_t)C + c] = l10; S.chol[2 * (size_t)C + c] = l11;
+    S.chol[3 * (size_t)C + c] = l20; S.chol[4 * (size_t)C + c] = l21; S.chol[5 * (size_t)C + c] = l22;
+}
+
+__global__ void fill_ring_kernel(int C, int W, SamplerDev S)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    // slot (iteration % W) holds the sample of that iteration; iteration 0 is the start value
+    S.ring[c] = S.q[c];
+}
+
+extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *data_dev, void *stream_)
+{
+    if (!s || !q0_dev || !data_dev) return set_err(RSFM_ERR_INVALID, "rsfm_init: NULL argument%s", "");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int d = s->cfg.n_params, C = s->C, n = s->cfg.n_out;
+    CUDA_TRY(cudaMemcpyAsync(s->d.q, q0_dev, sizeof(double) * d * (size_t)C, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d.data, data_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+    const size_t planes = (d == 1) ? 1 : (size_t)(1 + d);
+    if (!s->scratch) CUDA_TRY(cudaMalloc((void **)&s->scratch, sizeof(double) * planes * n * (size_t)C));
+    CUDA_TRY(cudaMemsetAsync(s->d.accepted, 0, sizeof(unsigned int) * C, stream));
+    CUDA_TRY(cudaMemsetAsync(s->d.status, 0, sizeof(int) * C, stream));
+    CUDA_TRY(cudaMemsetAsync(s->d.nrhs, 0, sizeof(unsigned long long) * C, stream));
+    CUDA_TRY(cudaMemsetAsync(s->d.nstep, 0, sizeof(unsigned long long) * C, stream));
+    CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * (d + tri(d)) * (size_t)C, stream));
+    const int block = pick_block(C), grid = (C + block - 1) / block;
+    const ModelK M = make_model(&s->cfg);
+    for (int pass = 0; pass <= d; pass++) {
+        if (d == 1)
+            rsf_init_kernel<1><<<grid, block, 0, stream>>>(M, C, pass, s->cfg.a, s->cfg.b, s->cfg.n_prior_len, s->d, s->scratch);
+        else
+            rsf_init_kernel<3><<<grid, block, 0, stream>>>(M, C, pass, s->cfg.a, s->cfg.b, s->cfg.n_prior_len, s->d, s->scratch);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (d == 3) {
+        rsf_init_finish_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, n, s->d, s->scratch);
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        fill_ring_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, s->cfg.adapt_interval, s->d);
+        CUDA_TRY(cudaGetLastError());
+    }
+    // the base trajectory is only needed during init; release it (it can be GBs)
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    cudaFree(s->scratch);
+    s->scratch = nullptr;
+    s->iteration = 0;
+    s->suff_count = 0;
+    s->initialised = 1;
+    return RSFM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fused MCMC iterations
+// ---------------------------------------------------------------------------
+struct RunArgs {
+    int n_iters;
+    long long iter0;
+    unsigned long long seed, chain_id0;
+    // outputs
+    double *samples;        // [n_iters][d][C]
+    double *sigma2_out;     // [n_iters][C]
+    unsigned char *accept;  // [n_iters][C]
+    double *draws;          // [n_iters][d+2][C]
+    // deterministic inputs
+    const double *proposals;  // [n_iters][d][C]
+    const double *uniforms;   // [n_iters][C]
+    const double *gammas;     // [n_iters][C]
+    int proposals_are_z;
+    int deterministic;
+    // config
+    double a0, b0, n0;
+    double lo[RSFM_MAX_PARAMS], hi[RSFM_MAX_PARAMS];
+    int adapt_mode, adapt_interval;
+};
+
+template <int D>
+__global__ void __launch_bounds__(128)
+rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
+{
+    __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    constexpr int T = D * (D + 1) / 2;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = c < C;
+    const int cc = active ? c : C - 1;
+    const size_t Cz = (size_t)C;
+
+    double q[D], L[T], sq[D], sqq[T];
+#pragma unroll
+    for (int j = 0; j < D; j++) { q[j] = S.q[j * Cz + cc]; sq[j] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < T; j++) { L[j] = S.chol[j * Cz + cc]; sqq[j] = 0.0; }
+    double ss = S.sse[cc], s2 = S.sigma2[cc];
+    unsigned int n_acc = 0;
+    unsigned long long nrhs = 0, nstep = 0;
+    int status = 0;
+    const unsigned long long gid = A.chain_id0 + (unsigned long long)cc;
+    const PhiloxKey key = philox_key(A.seed);
+    const double gshape = 0.5 * (A.n0 + (double)M.n_out);          // MCMC.py:158
+    SeriesStage series;
+    series.begin(s_tile, s_bar, S.data, M.n_out);
+
+    for (int it = 0; it < A.n_iters; it++) {
+        const unsigned int giter = (unsigned int)(A.iter0 + it);
+        // ---- proposal (MCMC.py:497) ----
+        double qn[D];
+        if (A.deterministic && !A.proposals_are_z) {
+#pragma unroll
+            for (int j = 0; j < D; j++) qn[j] = A.proposals[((size_t)it * D + j) * Cz + cc];
+        } else {
+            double z[D];
+            if (A.deterministic) {
+#pragma unroll
+                for (int j = 0; j < D; j++) z[j] = A.proposals[((size_t)it * D + j) * Cz + cc];
+            } else {
+                double z0, z1;
+                philox_normal2(key, gid, giter, 0u, z0, z1);
+                z[0] = z0;
+                if (D > 1) z[1] = z1;
+                if (D > 2) { philox_normal2(key, gid, giter, 1u, z0, z1); z[2] = z0; }
+            }
+            if (D == 1) {
+                qn[0] = q[0] + sqrt(L[0]) * z[0];       // L[0] is the proposal variance for d = 1
+            } else {
+                qn[0] = q[0] + L[0] * z[0];
+                qn[1] = q[1] + L[1] * z[0] + L[2] * z[1];
+                qn[2] = q[2] + L[3] * z[0] + L[4] * z[1] + L[5] * z[2];
+            }
+        }
+        // ---- strict box prior (MCMC.py:318-320) ----
+        bool inb = true;
+#pragma unroll
+        for (int j = 0; j < D; j++) inb = inb && (qn[j] > A.lo[j]) && (qn[j] < A.hi[j]);
+        const bool solve = active && inb;
+        // ---- forward solve + SSE (MCMC.py:324, 381-387) ----
+        const double pa = (D == 3) ? qn[0] : A.a0;
+        const double pb = (D == 3) ? qn[1] : A.b0;
+        const double pdc = solve ? qn[D - 1] : q[D - 1];
+        series.start_solve();
+        SolveOut o = rsf_solve(M, solve ? pa : ((D == 3) ? q[0] : A.a0), solve ? pb : ((D == 3) ? q[1] : A.b0), pdc,
+                               solve, series, nullptr, nullptr, Cz, 1.0, nullptr);
+        // ---- accept / reject (MCMC.py:327-331) ----
+        bool acc = false;
+        double u = nan("");
+        if (solve) {
+            nrhs += o.nrhs; nstep += o.nstep; status |= o.status;
+            if (A.deterministic) u = A.uniforms[(size_t)it * Cz + cc];
+            else u = philox_uniform(key, gid, giter, 2u);
+            double la = 0.5 * (ss - o.sse) / s2;
+            if (la > 0.0) la = 0.0;
+            acc = la > log(u);
+            if (acc) {
+#pragma unroll
+                for (int j = 0; j < D; j++) q[j] = qn[j];
+                ss = o.sse;
+                n_acc++;
+            }
+        }
+        // ---- sigma^2 Gibbs draw (MCMC.py:158-160) ----
+        double g0;
+        if (A.deterministic) g0 = A.gammas[(size_t)it * Cz + cc];
+        else g0 = philox_gamma(key, gid, giter, gshape);
+        {
+            const double bval = 0.5 * (A.n0 * s2 + ss);
+            const double scale = 1.0 / bval;
+            s2 = 1.0 / (g0 * scale);
+        }
+        // ---- outputs ----
+        if (active) {
+            if (A.samples) {
+#pragma unroll
+                for (int j = 0; j < D; j++) A.samples[((size_t)it * D + j) * Cz + c] = q[j];
+            }
+            if (A.sigma2_out) A.sigma2_out[(size_t)it * Cz + c] = s2;
+            if (A.accept) A.accept[(size_t)it * Cz + c] = acc ? 1 : 0;
+            if (A.draws) {
+#pragma unroll
+                for (int j = 0; j < D; j++) A.draws[((size_t)it * (D + 2) + j) * Cz + c] = qn[j];
+                A.draws[((size_t)it * (D + 2) + D) * Cz + c] = u;
+                A.draws[((size_t)it * (D + 2) + D + 1) * Cz + c] = g0;
+            }
+        }
+        // ---- adaptation ----
+        if (A.adapt_mode == RSFM_ADAPT_POOLED) {
+#pragma unroll
+            for (int j = 0; j < D; j++) sq[j] += q[j];
+            int t = 0;
+#pragma unroll
+            for (int i = 0; i < D; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) sqq[t++] += q[i] * q[j];
+        }
+        if (D == 1 && A.adapt_mode == RSFM_ADAPT_COMPAT && active) {
+            // MCMC.py:523-527 + 200-204: V <- chol(2.38^2/len(keys) * cov(last W samples)), W = adapt_interval,
+            // len(qpriors.keys()) = 2 for the dict form.  The Cholesky FACTOR is then used as a covariance (q3).
+            const int W = A.adapt_interval;
+            const long long gi = A.iter0 + it + 1;              // chain index of the sample just appended
+            S.ring[(size_t)(gi % W) * Cz + c] = q[0];
+            if (gi % W == 0) {
+                double mean = 0.0;
+                for (int w = 1; w <= W; w++) mean += S.ring[(size_t)((gi - W + w) % W) * Cz + c];
+                mean /= W;
+                double v = 0.0;
+                for (int w = 1; w <= W; w++) {
+                    const double dlt = S.ring[(size_t)((gi - W + w) % W) * Cz + c] - mean;
+                    v += dlt * dlt;
+                }
+                v /= (W - 1);
+                const double vnew = 2.38 * 2.38 / 2.0 * v;
+                if (vnew > 0.0) L[0] = sqrt(vnew);             // cov = 0 -> cholesky raises -> unchanged (q4)
+            }
+        }
+    }
+
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < D; j++) S.q[j * Cz + c] = q[j];
+#pragma unroll
+        for (int j = 0; j < T; j++) S.chol[j * Cz + c] = L[j];
+        S.sse[c] = ss; S.sigma2[c] = s2;
+        S.accepted[c] += n_acc;
+        S.nrhs[c] += nrhs; S.nstep[c] += nstep; S.status[c] |= status;
+        if (A.adapt_mode == RSFM_ADAPT_POOLED) {
+#pragma unroll
+            for (int j = 0; j < D; j++) S.suff[j * Cz + c] += sq[j];
+#pragma unroll
+            for (int j = 0; j < T; j++) S.suff[(D + j) * Cz + c] += sqq[j];
+        }
+    }
+}
+
+static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
+{
+    if (!s->initialised) return set_err(RSFM_ERR_STATE, "sampler used before rsfm_init%s", "");
+    if (A.n_iters < 1) return set_err(RSFM_ERR_INVALID, "n_iters < 1%s", "");
+    const int C = s->C, block = pick_block(C), grid = (C + block - 1) / block;
+    A.iter0 = s->iteration; A.seed = s->seed; A.chain_id0 = s->chain_id0;
+    A.a0 = s->cfg.a; A.b0 = s->cfg.b; A.n0 = s->cfg.n0;
+    for (int i = 0; i < RSFM_MAX_PARAMS; i++) { A.lo[i] = s->cfg.lo[i]; A.hi[i] = s->cfg.hi[i]; }
+    A.adapt_mode = s->cfg.adapt_mode; A.adapt_interval = s->cfg.adapt_interval;
+    const ModelK M = make_model(&s->cfg);
+    if (s->cfg.n_params == 1) rsf_mcmc_kernel<1><<<grid, block, 0, stream>>>(M, C, s->d, A);
+    else rsf_mcmc_kernel<3><<<grid, block, 0, stream>>>(M, C, s->d, A);
+    CUDA_TRY(cudaGetLastError());
+    s->iteration += A.n_iters;
+    if (s->cfg.adapt_mode == RSFM_ADAPT_POOLED) s->suff_count += A.n_iters;
+    return RSFM_OK;
+}
+
+extern "C" int rsfm_run(rsfm_sampler *s, int32_t n_iters, double *samples_out_dev, double *sigma2_out_dev,
+                        uint8_t *accept_out_dev, double *draws_out_dev, void *stream)
+{
+    if (!s) return set_err(RSFM_ERR_INVALID, "rsfm_run: NULL sampler%s", "");
+    RunArgs A;
+    memset(&A, 0, sizeof(A));
+    A.n_iters = n_iters; A.samples = samples_out_dev; A.sigma2_out = sigma2_out_dev; A.accept = accept_out_dev;
+    A.draws = draws_out_dev; A.deterministic = 0;
+    return launch_run(s, A, (cudaStream_t)stream);
+}
+
+extern "C" int rsfm_run_deterministic(rsfm_sampler *s, int32_t n_iters, const double *proposals_dev,
+                                      int32_t proposals_are_z, const double *uniforms_dev, const double *gammas_dev,
+                                      double *samples_out_dev, double *sigma2_out_dev, uint8_t *accept_out_dev,
+                                      void *stream)
+{
+    if (!s || !proposals_dev || !uniforms_dev || !gammas_dev)
+        return set_err(RSFM_ERR_INVALID, "rsfm_run_deterministic: NULL argument%s", "");
+    RunArgs A;
+    memset(&A, 0, sizeof(A));
+    A.n_iters = n_iters; A.samples = samples_out_dev; A.sigma2_out = sigma2_out_dev; A.accept = accept_out_dev;
+    A.proposals = proposals_dev; A.uniforms = uniforms_dev; A.gammas = gammas_dev;
+    A.proposals_are_z = proposals_are_z; A.deterministic = 1;
+    return launch_run(s, A, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// state access
+// ---------------------------------------------------------------------------
+extern "C" int rsfm_get_state(rsfm_sampler *s, double *q_dev, double *sse_dev, double *sigma2_dev, double *chol_dev,
+                              uint32_t *accepted_dev, int32_t *status_dev, uint64_t *nrhs_dev, uint64_t *nstep_dev,
+                              void *stream_)
+{
+    if (!s) return set_err(RSFM_ERR_INVALID, "rsfm_get_state: NULL sampler%s", "");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const size_t C = s->C; const int d = s->cfg.n_params;
+    if (q_dev) CUDA_TRY(cudaMemcpyAsync(q_dev, s->d.q, sizeof(double) * d * C, cudaMemcpyDeviceToDevice, st));
+    if (sse_dev) CUDA_TRY(cudaMemcpyAsync(sse_dev, s->d.sse, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
+    if (sigma2_dev) CUDA_TRY(cudaMemcpyAsync(sigma2_dev, s->d.sigma2, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
+    if (chol_dev) CUDA_TRY(cudaMemcpyAsync(chol_dev, s->d.chol, sizeof(double) * tri(d) * C, cudaMemcpyDeviceToDevice, st));
+    if (accepted_dev) CUDA_TRY(cudaMemcpyAsync(accepted_dev, s->d.accepted, sizeof(uint32_t) * C, cudaMemcpyDeviceToDevice, st));
+    if (status_dev) CUDA_TRY(cudaMemcpyAsync(status_dev, s->d.status, sizeof(int32_t) * C, cudaMemcpyDeviceToDevice, st));
+    if (nrhs_dev) CUDA_TRY(cudaMemcpyAsync(nrhs_dev, s->d.nrhs, sizeof(uint64_t) * C, cudaMemcpyDeviceToDevice, st));
+    if (nstep_dev) CUDA_TRY(cudaMemcpyAsync(nstep_dev, s->d.nstep, sizeof(uint64_t) * C, cudaMemcpyDeviceToDevice, st));
+    return RSFM_OK;
+}
+
+extern "C" int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double *sse_dev, const double *sigma2_dev,
+                              const double *chol_dev, int64_t iteration, void *stream_)
+{
+    if (!s) return set_err(RSFM_ERR_INVALID, "rsfm_set_state: NULL sampler%s", "");
+    if (!s->initialised) return set_err(RSFM_ERR_STATE, "rsfm_set_state before rsfm_init (the data series lives in the sampler)%s", "");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const size_t C = s->C; const int d = s->cfg.n_params;
+    if (q_dev) CUDA_TRY(cudaMemcpyAsync(s->d.q, q_dev, sizeof(double) * d * C, cudaMemcpyDeviceToDevice, st));
+    if (sse_dev) CUDA_TRY(cudaMemcpyAsync(s->d.sse, sse_dev, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
+    if (sigma2_dev) CUDA_TRY(cudaMemcpyAsync(s->d.sigma2, sigma2_dev, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
+    if (chol_dev) CUDA_TRY(cudaMemcpyAsync(s->d.chol, chol_dev, sizeof(double) * tri(d) * C, cudaMemcpyDeviceToDevice, st));
+    if (iteration >= 0) s->iteration = iteration;
+    return RSFM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pooled sufficient statistics: sum over chains with warp shuffles
+// ---------------------------------------------------------------------------
+__global__ void suffstats_kernel(int C, int rows, const double *__restrict__ suff, double *__restrict__ out)
+{
+    // one block per row; grid-stride not needed: blockDim = 1024
+    const int r = blockIdx.x;
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) acc += suff[(size_t)r * C + c];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL_MASK, acc, o);
+    __shared__ double warp_sum[32];
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? warp_sum[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL_MASK, v, o);
+        if (threadIdx.x == 0) out[r] = v;
+    }
+    (void)rows;
+}
+
+extern "C" int rsfm_get_suffstats(rsfm_sampler *s, double *out_dev, int32_t reset, void *stream_)
+{
+    if (!s || !out_dev) return set_err(RSFM_ERR_INVALID, "rsfm_get_suffstats: NULL argument%s", "");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int d = s->cfg.n_params, rows = d + tri(d);
+    suffstats_kernel<<<rows, 1024, 0, st>>>(s->C, rows, s->d.suff, out_dev + 1);
+    CUDA_TRY(cudaGetLastError());
+    const double n = (double)s->suff_count * (double)s->C;
+    CUDA_TRY(cudaMemcpyAsync(out_dev, &n, sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));      // `n` lives on this stack frame
+    if (reset) {
+        CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * rows * (size_t)s->C, st));
+        s->suff_count = 0;
+    }
+    return RSFM_OK;
+}
+
+__global__ void broadcast_chol_kernel(int C, int T, const double *__restrict__ src, double *__restrict__ chol)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    for (int j = 0; j < T; j++) chol[(size_t)j * C + c] = src[j];
+}
+
+extern "C" int rsfm_set_proposal_chol(rsfm_sampler *s, const double *chol_host, void *stream_)
+{
+    if (!s || !chol_host) return set_err(RSFM_ERR_INVALID, "rsfm_set_proposal_chol: NULL argument%s", "");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int T = tri(s->cfg.n_params);
+    CUDA_TRY(cudaMemcpyAsync(s->reduce_out, chol_host, sizeof(double) * T, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    broadcast_chol_kernel<<<(s->C + 255) / 256, 256, 0, st>>>(s->C, T, s->reduce_out, s->d.chol);
+    CUDA_TRY(cudaGetLastError());
+    return RSFM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// per-chain diagnostics: mean, variance, ESS (Geyer initial positive sequence)
+// ---------------------------------------------------------------------------
+__global__ void chain_diag_kernel(const double *__restrict__ x, int n, int d, int C, int p, int max_lag,
+                                  double *__restrict__ mean_out, double *__restrict__ var_out,
+                                  double *__restrict__ ess_out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const size_t stride = (size_t)d * C;
+    const double *xc = x + (size_t)p * C + c;
+    double mean = 0.0;
+    for (int i = 0; i < n; i++) mean += xc[i * stride];
+    mean /= n;
+    double c0 = 0.0;
+    for (int i = 0; i < n; i++) { const double e = xc[i * stride] - mean; c0 += e * e; }
+    if (mean_out) mean_out[c] = mean;
+    if (var_out) var_out[c] = n > 1 ? c0 / (n - 1) : 0.0;
+    if (!ess_out) return;
+    if (!(c0 > 0.0)) { ess_out[c] = (double)n; return; }      // constant chain: no information, report n
+    // rho_t = c_t / c_0 with c_t = sum_{i<n-t} (x_i - m)(x_{i+t} - m);  tau = -1 + 2 sum_{pairs} P_k,
+    // P_k = rho_{2k} + rho_{2k+1}, truncated at the first non-positive pair and made monotone.
+    double tau = 0.0, prev_pair = 1e300;
+    const int L = max_lag < n ? max_lag : n - 1;
+    for (int t = 0; t + 1 <= L; t += 2) {
+        double ca = 0.0, cb = 0.0;
+        for (int i = 0; i + t < n; i++) {
+            const double ei = xc[i * stride] - mean;
+            ca += ei * (xc[(i + t) * stride] - mean);
+            if (i + t + 1 < n) cb += ei * (xc[(i + t + 1) * stride] - mean);
+        }
+        double pair = (ca + cb) / c0;
+        if (pair <= 0.0) break;
+        if (pair > prev_pair) pair = prev_pair;
+        prev_pair = pair;
+        tau += 2.0 * pair;
+    }
+    tau -= 1.0;
+    if (tau < 1.0 / n) tau = 1.0 / n;
+    ess_out[c] = n / tau;
+}
+
+extern "C" int rsfm_chain_diagnostics(const double *samples_dev, int32_t n, int32_t d, int32_t C, int32_t p,
+                                      int32_t max_lag, double *mean_dev, double *var_dev, double *ess_dev,
+                                      void *stream)
+{
+    if (!samples_dev || n < 2 || d < 1 || C < 1 || p < 0 || p >= d)
+        return set_err(RSFM_ERR_INVALID, "rsfm_chain_diagnostics: bad argument%s", "");
+    int rc = require_device();
+    if (rc) return rc;
+    chain_diag_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(samples_dev, n, d, C, p, max_lag, mean_dev,
+                                                                          var_dev, ess_dev);
+    CUDA_TRY(cudaGetLastError());
+    return RSFM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// FP64 peak: 8 independent DFMA chains per thread, all SMs full
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double seed, double *sink)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 0.999999, b = 1e-9;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+        }
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 12345.678) sink[0] = r;     // never true; keeps the chains alive
+}
+
+extern "C" int rsfm_measure_fp64_peak(double millis, double *flops_out)
+{
+    if (!flops_out) return set_err(RSFM_ERR_INVALID, "rsfm_measure_fp64_peak: NULL%s", "");
+    int rc = require_device();
+    if (rc) return rc;
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *sink = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int grid = sms * 8, block = 256;
+    int iters = 2000;
+    float ms = 0.f;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        dfma_peak_kernel<<<grid, block>>>(iters, 1.0, sink);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)grid * (double)block / (ms * 1e-3);
+        if (rep > 0 && flops > best) best = flops;
+        if (ms < millis) iters = (int)fmin(2.0e6, iters * fmax(1.5, millis / fmax(ms, 1e-3)));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *flops_out = best;
+    return RSFM_OK;
+}

@@ -1,0 +1,308 @@
+"""``MCMC`` -- drop-in for the reference Metropolis sampler, fused on B200.
+
+Mirrors the reference class (MCMC.py:4-544): same constructor arguments, the same
+attributes after ``sample()`` (``std2``, ``Vstart``, ``nburn`` ...), the same return
+shape ``(d, nsamples + 1 - nburn)`` and the same per-iteration semantics (SURVEY.md
+Appendix A), including the quirks that depend on the prior container type:
+
+  * ``["Uniform", lo, hi]`` (main.py:54): ``len(qpriors) = 3`` degrees-of-freedom
+    correction (q5) and NO adaptation, because ``qpriors.keys()`` raises inside a
+    bare ``except`` (q2);
+  * ``{1: lo, 2: hi}`` (MCMC.py:38): ``len = 2`` and the per-chain, last-10-samples,
+    Cholesky-factor-used-as-covariance update of MCMC.py:200-204 (q3).
+
+The loop itself (propose, bounds test, forward solve, SSE, accept, sigma^2 draw,
+adaptation) runs inside one CUDA kernel (``rsf_mcmc_kernel`` in librsfm) for all
+chains and all iterations; nothing is sampled or integrated on the CPU.
+
+Extensions (keyword-only; defaults reproduce the reference): ``n_chains``,
+``seed``, ``device``, ``param_names`` (("Dc",) or ("a", "b", "Dc")), ``bounds``,
+``deterministic_inputs``, ``compat_adapt``, ``adapt`` ("pooled" = Haario-style
+covariance pooled over chains and ranks), ``shard`` (split chains over
+torch.distributed ranks).
+"""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _lib
+from .sharding import ChainShard, all_reduce_sum_
+
+
+class MCMC:
+    def __init__(self, model, data, dc_true, qpriors, qstart, nsamples=100, lstm_model={},
+                 adapt_interval=10, verbose=True, *, n_chains=1, seed=None, device=None,
+                 param_names=("Dc",), bounds=None, deterministic_inputs=None, compat_adapt=None,
+                 adapt=None, adapt_start=100, shard=False, keep_on_device=False):
+        # reference attributes, MCMC.py:88-99
+        self.model = model
+        self.qstart = qstart
+        self.qpriors = qpriors
+        self.nsamples = nsamples
+        self.nburn = int(nsamples / 2)
+        self.verbose = verbose
+        self.adapt_interval = adapt_interval
+        self.data = data
+        self.lstm_model = lstm_model
+        self.n0 = 0.01
+        self.qstart_limits = np.array([[self.qpriors[1], self.qpriors[2]]])
+        self.dc_true = dc_true
+        # extensions
+        self.n_chains = int(n_chains)
+        self.seed = seed
+        self.device = device
+        self.param_names = tuple(param_names)
+        self.bounds = bounds
+        self.deterministic_inputs = deterministic_inputs
+        self.adapt = adapt
+        self.adapt_start = int(adapt_start)
+        self.shard = bool(shard)
+        self.keep_on_device = bool(keep_on_device)
+        if self.param_names not in (("Dc",), ("a", "b", "Dc")):
+            raise ValueError("param_names must be ('Dc',) or ('a', 'b', 'Dc')")
+        if compat_adapt is None:
+            # reference behaviour follows the container type of qpriors (q2 / q3)
+            compat_adapt = hasattr(qpriors, "keys") and adapt is None
+        self.compat_adapt = bool(compat_adapt)
+        if self.compat_adapt and len(self.param_names) != 1:
+            raise ValueError("compat_adapt reproduces the reference's d = 1 update only")
+        if adapt not in (None, "pooled"):
+            raise ValueError("adapt must be None or 'pooled'")
+        # results
+        self.std2 = None
+        self.Vstart = None
+        self.acceptance_ratio = None
+        self.samples_device = None
+        self.stats = {}
+
+    # ------------------------------------------------------------------
+    def _bounds(self, d):
+        if self.bounds is not None:
+            b = np.asarray(self.bounds, dtype=np.float64).reshape(d, 2)
+            return b[:, 0].copy(), b[:, 1].copy()
+        # the reference has ONE shared bound pair (MCMC.py:98, q10)
+        lo = np.full(d, float(self.qpriors[1]))
+        hi = np.full(d, float(self.qpriors[2]))
+        return lo, hi
+
+    def _start_values(self, torch, dev, d, shard):
+        """q0 as a [d, C_local] device tensor from a scalar, [d], [C] or [C, d] qstart."""
+        q = np.asarray(self.qstart, dtype=np.float64)
+        cg = self.n_chains
+        if q.ndim == 0:
+            q0 = np.full((d, cg), float(q))
+        elif q.ndim == 1 and q.size == d and (d > 1 or cg == 1):
+            q0 = np.repeat(q.reshape(d, 1), cg, axis=1)
+        elif q.ndim == 1 and d == 1 and q.size == cg:
+            q0 = q.reshape(1, cg)
+        elif q.ndim == 2 and q.shape == (cg, d):
+            q0 = np.ascontiguousarray(q.T)
+        else:
+            raise ValueError(f"qstart of shape {q.shape} does not match d = {d}, n_chains = {cg}")
+        q0 = q0[:, shard.start:shard.stop]
+        return torch.from_numpy(np.ascontiguousarray(q0)).to(dev)
+
+    # ------------------------------------------------------------------
+    def sample(self, MAKE_ANIMATIONS=False):
+        """Run the chains.  Returns ``qparams[:, nburn:]`` like MCMC.py:544.
+
+        Shape ``(d, nsamples + 1 - nburn)`` for one chain, ``(n_chains_local, d,
+        nsamples + 1 - nburn)`` otherwise.  ``MAKE_ANIMATIONS`` (matplotlib/ffmpeg
+        movie, MCMC.py:471-492) is outside the scope of this package and ignored.
+        """
+        if self.lstm_model:
+            raise NotImplementedError("the reduced-order-model branch (MCMC.py:124-125) is dead code in the "
+                                      "reference (no such attribute exists) and is not provided")
+        if not hasattr(self.model, "to_cfg"):
+            raise TypeError("model must be a bayesian-markov-chain-monte-carlo_b200 RateStateModel: the forward "
+                            "solve runs inside the CUDA kernel, a Python evaluate() cannot be called from it")
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        dev = torch.device(self.device) if self.device is not None else self.model._device(torch)
+        d = len(self.param_names)
+        shard = ChainShard.for_current_rank(self.n_chains) if self.shard else ChainShard(0, self.n_chains, self.n_chains)
+        cl = shard.count
+        n_out = self.model.num_outputs()
+        data = np.ascontiguousarray(np.asarray(self.data, dtype=np.float64).reshape(-1))
+        if data.size != n_out:
+            raise ValueError(f"data has {data.size} points, the model produces {n_out}")
+
+        cfg = self.model.to_cfg()
+        cfg.n_params = d
+        lo, hi = self._bounds(d)
+        for j in range(d):
+            cfg.lo[j], cfg.hi[j] = lo[j], hi[j]
+        cfg.n0 = float(self.n0)
+        cfg.n_prior_len = len(self.qpriors)                       # MCMC.py:261 (q5)
+        cfg.adapt_interval = int(self.adapt_interval)
+        cfg.adapt_mode = (_lib.ADAPT_COMPAT if self.compat_adapt else
+                          _lib.ADAPT_POOLED if self.adapt == "pooled" else _lib.ADAPT_NONE)
+        seed = self.seed
+        if seed is None:
+            # the reference draws from the global NumPy generator; derive the Philox key from it so
+            # that np.random.seed(...) before the call makes runs reproducible here too
+            s = np.random.randint(0, 2 ** 31 - 1, size=2)
+            seed = (int(s[0]) << 31) | int(s[1])
+        self.seed_used = int(seed)
+
+        t_begin = time.perf_counter()
+        with torch.cuda.device(dev):
+            stream = _lib.current_stream(torch, dev)
+            data_t = torch.from_numpy(data).to(dev)
+            q0 = self._start_values(torch, dev, d, shard)
+            handle = lib.rsfm_create(C.byref(cfg), cl, C.c_uint64(self.seed_used), C.c_uint64(shard.start))
+            if not handle:
+                _lib.check(-1, "rsfm_create")
+            try:
+                _lib.check(lib.rsfm_init(handle, _lib.ptr(q0), _lib.ptr(data_t), stream), "rsfm_init")
+                s2_0 = torch.empty(cl, dtype=torch.float64, device=dev)
+                chol0 = torch.empty((d * (d + 1) // 2, cl), dtype=torch.float64, device=dev)
+                _lib.check(lib.rsfm_get_state(handle, None, None, _lib.ptr(s2_0), _lib.ptr(chol0), None, None,
+                                              None, None, stream), "rsfm_get_state")
+                ns = int(self.nsamples)
+                chain = torch.empty((ns + 1, d, cl), dtype=torch.float64, device=dev)
+                std2 = torch.empty((ns + 1, cl), dtype=torch.float64, device=dev)
+                accept = torch.empty((ns, cl), dtype=torch.uint8, device=dev)
+                want_draws = cl == 1 and self.deterministic_inputs is None
+                draws = torch.empty((ns, d + 2, cl), dtype=torch.float64, device=dev) if want_draws else None
+                chain[0] = q0
+                std2[0] = s2_0
+                if self.deterministic_inputs is not None:
+                    self._run_deterministic(torch, lib, handle, dev, d, cl, ns, chain, std2, accept, stream)
+                elif cfg.adapt_mode == _lib.ADAPT_POOLED:
+                    self._run_pooled(torch, lib, handle, dev, d, cl, ns, chain, std2, accept, stream)
+                else:
+                    _lib.check(lib.rsfm_run(handle, ns, _lib.ptr(chain[1:]), _lib.ptr(std2[1:]), _lib.ptr(accept),
+                                            _lib.ptr(draws), stream), "rsfm_run")
+                acc_cnt = torch.empty(cl, dtype=torch.int32, device=dev)
+                status = torch.empty(cl, dtype=torch.int32, device=dev)
+                nrhs = torch.empty(cl, dtype=torch.int64, device=dev)
+                nstep = torch.empty(cl, dtype=torch.int64, device=dev)
+                _lib.check(lib.rsfm_get_state(handle, None, None, None, None, _lib.ptr(acc_cnt), _lib.ptr(status),
+                                              _lib.ptr(nrhs), _lib.ptr(nstep), stream), "rsfm_get_state")
+                torch.cuda.synchronize(dev)
+            finally:
+                lib.rsfm_destroy(handle)
+        elapsed = time.perf_counter() - t_begin
+
+        nb = self.nburn
+        self.samples_device = chain                       # [nsamples+1, d, C_local], start value included
+        self.std2_device = std2
+        self.accept_device = accept
+        in_bounds = None
+        # ---- reference-shaped host outputs (device -> host copy of the results) ----
+        chain_h = chain[nb:].permute(2, 1, 0).contiguous().cpu().numpy()      # [C, d, n]
+        std2_h = std2[nb:].t().contiguous().cpu().numpy()                      # [C, n]
+        accept_h = accept.t().contiguous().cpu().numpy()                       # [C, ns]
+        self.Vstart = self._vstart_host(chol0, d)
+        self.status = status.cpu().numpy()
+        n_acc = acc_cnt.cpu().numpy().astype(np.int64)
+        self.acceptance_ratio = n_acc / float(self.nsamples)
+        self.stats = {
+            "elapsed_s": elapsed, "n_chains_local": cl, "chain_id0": shard.start,
+            "nrhs": int(nrhs.sum().item()), "nstep": int(nstep.sum().item()),
+            "failed_chains": int((status != 0).sum().item()),
+        }
+        if cl == 1:
+            if draws is not None:
+                dr = draws[:, :, 0].cpu().numpy()
+                in_bounds = ~np.isnan(dr[:, d])
+                evaluated = dr[in_bounds, :d]
+                # the reference leaves model.Dc at the last evaluated proposal, a 1-element array (q6)
+                last = evaluated[-1, d - 1] if evaluated.shape[0] else float(np.ravel(self.qstart)[0])
+                self.model.Dc = np.array([last])
+                if self.verbose:
+                    for i in range(self.nsamples):               # MCMC.py:503-504
+                        print(i, bool(accept_h[0, i]))
+                        print("Generated Sample ---- ", dr[i, d - 1] if d == 1 else dr[i, :d])
+            if self.verbose:
+                print("acceptance ratio:", self.acceptance_ratio[0])      # MCMC.py:530
+            self.std2 = std2_h[0]                                          # MCMC.py:533
+            self.accepts = accept_h[0]
+            return chain_h[0]                                              # (d, nsamples+1-nburn), MCMC.py:544
+        if self.verbose:
+            print("acceptance ratio:", float(self.acceptance_ratio.mean()))
+        self.std2 = std2_h
+        self.accepts = accept_h
+        return chain_h
+
+    # ------------------------------------------------------------------
+    @staticmethod
+    def _vstart_host(chol0, d):
+        c = chol0[:, 0].cpu().numpy()
+        if d == 1:
+            return np.array([[c[0]]])                            # (1, 1) like MCMC.py:266
+        low = np.zeros((d, d))
+        low[np.tril_indices(d)] = c
+        return low @ low.T
+
+    def _run_deterministic(self, torch, lib, handle, dev, d, cl, ns, chain, std2, accept, stream):
+        """Host-supplied randomness: step-for-step replay."""
+        di = self.deterministic_inputs
+
+        def dev3(x, shape):
+            t = torch.as_tensor(np.asarray(x, dtype=np.float64)).reshape(shape).to(dev).contiguous()
+            return t
+
+        key = "z" if "z" in di else "proposals"
+        prop = dev3(di[key], (ns, d, cl))
+        uni = dev3(np.nan_to_num(np.asarray(di["uniforms"], dtype=np.float64), nan=0.5), (ns, cl))
+        gam = dev3(di["gammas"], (ns, cl))
+        _lib.check(lib.rsfm_run_deterministic(handle, ns, _lib.ptr(prop), 1 if key == "z" else 0, _lib.ptr(uni),
+                                              _lib.ptr(gam), _lib.ptr(chain[1:]), _lib.ptr(std2[1:]),
+                                              _lib.ptr(accept), stream), "rsfm_run_deterministic")
+        torch.cuda.synchronize(dev)
+
+    def _run_pooled(self, torch, lib, handle, dev, d, cl, ns, chain, std2, accept, stream):
+        """Haario-style adaptive Metropolis with the covariance pooled over all chains of all ranks.
+
+        Every ``adapt_interval`` iterations (after ``adapt_start``): local sufficient statistics
+        (n, sum q, sum qq^T) -> one small all-reduce -> every rank forms the same
+        (2.38^2/d) * cov and installs its Cholesky factor.
+        """
+        from .adaptation import proposal_from_suffstats
+        tri = d * (d + 1) // 2
+        suff = torch.zeros(1 + d + tri, dtype=torch.float64, device=dev)
+        total = torch.zeros_like(suff)
+        done = 0
+        w = int(self.adapt_interval)
+        self.adapt_history = []
+        while done < ns:
+            k = min(w, ns - done)
+            _lib.check(lib.rsfm_run(handle, k, _lib.ptr(chain[1 + done:]), _lib.ptr(std2[1 + done:]),
+                                    _lib.ptr(accept[done:]), None, stream), "rsfm_run")
+            done += k
+            _lib.check(lib.rsfm_get_suffstats(handle, _lib.ptr(suff), 1, stream), "rsfm_get_suffstats")
+            all_reduce_sum_(suff)
+            if done > self.adapt_start // 2:          # discard the earliest draws from the pooled moments
+                total += suff
+            if done >= self.adapt_start and done < ns and total[0].item() > d + 1:
+                fac = proposal_from_suffstats(total.cpu().numpy(), d)
+                if fac is not None:
+                    arr = (C.c_double * tri)(*fac)
+                    _lib.check(lib.rsfm_set_proposal_chol(handle, arr, stream), "rsfm_set_proposal_chol")
+                    self.adapt_history.append((done, fac.copy()))
+
+    # ------------------------------------------------------------------
+    def diagnostics(self, max_lag=None):
+        """Split-R-hat and bulk ESS of the post-burn-in draws, pooled over ranks."""
+        from .diagnostics import chain_diagnostics
+        if self.samples_device is None:
+            raise RuntimeError("call sample() first")
+        return chain_diagnostics(self.samples_device[self.nburn:], max_lag=max_lag)
+
+    def save_samples(self, filename):
+        """Write the post-burn-in samples in the reference's JSON ndarray format (json_save_load.py:37-38)."""
+        from .ndarray_json import save_object
+        if self.samples_device is None:
+            raise RuntimeError("call sample() first")
+        nb = self.nburn
+        obj = {
+            "param_names": list(self.param_names),
+            "samples": self.samples_device[nb:].permute(2, 1, 0).contiguous().cpu().numpy(),
+            "std2": self.std2_device[nb:].t().contiguous().cpu().numpy(),
+            "acceptance_ratio": np.asarray(self.acceptance_ratio, dtype=np.float64),
+            "nsamples": int(self.nsamples), "nburn": int(nb), "seed": int(self.seed_used),
+        }
+        save_object(obj, filename)

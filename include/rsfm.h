@@ -1,0 +1,172 @@
+/* rsfm.h -- C ABI of the B200 RSF-MCMC hot path (librsfm.so).
+ *
+ * The reference (SaumikDana/Bayesian-Markov-chain-Monte-Carlo) has no FFI layer:
+ * its boundary is two duck-typed Python protocols.  This
+ * header is what a Python facade binds with ctypes underneath those protocols;
+ * every entry point cites the reference code it replaces.  Plain pointers and
+ * sizes only: no torch types.  All `*_dev` pointers are CUDA device pointers
+ * owned by the caller; `stream` is a cudaStream_t passed as void*.  Functions
+ * return 0 on success and a negative rsfm_status on error, never throw, and do
+ * not synchronise the stream unless stated.
+ *
+ * Layouts are chain-minor ("SoA") so that one warp = 32 consecutive chains reads
+ * and writes 256 contiguous bytes:
+ *     params   [P][C]          q0, proposals  [d][C] or [n_iters][d][C]
+ *     series   [n_out][C]      (time-major acc output)
+ *     samples  [n_iters][d][C]
+ */
+#ifndef RSFM_H
+#define RSFM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSFM_ABI_VERSION 1
+#define RSFM_MAX_PARAMS 3
+
+typedef enum {
+    RSFM_OK = 0,
+    RSFM_ERR_INVALID = -1,     /* bad argument */
+    RSFM_ERR_CUDA = -2,        /* CUDA runtime error, see rsfm_last_error() */
+    RSFM_ERR_NO_DEVICE = -3,   /* no sm_100 device: there is NO CPU fallback */
+    RSFM_ERR_STATE = -4        /* sampler used before rsfm_init */
+} rsfm_status;
+
+/* load-point velocity */
+enum { RSFM_LOAD_SINE_DECAY = 0,   /* RateStateModel.py:327-329 (reference) */
+       RSFM_LOAD_VSTEP = 1 };      /* piecewise-constant extension */
+
+/* time-integration mode */
+enum { RSFM_INTEG_PARITY = 0,      /* fresh dop853 call + hinit per output interval:
+                                      scipy ode('dop853') as driven by RateStateModel.py:380-389 */
+       RSFM_INTEG_CARRY = 1 };     /* carry h and the FSAL stage across output points */
+
+/* proposal-covariance adaptation */
+enum { RSFM_ADAPT_NONE = 0,        /* list-typed priors: update silently dead (quirk q2) */
+       RSFM_ADAPT_COMPAT = 1,      /* dict-typed priors: MCMC.py:200-204 as written (quirk q3) */
+       RSFM_ADAPT_POOLED = 2 };    /* host-driven: rsfm_get_suffstats + rsfm_set_proposal_chol */
+
+/* per-chain solver status word ("flag, not hang") */
+enum { RSFM_CHAIN_OK = 0,
+       RSFM_CHAIN_NMAX = 2,        /* dop853 idid = -2, "larger nsteps is needed" (quirk q9) */
+       RSFM_CHAIN_HSMALL = 3,      /* dop853 idid = -3 */
+       RSFM_CHAIN_NONFINITE = 4 };
+
+/* Model + solver constants.  Defaults (rsfm_cfg_defaults) are the reference's
+ * RateStateModel.py:5-11,167-184 and the tolerances of :374. */
+typedef struct rsfm_cfg {
+    double  a, b, mu_ref, V_ref, k1;     /* :167-171; a, b are per-chain when sampled */
+    double  t_start, t_final;            /* :174-175 */
+    double  delta_t;                     /* :177, computed by the host exactly as the reference */
+    double  mu_t_zero;                   /* :180 */
+    double  vstep_period, vstep_factor;  /* RSFM_LOAD_VSTEP only */
+    double  rtol, atol;                  /* :374 */
+    double  n0;                          /* MCMC.py:97 */
+    double  lo[RSFM_MAX_PARAMS];         /* strict box prior, MCMC.py:98,318-320 */
+    double  hi[RSFM_MAX_PARAMS];
+    int32_t n_out;                       /* int(floor((t_final-t_start)/delta_t)), :358 (quirk q8) */
+    int32_t nmax;                        /* scipy nsteps (500) */
+    int32_t radiation_damping;           /* :183 */
+    int32_t loading;                     /* RSFM_LOAD_* */
+    int32_t integ_mode;                  /* RSFM_INTEG_* */
+    int32_t n_params;                    /* d: 1 = (Dc), 3 = (a, b, Dc) */
+    int32_t n_prior_len;                 /* len(qpriors): 3 list form, 2 dict form, MCMC.py:261 (q5) */
+    int32_t adapt_interval;              /* MCMC.py:58 */
+    int32_t adapt_mode;                  /* RSFM_ADAPT_* */
+    int32_t reserved;
+} rsfm_cfg;
+
+typedef struct rsfm_sampler rsfm_sampler;   /* opaque; owns per-chain device state */
+
+int          rsfm_abi_version(void);
+const char  *rsfm_last_error(void);
+void         rsfm_cfg_defaults(rsfm_cfg *cfg);
+
+/* Number of CUDA devices usable by this library (compute capability 10.x). */
+int          rsfm_device_count(void);
+
+/* Batched RateStateModel.evaluate() (RateStateModel.py:188-395) + optional SSE
+ * (MCMC.py:387).  dc_dev [C] is required; a_dev, b_dev [C] may be NULL (cfg->a,
+ * cfg->b are used).  Outputs, each optional (NULL to skip):
+ *   acc_out_dev [n_out][C]  backward-difference acceleration (:388)
+ *   t_out_dev   [n_out][C]  output times as accumulated by the solver (:384)
+ *   sse_out_dev [C]         sum_k (acc_k - data_k)^2, needs data_dev [n_out]
+ *   status_dev  [C]         RSFM_CHAIN_*
+ *   filled_dev  [C]         entries written before a failure (n_out when ok)
+ *   nrhs_dev, nstep_dev [C] executed RHS evaluations / attempted steps */
+int rsfm_forward_batch(const rsfm_cfg *cfg, int32_t C,
+                       const double *dc_dev, const double *a_dev, const double *b_dev,
+                       const double *data_dev,
+                       double *acc_out_dev, double *t_out_dev, double *sse_out_dev,
+                       int32_t *status_dev, int32_t *filled_dev,
+                       uint64_t *nrhs_dev, uint64_t *nstep_dev, void *stream);
+
+/* Sampler object = the state of C independent MCMC.sample() runs (MCMC.py:391-544).
+ * chain_id0 is the global id of local chain 0 (Philox key = seed, counter =
+ * global chain id, iteration, slot), so results do not depend on the sharding. */
+rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t seed, uint64_t chain_id0);
+void          rsfm_destroy(rsfm_sampler *s);
+
+/* compute_initial_covariance + first SSqcalc (MCMC.py:206-266, 464-468):
+ * sigma2_0 = SSE(q0)/(N - n_prior_len), Vstart = sigma2_0 (X'X)^-1 from forward
+ * differences with relative step 1e-6; proposal factor = chol(Vstart).
+ * q0_dev [d][C]; data_dev [n_out] is copied into the sampler. */
+int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *data_dev, void *stream);
+
+/* n_iters iterations of the loop MCMC.py:494-527 for every chain, one launch.
+ * Outputs (each optional): samples_out_dev [n_iters][d][C], sigma2_out_dev
+ * [n_iters][C], accept_out_dev [n_iters][C].  draws_out_dev, if not NULL, receives
+ * the random draws actually used, [n_iters][d+2][C] = (proposal[d], U, unit gamma),
+ * so that the CPU oracle can replay the chain (U is NaN when not drawn, q10). */
+int rsfm_run(rsfm_sampler *s, int32_t n_iters,
+             double *samples_out_dev, double *sigma2_out_dev, uint8_t *accept_out_dev,
+             double *draws_out_dev, void *stream);
+
+/* Same loop with host-supplied randomness:
+ * proposals_dev [n_iters][d][C] (absolute proposals, or standard normals z when
+ * proposals_are_z != 0: q' = q + L z), uniforms_dev [n_iters][C] (consumed only
+ * for in-bounds proposals), gammas_dev [n_iters][C] unit-scale Gamma((n0+N)/2). */
+int rsfm_run_deterministic(rsfm_sampler *s, int32_t n_iters,
+                           const double *proposals_dev, int32_t proposals_are_z,
+                           const double *uniforms_dev, const double *gammas_dev,
+                           double *samples_out_dev, double *sigma2_out_dev,
+                           uint8_t *accept_out_dev, void *stream);
+
+/* Per-chain state, for output, checkpoint/resume and tests.  Any pointer may be
+ * NULL.  q [d][C], sse [C], sigma2 [C], chol [d(d+1)/2][C] (row-major lower
+ * triangle; d = 1: the proposal VARIANCE as the reference stores it), accepted
+ * [C], status [C], nrhs/nstep [C] cumulative executed work. */
+int rsfm_get_state(rsfm_sampler *s, double *q_dev, double *sse_dev, double *sigma2_dev,
+                   double *chol_dev, uint32_t *accepted_dev, int32_t *status_dev,
+                   uint64_t *nrhs_dev, uint64_t *nstep_dev, void *stream);
+int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double *sse_dev,
+                   const double *sigma2_dev, const double *chol_dev, int64_t iteration,
+                   void *stream);
+int64_t rsfm_iteration(const rsfm_sampler *s);
+
+/* Pooled adaptation (extension): local sufficient
+ * statistics out_dev[1 + d + d(d+1)/2] = (n, sum q, sum q q^T lower) accumulated
+ * over all chains and iterations since the last reset; the caller all-reduces
+ * them over ranks (NCCL) and installs one common factor for every chain. */
+int rsfm_get_suffstats(rsfm_sampler *s, double *out_dev, int32_t reset, void *stream);
+int rsfm_set_proposal_chol(rsfm_sampler *s, const double *chol_host /* [d(d+1)/2] */, void *stream);
+
+/* Diagnostics over a samples buffer [n][d][C] (device): per-chain mean, variance
+ * (ddof 1) and autocovariance-based effective sample size (Geyer initial positive
+ * sequence, lags < max_lag), for parameter p.  Outputs [C] each, optional. */
+int rsfm_chain_diagnostics(const double *samples_dev, int32_t n, int32_t d, int32_t C, int32_t p,
+                           int32_t max_lag, double *mean_dev, double *var_dev, double *ess_dev,
+                           void *stream);
+
+/* FP64 roofline denominator: runs a dependent-free DFMA kernel for about
+ * `millis` ms on the current device and returns the sustained FP64 FMA rate in
+ * FLOP/s (2 flops per DFMA) through *flops_out.  Synchronises. */
+int rsfm_measure_fp64_peak(double millis, double *flops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSFM_H */

@@ -1,0 +1,182 @@
+"""Parity of the CUDA forward solve (rsf_forward_kernel through the C ABI) with the CPU oracle
+and with golden vectors from the unmodified reference."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+# |acc_gpu - acc_ref| <= 1e-9 * max|acc_ref| + 1e-12 outside the stiff regime,
+# 1e-6 * max|acc_ref| for Dc < 50 where accepted-step sequences may legitimately differ.
+RTOL, ATOL, RTOL_STIFF = 1e-9, 1e-12, 1e-6
+
+
+def _check(acc_g, acc_ref, dc):
+    scale = np.max(np.abs(acc_ref))
+    tol = (RTOL_STIFF if dc < 50 else RTOL) * scale + ATOL
+    err = np.max(np.abs(acc_g - acc_ref))
+    assert err <= tol, f"Dc={dc}: err {err:.3e} > tol {tol:.3e}"
+    return err / scale
+
+
+def test_golden_trajectories(cuda, pkg):
+    g = load_golden("forward_trajectories.json")
+    worst = 0.0
+    for case in g["cases"]:
+        if "filled" in case:
+            continue
+        m = pkg.RateStateModel(number_time_steps=case["N"], end_time=case.get("end_time", 50.0))
+        m.RadiationDamping = case["RadiationDamping"]
+        m.Dc = case["Dc"]
+        t, acc, acc_noise = m.evaluate()
+        assert acc.shape == case["acc"].shape and acc.dtype == np.float64
+        assert t[-1] == pytest.approx(case["t_last"], abs=1e-12)
+        assert acc[0] == 0.0
+        rel = _check(acc, case["acc"], case["Dc"])
+        if case["Dc"] >= 50:
+            worst = max(worst, rel)
+    assert worst < 1e-11      # expected agreement is ~1e-13; the gate above is 1e-9
+
+
+def test_batch_vs_oracle_and_counters(cuda, pkg, orc):
+    dcs = np.array([0.05, 0.5, 1.0, 10.0, 60.0, 100.0, 333.0, 1000.0, 1350.0, 2500.0, 5000.0, 9999.0, 20000.0])
+    m = pkg.RateStateModel()
+    out = m.evaluate_batch(dcs, want_t=True)
+    acc_g = out["acc"].t().cpu().numpy()
+    om = orc.make_model()
+    _, acc_o, nrhs_o = orc.forward_batch(om, dcs, want_acc=True)
+    for i, dc in enumerate(dcs):
+        _check(acc_g[i], acc_o[i], dc)
+    assert np.all(out["status"].cpu().numpy() == 0)
+    assert np.all(out["filled"].cpu().numpy() == 500)
+    # executed RHS count: the kernel skips the bit-identical restart evaluation of every interval
+    # after the first, so it executes exactly (n_out - 2) fewer RHS than SciPy for the same steps
+    nrhs_g = out["nrhs"].cpu().numpy()
+    nonstiff = dcs >= 50
+    assert np.array_equal(nrhs_g[nonstiff], nrhs_o[nonstiff] - 498)
+    nstep_g = out["nstep"].cpu().numpy()
+    assert np.all(nstep_g[nonstiff] == 503)
+    # output times accumulate exactly like the reference (t_k+1 = t_k + delta_t inside the solver)
+    tt = out["t"][:, 7].cpu().numpy()
+    t_o, _, _ = orc.forward(orc.make_model(Dc=1000.0))
+    assert np.array_equal(tt, t_o)
+
+
+@pytest.mark.parametrize("damping", [True, False])
+def test_sse_vs_oracle(cuda, pkg, orc, damping):
+    g = load_golden("sse_grid.json")
+    m = pkg.RateStateModel()
+    m.RadiationDamping = damping
+    out = m.evaluate_batch(g["grid"], data=g["data"], want_acc=False)
+    sse_o, _, _ = orc.forward_batch(orc.make_model(radiation_damping=int(damping)), g["grid"], data=g["data"])
+    assert np.allclose(out["sse"].cpu().numpy(), sse_o, rtol=1e-10, atol=0)
+    if damping:
+        assert np.allclose(out["sse"].cpu().numpy(), g["sse"], rtol=1e-10, atol=0)     # reference values
+
+
+def test_silent_failure_is_flagged(cuda, pkg, orc):
+    """Dc <= 1e-4: the reference bails in interval 1 with a zero tail (q9); the kernel flags it."""
+    g = load_golden("forward_trajectories.json")
+    case = [c for c in g["cases"] if "filled" in c][0]
+    m = pkg.RateStateModel()
+    out = m.evaluate_batch([case["Dc"], 1000.0, 5e-5], data=np.zeros(500))
+    st = out["status"].cpu().numpy()
+    assert st[0] == pkg._lib.CHAIN_NMAX and st[1] == 0 and st[2] == pkg._lib.CHAIN_NMAX
+    assert out["filled"].cpu().numpy()[0] == case["filled"]
+    acc = out["acc"][:, 0].cpu().numpy()
+    assert np.all(acc[case["filled"]:] == 0.0) and acc[1] != 0.0
+    # the partial value stored at k = 1 agrees with the oracle's (same failure point)
+    _, acc_o, sto = orc.forward(orc.make_model(Dc=case["Dc"]))
+    assert acc[1] == pytest.approx(acc_o[1], rel=1e-3)
+    m.Dc = case["Dc"]
+    with pytest.warns(UserWarning, match="larger nsteps"):
+        m.evaluate()
+
+
+@pytest.mark.parametrize("c", [1, 31, 32, 33, 257, 5000])
+def test_ragged_batch_sizes(cuda, pkg, orc, c):
+    rng = np.random.default_rng(c)
+    dcs = rng.uniform(200.0, 5000.0, size=c)
+    data = orc.forward(orc.make_model(Dc=1350.0))[1]
+    m = pkg.RateStateModel()
+    out = m.evaluate_batch(dcs, data=data, want_acc=False)
+    pick = rng.choice(c, size=min(c, 12), replace=False)
+    sse_o, _, _ = orc.forward_batch(orc.make_model(), dcs[pick], data=data)
+    assert np.allclose(out["sse"].cpu().numpy()[pick], sse_o, rtol=1e-9, atol=1e-18)
+
+
+@pytest.mark.parametrize("n,t_end", [(200, 30.0), (501, 50.1), (1025, 102.5), (2100, 210.0)])
+def test_other_grids_and_streamed_series(cuda, pkg, orc, n, t_end):
+    """n > 1024 exercises the streaming (non-resident) TMA tile path, odd n the tail element."""
+    dcs = np.array([300.0, 1350.0, 4000.0])
+    om = orc.make_model(number_time_steps=n, end_time=t_end)
+    assert orc.num_outputs(om) in (n, n - 1)
+    data = orc.forward(orc.make_model(Dc=900.0, number_time_steps=n, end_time=t_end))[1]
+    m = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
+    assert m.num_outputs() == orc.num_outputs(om)
+    out = m.evaluate_batch(dcs, data=data)
+    sse_o, acc_o, _ = orc.forward_batch(om, dcs, data=data, want_acc=True)
+    acc_g = out["acc"].t().cpu().numpy()
+    for i, dc in enumerate(dcs):
+        _check(acc_g[i], acc_o[i], dc)
+    assert np.allclose(out["sse"].cpu().numpy(), sse_o, rtol=1e-9, atol=0)
+
+
+def test_per_chain_a_b(cuda, pkg, orc):
+    rng = np.random.default_rng(3)
+    c = 40
+    a = rng.uniform(0.008, 0.013, c)
+    b = rng.uniform(0.012, 0.018, c)
+    dc = rng.uniform(500, 3000, c)
+    m = pkg.RateStateModel()
+    out = m.evaluate_batch(dc, a=a, b=b)
+    acc_g = out["acc"].t().cpu().numpy()
+    for i in range(0, c, 7):
+        _, acc_o, _ = orc.forward(orc.make_model(Dc=dc[i], a=a[i], b=b[i]))
+        _check(acc_g[i], acc_o, dc[i])
+
+
+def test_carry_mode_within_tolerance(cuda, pkg, orc):
+    """CARRY (h and FSAL carried across output points) must stay inside the same trajectory gate."""
+    dcs = np.array([60.0, 100.0, 1000.0, 1350.0, 5000.0])
+    m = pkg.RateStateModel()
+    m.integ_mode = "carry"
+    out = m.evaluate_batch(dcs)
+    acc_g = out["acc"].t().cpu().numpy()
+    _, acc_o, _ = orc.forward_batch(orc.make_model(), dcs, want_acc=True)
+    for i, dc in enumerate(dcs):
+        _check(acc_g[i], acc_o[i], dc)
+    assert np.all(out["nrhs"].cpu().numpy() < 6100)          # 12 instead of 13 executed RHS per interval
+
+
+def test_vstep_loading_vs_oracle(cuda, pkg, orc):
+    """VSTEP loading extension: same solver, piecewise-constant load-point velocity."""
+    n, t_end = 600, 60.0
+    kw = dict(loading=orc.LOAD_VSTEP, vstep_period=10.0, vstep_factor=3.0)
+    dcs = np.array([2.0, 20.0, 200.0])
+    m = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
+    m.loading, m.vstep_period, m.vstep_factor = "vstep", 10.0, 3.0
+    out = m.evaluate_batch(dcs)
+    acc_g = out["acc"].t().cpu().numpy()
+    _, acc_o, _ = orc.forward_batch(orc.make_model(number_time_steps=n, end_time=t_end, **kw), dcs, want_acc=True)
+    assert np.all(out["status"].cpu().numpy() == 0)
+    for i, dc in enumerate(dcs):
+        scale = np.max(np.abs(acc_o[i]))
+        assert np.max(np.abs(acc_g[i] - acc_o[i])) <= 1e-6 * scale
+
+
+def test_size_independent_properties_at_scale(cuda, pkg):
+    """Full-size batch (65,536 chains): identical parameters give identical results in every lane,
+    SSE against the model's own trajectory is exactly zero, and SSE grows away from the truth."""
+    m = pkg.RateStateModel()
+    m.Dc = 1325.0
+    _, acc, _ = m.evaluate()
+    c = 65536
+    dcs = np.full(c, 1325.0)
+    dcs[1::2] = 2000.0
+    out = m.evaluate_batch(dcs, data=acc, want_acc=False)
+    sse = out["sse"].cpu().numpy()
+    assert np.all(sse[0::2] == 0.0)
+    assert np.all(sse[1::2] == sse[1]) and sse[1] > 0
+    assert np.all(out["status"].cpu().numpy() == 0)

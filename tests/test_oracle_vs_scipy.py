@@ -1,0 +1,90 @@
+"""The oracle's DOP853 restatement against the third-party solver the reference
+actually calls: scipy.integrate.ode('dop853') (RateStateModel.py:374).  Both are
+driven with the SAME right-hand side (the oracle's C RHS through a callback), so
+any difference is integrator logic.  CPU only; SciPy is in the image."""
+import ctypes as C
+import warnings
+
+import numpy as np
+import pytest
+from scipy import integrate
+
+
+def _call(orc, model, t0, y0, t1):
+    lib = orc.lib()
+    lib.orc_dop853_call.argtypes = [C.POINTER(orc.OrcModel), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.c_double, C.POINTER(orc.OrcStats)]
+    lib.orc_dop853_call.restype = C.c_int
+    st = orc.OrcStats()
+    t = C.c_double(t0)
+    y = (C.c_double * 3)(*y0)
+    idid = lib.orc_dop853_call(C.byref(model), C.byref(t), y, t1, C.byref(st))
+    return idid, t.value, np.array(list(y)), st
+
+
+@pytest.mark.parametrize("dc,nint", [(1000.0, 60), (10.0, 60), (1.0, 40), (0.05, 12), (0.01, 6)])
+def test_interval_by_interval_bit_exact(orc, dc, nint):
+    model = orc.make_model(Dc=dc)
+    calls = []
+
+    def f(t, y):
+        calls.append(t)
+        return orc.rhs(model, t, y)
+
+    r = integrate.ode(f).set_integrator("dop853", rtol=1e-6, atol=1e-10)
+    r.set_initial_value([0.6, dc, 1.0], 0.0)
+    for _ in range(nint):
+        t0, y0 = r.t, np.array(r.y, dtype=float)
+        calls.clear()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r.integrate(r.t + 0.1)
+        idid, t1, y1, st = _call(orc, model, t0, y0, t0 + 0.1)
+        assert idid == 1 and r.successful()
+        assert t1 == r.t
+        assert np.array_equal(y1, np.asarray(r.y)), (dc, t0)
+        # SciPy may add benign repeat calls at step starts (stale irtrn); never fewer
+        assert len(calls) >= st.nrhs and len(calls) - st.nrhs <= st.nstep + 1
+
+
+def test_failure_semantics_nmax(orc):
+    """Dc = 1e-4: more than nmax = 500 steps in the first interval -> idid -2 at the same t, y."""
+    dc = 1e-4
+    model = orc.make_model(Dc=dc)
+    r = integrate.ode(lambda t, y: orc.rhs(model, t, y)).set_integrator("dop853", rtol=1e-6, atol=1e-10)
+    r.set_initial_value([0.6, dc, 1.0], 0.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r.integrate(0.1)
+    idid, t1, y1, st = _call(orc, model, 0.0, [0.6, dc, 1.0], 0.1)
+    assert not r.successful() and idid == -2
+    assert t1 == r.t and np.array_equal(y1, np.asarray(r.y))
+    assert st.nstep == 501
+
+
+def test_scipy_reject_rule_is_constant_shrink():
+    """SciPy 1.18's C dop853 shrinks a rejected step by exactly 0.3 whatever err is (dop853.f
+    would use h/min(1/0.3, err^(1/8)/0.9)).  The oracle and the CUDA kernel follow SciPy; this
+    test documents the observation they rely on."""
+    c2 = 0.05260015195876773
+    lam = 100.0
+    calls = []
+
+    def f(t, y):
+        calls.append(t)
+        return -lam * np.asarray(y) + np.sin(t)
+
+    r = integrate.ode(f).set_integrator("dop853", rtol=1e-6, atol=1e-10, first_step=0.011)
+    r.set_initial_value([1.0], 0.0)
+    r.integrate(0.5)
+    c = np.array(calls)
+    # attempt 1: the first non-zero call time is stage 2 (c2*h1) and stage 12 is called at h1; the
+    # first non-zero call after that is stage 2 of the retry (c2*h2).  (SciPy may insert repeat
+    # calls at t = 0.)
+    nz = np.nonzero(c)[0]
+    h1 = c[nz[0]] / c2
+    i12 = int(np.nonzero(np.isclose(c, h1, rtol=1e-12, atol=0))[0][0])
+    after = c[i12 + 1:]
+    h2 = after[np.nonzero(after)[0][0]] / c2
+    assert h1 == pytest.approx(0.011, rel=1e-12)
+    assert h2 / h1 == pytest.approx(0.3, rel=1e-12)
