@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "rsfm_abi_version", "rsfm_last_error", "rsfm_cfg_defaults", "rsfm_device_count",
     "rsfm_forward_batch", "rsfm_create", "rsfm_destroy", "rsfm_init", "rsfm_run",
     "rsfm_run_deterministic", "rsfm_get_state", "rsfm_set_state", "rsfm_iteration",
-    "rsfm_get_suffstats", "rsfm_set_proposal_chol", "rsfm_chain_diagnostics",
+    "rsfm_get_totals", "rsfm_get_suffstats", "rsfm_set_proposal_chol", "rsfm_chain_diagnostics",
     "rsfm_measure_fp64_peak",
 )
 
@@ -86,6 +86,8 @@ def load():
     lib.rsfm_set_state.restype = C.c_int
     lib.rsfm_iteration.argtypes = [vp]
     lib.rsfm_iteration.restype = i64
+    lib.rsfm_get_totals.argtypes = [vp, C.POINTER(u64), vp]
+    lib.rsfm_get_totals.restype = C.c_int
     lib.rsfm_get_suffstats.argtypes = [vp, vp, i32, vp]
     lib.rsfm_get_suffstats.restype = C.c_int
     lib.rsfm_set_proposal_chol.argtypes = [vp, C.POINTER(dbl), vp]

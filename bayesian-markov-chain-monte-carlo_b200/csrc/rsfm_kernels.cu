@@ -193,6 +193,7 @@ struct SamplerDev {
     int *status;                   // [C] sticky OR of RSFM_CHAIN_* of all solves
     unsigned long long *nrhs;      // [C]
     unsigned long long *nstep;     // [C]
+    unsigned long long *nsolve;    // [C] forward solves executed
 };
 
 struct rsfm_sampler {
@@ -206,6 +207,7 @@ struct rsfm_sampler {
     SamplerDev d;
     double *scratch;               // [n_out][C] base trajectory for rsfm_init
     double *reduce_out;            // [16] device scratch for suffstats
+    unsigned long long *totals;    // [8] device scratch for rsfm_get_totals
 };
 
 static int tri(int d) { return d * (d + 1) / 2; }
@@ -239,6 +241,8 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     alloc((void **)&s->d.status, sizeof(int) * Cz);
     alloc((void **)&s->d.nrhs, sizeof(unsigned long long) * Cz);
     alloc((void **)&s->d.nstep, sizeof(unsigned long long) * Cz);
+    alloc((void **)&s->d.nsolve, sizeof(unsigned long long) * Cz);
+    alloc((void **)&s->totals, sizeof(unsigned long long) * 8);
     alloc((void **)&s->reduce_out, sizeof(double) * 16);
     if (!ok) {
         set_err(RSFM_ERR_CUDA, "rsfm_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -253,7 +257,8 @@ extern "C" void rsfm_destroy(rsfm_sampler *s)
     if (!s) return;
     cudaFree(s->d.q); cudaFree(s->d.sse); cudaFree(s->d.sigma2); cudaFree(s->d.chol); cudaFree(s->d.ring);
     cudaFree(s->d.suff); cudaFree(s->d.data); cudaFree(s->d.accepted); cudaFree(s->d.status);
-    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->scratch); cudaFree(s->reduce_out);
+    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->d.nsolve); cudaFree(s->scratch);
+    cudaFree(s->reduce_out); cudaFree(s->totals);
     delete s;
 }
 
@@ -297,19 +302,19 @@ rsf_init_kernel(ModelK M, int C, int pass, double a0, double b0, int n_prior_len
         if (active) {
             S.sse[c] = o.sse;
             S.sigma2[c] = o.sse / (double)(M.n_out - n_prior_len);     // :261
-            S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status;
+            S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; S.nsolve[c] += 1;
         }
     } else if (D == 1) {
         SolveOut o = rsf_solve(M, a, b, dc, active, series, nullptr, scratch + cc, (size_t)C, fd_den, &xtx);
         if (active) {
             S.chol[c] = S.sigma2[c] * (1.0 / xtx);                     // Vstart, :265-266
-            S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status;
+            S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; S.nsolve[c] += 1;
         }
     } else {
         // d = 3: write the perturbed trajectory; columns are combined by rsf_init_finish_kernel
         SolveOut o = rsf_solve(M, a, b, dc, active, series, scratch + (size_t)pass * plane + cc, nullptr,
                                (size_t)C, 1.0, nullptr);
-        if (active) { S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; }
+        if (active) { S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; S.nsolve[c] += 1; }
     }
 }
 
@@ -373,6 +378,7 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     CUDA_TRY(cudaMemsetAsync(s->d.status, 0, sizeof(int) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.nrhs, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.nstep, 0, sizeof(unsigned long long) * C, stream));
+    CUDA_TRY(cudaMemsetAsync(s->d.nsolve, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * (d + tri(d)) * (size_t)C, stream));
     const int block = pick_block(C), grid = (C + block - 1) / block;
     const ModelK M = make_model(&s->cfg);
@@ -444,6 +450,7 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
     double ss = S.sse[cc], s2 = S.sigma2[cc];
     unsigned int n_acc = 0;
     unsigned long long nrhs = 0, nstep = 0;
+    unsigned int nsolve = 0;
     int status = 0;
     const unsigned long long gid = A.chain_id0 + (unsigned long long)cc;
     const PhiloxKey key = philox_key(A.seed);
@@ -494,7 +501,7 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
         bool acc = false;
         double u = nan("");
         if (solve) {
-            nrhs += o.nrhs; nstep += o.nstep; status |= o.status;
+            nrhs += o.nrhs; nstep += o.nstep; status |= o.status; nsolve++;
             if (A.deterministic) u = A.uniforms[(size_t)it * Cz + cc];
             else u = philox_uniform(key, gid, giter, 2u);
             double la = 0.5 * (ss - o.sse) / s2;
@@ -570,7 +577,7 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
         for (int j = 0; j < T; j++) S.chol[j * Cz + c] = L[j];
         S.sse[c] = ss; S.sigma2[c] = s2;
         S.accepted[c] += n_acc;
-        S.nrhs[c] += nrhs; S.nstep[c] += nstep; S.status[c] |= status;
+        S.nrhs[c] += nrhs; S.nstep[c] += nstep; S.status[c] |= status; S.nsolve[c] += nsolve;
         if (A.adapt_mode == RSFM_ADAPT_POOLED) {
 #pragma unroll
             for (int j = 0; j < D; j++) S.suff[j * Cz + c] += sq[j];
@@ -657,6 +664,36 @@ extern "C" int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double
     if (sigma2_dev) CUDA_TRY(cudaMemcpyAsync(s->d.sigma2, sigma2_dev, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
     if (chol_dev) CUDA_TRY(cudaMemcpyAsync(s->d.chol, chol_dev, sizeof(double) * tri(d) * C, cudaMemcpyDeviceToDevice, st));
     if (iteration >= 0) s->iteration = iteration;
+    return RSFM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// work totals (forward solves, RHS evaluations, steps, accepted moves, failed chains)
+// ---------------------------------------------------------------------------
+__global__ void totals_kernel(int C, SamplerDev S, unsigned long long *__restrict__ out)
+{
+    unsigned long long v[5] = {0, 0, 0, 0, 0};
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        v[0] += S.nsolve[c]; v[1] += S.nrhs[c]; v[2] += S.nstep[c]; v[3] += S.accepted[c];
+        v[4] += S.status[c] != 0 ? 1 : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_down_sync(FULL_MASK, v[j], o);
+        if ((threadIdx.x & 31) == 0 && v[j]) atomicAdd(&out[j], v[j]);
+    }
+}
+
+extern "C" int rsfm_get_totals(rsfm_sampler *s, uint64_t *out_host, void *stream_)
+{
+    if (!s || !out_host) return set_err(RSFM_ERR_INVALID, "rsfm_get_totals: NULL argument%s", "");
+    cudaStream_t st = (cudaStream_t)stream_;
+    CUDA_TRY(cudaMemsetAsync(s->totals, 0, sizeof(unsigned long long) * 8, st));
+    const int grid = (s->C + 255) / 256 < 592 ? (s->C + 255) / 256 : 592;
+    totals_kernel<<<grid, 256, 0, st>>>(s->C, s->d, s->totals);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_host, s->totals, sizeof(uint64_t) * 5, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return RSFM_OK;
 }
 

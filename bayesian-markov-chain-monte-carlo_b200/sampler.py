@@ -34,7 +34,7 @@ class MCMC:
     def __init__(self, model, data, dc_true, qpriors, qstart, nsamples=100, lstm_model={},
                  adapt_interval=10, verbose=True, *, n_chains=1, seed=None, device=None,
                  param_names=("Dc",), bounds=None, deterministic_inputs=None, compat_adapt=None,
-                 adapt=None, adapt_start=100, shard=False, keep_on_device=False):
+                 adapt=None, adapt_start=100, shard=False, chain_id0=0, keep_on_device=False):
         # reference attributes, MCMC.py:88-99
         self.model = model
         self.qstart = qstart
@@ -58,6 +58,7 @@ class MCMC:
         self.adapt = adapt
         self.adapt_start = int(adapt_start)
         self.shard = bool(shard)
+        self.chain_id0 = int(chain_id0)        # global id of chain 0 when not sharding (Philox counter)
         self.keep_on_device = bool(keep_on_device)
         if self.param_names not in (("Dc",), ("a", "b", "Dc")):
             raise ValueError("param_names must be ('Dc',) or ('a', 'b', 'Dc')")
@@ -123,6 +124,7 @@ class MCMC:
         d = len(self.param_names)
         shard = ChainShard.for_current_rank(self.n_chains) if self.shard else ChainShard(0, self.n_chains, self.n_chains)
         cl = shard.count
+        id0 = shard.start if self.shard else self.chain_id0
         n_out = self.model.num_outputs()
         data = np.ascontiguousarray(np.asarray(self.data, dtype=np.float64).reshape(-1))
         if data.size != n_out:
@@ -151,7 +153,7 @@ class MCMC:
             stream = _lib.current_stream(torch, dev)
             data_t = torch.from_numpy(data).to(dev)
             q0 = self._start_values(torch, dev, d, shard)
-            handle = lib.rsfm_create(C.byref(cfg), cl, C.c_uint64(self.seed_used), C.c_uint64(shard.start))
+            handle = lib.rsfm_create(C.byref(cfg), cl, C.c_uint64(self.seed_used), C.c_uint64(id0))
             if not handle:
                 _lib.check(-1, "rsfm_create")
             try:
@@ -181,6 +183,8 @@ class MCMC:
                 nstep = torch.empty(cl, dtype=torch.int64, device=dev)
                 _lib.check(lib.rsfm_get_state(handle, None, None, None, None, _lib.ptr(acc_cnt), _lib.ptr(status),
                                               _lib.ptr(nrhs), _lib.ptr(nstep), stream), "rsfm_get_state")
+                tot = (C.c_uint64 * 5)()
+                _lib.check(lib.rsfm_get_totals(handle, tot, stream), "rsfm_get_totals")
                 torch.cuda.synchronize(dev)
             finally:
                 lib.rsfm_destroy(handle)
@@ -200,8 +204,8 @@ class MCMC:
         n_acc = acc_cnt.cpu().numpy().astype(np.int64)
         self.acceptance_ratio = n_acc / float(self.nsamples)
         self.stats = {
-            "elapsed_s": elapsed, "n_chains_local": cl, "chain_id0": shard.start,
-            "nrhs": int(nrhs.sum().item()), "nstep": int(nstep.sum().item()),
+            "elapsed_s": elapsed, "n_chains_local": cl, "chain_id0": id0,
+            "nsolves": int(tot[0]), "nrhs": int(tot[1]), "nstep": int(tot[2]),
             "failed_chains": int((status != 0).sum().item()),
         }
         if cl == 1:

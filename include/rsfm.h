@@ -147,6 +147,11 @@ int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double *sse_dev,
                    void *stream);
 int64_t rsfm_iteration(const rsfm_sampler *s);
 
+/* Work totals since rsfm_init, summed over chains on the device and copied to
+ * out_host[5] = (forward solves executed, RHS evaluations, attempted steps,
+ * accepted moves, chains with a non-zero status).  Synchronises the stream. */
+int rsfm_get_totals(rsfm_sampler *s, uint64_t *out_host, void *stream);
+
 /* Pooled adaptation (extension): local sufficient
  * statistics out_dev[1 + d + d(d+1)/2] = (n, sum q, sum q q^T lower) accumulated
  * over all chains and iterations since the last reset; the caller all-reduces

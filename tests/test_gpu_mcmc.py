@@ -60,7 +60,7 @@ def test_free_running_chains_replay_through_oracle(cuda, pkg, orc):
     model = pkg.RateStateModel()
     cfg = model.to_cfg()
     cfg.n_params, cfg.n_prior_len = 1, 3
-    cfg.lo[0], cfg.hi[0] = 1000.0, 1800.0                # tight bounds: out-of-bounds proposals do occur
+    cfg.lo[0], cfg.hi[0] = 1270.0, 1380.0                # tight bounds: out-of-bounds proposals do occur
     c, ns = 48, 40
     dev = torch.device("cuda", 0)
     q0 = torch.full((1, c), 1300.0, dtype=torch.float64, device=dev)
@@ -83,7 +83,7 @@ def test_free_running_chains_replay_through_oracle(cuda, pkg, orc):
         prop, u, gam = draws[:, 0, ch], draws[:, 1, ch], draws[:, 2, ch]
         n_oob += int(np.isnan(u).sum())
         assert np.all((u[~np.isnan(u)] > 0) & (u[~np.isnan(u)] < 1)) and np.all(gam > 0)
-        chain_o, s2_o, acc_o, _, _ = orc.chain_replay(orc.make_model(), g["data"], 1300.0, 1000.0, 1800.0, 3, ns,
+        chain_o, s2_o, acc_o, _, _ = orc.chain_replay(orc.make_model(), g["data"], 1300.0, 1270.0, 1380.0, 3, ns,
                                                       prop, np.nan_to_num(u, nan=0.5), gam)
         assert np.array_equal(acc[:, ch], acc_o)
         assert np.array_equal(samples[:, 0, ch], chain_o[1:])

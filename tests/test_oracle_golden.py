@@ -103,3 +103,30 @@ def test_compat_adaptation_matches_reference(orc):
 def test_list_priors_never_adapt():
     g = load_golden("chain_list_priors.json")
     assert len(np.unique(g["V_used"])) == 1           # quirk q2
+
+
+# ---- the NumPy/SciPy form of the oracle (oracle/scipy_port.py), the CPU baseline bench.py times ----
+def test_scipy_port_trajectory_bit_exact():
+    from oracle import scipy_port
+    g = load_golden("forward_trajectories.json")
+    case = [c for c in g["cases"] if c["Dc"] == 1350.0 and c["RadiationDamping"]][0]
+    m = scipy_port.PortModel()
+    m.Dc = 1350.0
+    t, acc, _ = m.evaluate()
+    assert np.array_equal(acc, case["acc"])
+    assert m.n_rhs >= 7034
+
+
+def test_scipy_port_chain_bit_exact():
+    """Same seed, same draw order (normal -> [randn(N) -> rand] -> gamma) => the reference's chain."""
+    from oracle import scipy_port
+    g = load_golden("chain_list_priors.json")
+    ns, nb = 40, g["nburn"]
+    r = scipy_port.run_chain(g["data"], g["qstart"], g["lo"], g["hi"], ns, n_prior_len=3, seed=g["seed"])
+    # the golden chain has 120 iterations; the first 40 decisions and states must coincide
+    assert np.array_equal(r["accepts"], g["accepts"][:ns].astype(bool))
+    full_ref, _, _, _, _ = __import__("oracle.oracle", fromlist=["x"]).chain_replay(
+        __import__("oracle.oracle", fromlist=["x"]).make_model(), g["data"], g["qstart"], g["lo"], g["hi"], 3,
+        g["nsamples"], g["proposals"], np.nan_to_num(g["uniforms"], nan=0.5), g["gammas_unit"])[0:5]
+    assert np.array_equal(r["chain"], full_ref[:ns + 1])
+    assert r["n_solves"] == 3 + ns
