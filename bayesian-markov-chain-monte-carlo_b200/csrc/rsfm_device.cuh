@@ -37,20 +37,6 @@ struct ModelK {
     int n_out, nmax, damping, loading, integ_mode;
 };
 
-struct ChainConst {
-    double b, inv_a, inv_dc, kprime;
-};
-
-__device__ __forceinline__ ChainConst make_chain_const(double a, double b, double dc)
-{
-    ChainConst c;
-    c.b = b;
-    c.inv_a = 1.0 / a;
-    c.inv_dc = 1.0 / dc;
-    c.kprime = 1e-2 * 10 / dc;            // RateStateModel.py:324
-    return c;
-}
-
 // ---------------------------------------------------------------------------
 // TMA bulk-copy staging of the observed series
 // ---------------------------------------------------------------------------
@@ -177,56 +163,242 @@ struct SeriesStage {
 // ---------------------------------------------------------------------------
 // model
 // ---------------------------------------------------------------------------
-// load-point velocity, RateStateModel.py:327-329 (SINE_DECAY) / VSTEP extension
-__device__ __noinline__ double loading_velocity(int loading, double V_ref, double t_start, double period,
-                                                double factor, double t)
+// Butcher tableau and series coefficients live in the constant bank (loaded into uniform registers
+// by the compiler; FP64 instructions on sm_100 take register or uniform-register operands).
+struct Dop853Tab {
+    double c[12];                                   // abscissae of stages 2..12 (+ pad)
+    double a21, a31, a32, a41, a43, a51, a53, a54, a61, a64, a65, a71, a74, a75, a76;
+    double a81, a84, a85, a86, a87, a91, a94, a95, a96, a97, a98;
+    double a101, a104, a105, a106, a107, a108, a109;
+    double a111, a114, a115, a116, a117, a118, a119, a1110;
+    double a121, a124, a125, a126, a127, a128, a129, a1210, a1211;
+    double b1, b6, b7, b8, b9, b10, b11, b12;
+    double e1, e6, e7, e8, e9, e10, e11, e12;
+    double bhh1, bhh2, bhh3;
+    double lp[6];      // log1p series (Horner, highest first): (f + lp0) lp1, then + lp2.. ; see rsf_rhs
+    double ex[6];      // expm1 series
+};
+__constant__ Dop853Tab TB = {
+    {DP_C2, DP_C3, DP_C4, DP_C5, DP_C6, DP_C7, DP_C8, DP_C9, DP_C10, DP_C11, 1.0, 0.0},
+    DP_A2_1, DP_A3_1, DP_A3_2, DP_A4_1, DP_A4_3, DP_A5_1, DP_A5_3, DP_A5_4, DP_A6_1, DP_A6_4, DP_A6_5,
+    DP_A7_1, DP_A7_4, DP_A7_5, DP_A7_6,
+    DP_A8_1, DP_A8_4, DP_A8_5, DP_A8_6, DP_A8_7, DP_A9_1, DP_A9_4, DP_A9_5, DP_A9_6, DP_A9_7, DP_A9_8,
+    DP_A10_1, DP_A10_4, DP_A10_5, DP_A10_6, DP_A10_7, DP_A10_8, DP_A10_9,
+    DP_A11_1, DP_A11_4, DP_A11_5, DP_A11_6, DP_A11_7, DP_A11_8, DP_A11_9, DP_A11_10,
+    DP_A12_1, DP_A12_4, DP_A12_5, DP_A12_6, DP_A12_7, DP_A12_8, DP_A12_9, DP_A12_10, DP_A12_11,
+    DP_B1, DP_B6, DP_B7, DP_B8, DP_B9, DP_B10, DP_B11, DP_B12,
+    DP_ER1, DP_ER6, DP_ER7, DP_ER8, DP_ER9, DP_ER10, DP_ER11, DP_ER12,
+    DP_BHH1, DP_BHH2, DP_BHH3,
+    {-6.0 / 5.0, -1.0 / 6.0, -0.25, 0.3333333333333333, -0.5, 0.0},
+    {7.0, 1.0 / 5040.0, 0.008333333333333333, 0.041666666666666664, 0.16666666666666666, 0.5},
+};
+
+// Relative load-point perturbation L(t) with V_l = V_ref (1 + L):
+// SINE_DECAY  L = exp(-t/20) sin(10 t)            RateStateModel.py:327-329
+// VSTEP       L = factor - 1 on odd periods, 0 on even periods (extension)
+__device__ __noinline__ double loading_rel(int loading, double t_start, double period, double factor, double t)
 {
     if (loading == RSFM_LOAD_VSTEP) {
         const double ph = floor((t - t_start) / period);
         const long long i = (long long)ph;
-        return (i & 1) ? factor * V_ref : V_ref;
+        return (i & 1) ? factor - 1.0 : 0.0;
     }
-    return V_ref * (1.0 + exp(-t / 20.0) * sin(10.0 * t));
+    return exp(-t / 20.0) * sin(10.0 * t);
 }
 
 __device__ __forceinline__ double loading_of(const ModelK &M, double t)
 {
-    return loading_velocity(M.loading, M.V_ref, M.t_start, M.vstep_period, M.vstep_factor, t);
+    return loading_rel(M.loading, M.t_start, M.vstep_period, M.vstep_factor, t);
 }
 
-// friction(t, y), RateStateModel.py:336-353; V_l is passed in (time-only term)
-__device__ __forceinline__ void rsf_rhs(const ModelK &M, const ChainConst &c, double vl, double mu, double th,
-                                        double &dmu, double &dth, double &dV)
+struct ChainConst {
+    double b, inv_a, w, kV, voa0, k1e, mu_ref;
+    // w = V_ref/Dc, kV = k' V_ref with k' = 0.1/Dc (RateStateModel.py:324), voa0 = V_ref/a,
+    // k1e = k1 when RadiationDamping else 0 (:349)
+};
+
+__device__ __forceinline__ ChainConst make_chain_const(const ModelK &M, double a, double b, double dc)
 {
-    const double temp = c.inv_a * (mu - M.mu_ref - c.b * log(M.V_ref * th * c.inv_dc));   // :336
-    const double v = M.V_ref * exp(temp);                                                // :337
-    dth = 1.0 - v * th * c.inv_dc;                                                       // :340
-    dmu = c.kprime * vl - c.kprime * v;                                                  // :343
-    const double voa = v * c.inv_a;
-    const double s = (c.b / th) * dth;
-    dV = voa * (dmu - s);                                                                // :346
-    if (M.damping) {                                                                     // :349-353
-        dmu = dmu - M.k1 * dV;
-        dV = voa * (dmu - s);
+    ChainConst c;
+    c.b = b;
+    c.inv_a = 1.0 / a;
+    c.w = M.V_ref / dc;
+    c.kV = (1e-2 * 10 / dc) * M.V_ref;
+    c.voa0 = M.V_ref * c.inv_a;
+    c.k1e = M.damping ? M.k1 : 0.0;
+    c.mu_ref = M.mu_ref;
+    return c;
+}
+
+// friction(t, y), RateStateModel.py:336-353, in a cancellation-free form.  With x = V_ref theta/Dc =
+// 1 + f, v = V_ref e^temp = V_ref (1 + E) and V_l = V_ref (1 + L):
+//     theta' = 1 - v theta/Dc = -(E + f + E f)          (:340)
+//     mu'    = k'(V_l - v)    = k' V_ref (L - E)         (:343)
+//     V'     = (v/a)(mu' - (b/theta) theta')             (:346)
+//     damping (:349-353): mu' <- mu' - k1 V' ; V' <- (v/a)(mu' - ...) = V' (1 - k1 v/a)
+// The reference evaluates the same expressions with ~1e-16 absolute rounding noise in the
+// differences; this form is algebraically identical and differs from it at that noise level only.
+//
+// FAST = true: branch-free.  log1p and expm1 are the Taylor series truncated for |f| < 2^-9 (terms
+// to f^5, truncation < 1e-17 relative) and |temp| < 2^-6 (terms to t^6), each a Horner chain with one
+// constant per FMA; 1/theta is refreshed from the previous evaluation by two Newton steps (theta
+// moves ~1e-6 relative between stages).  The three range conditions are OR-ed into `bad`; the
+// caller recomputes with FAST = false (libdevice log1p / expm1, true division) when it is set.
+// Along every trajectory with Dc >= 120 of the reference's loading the fast ranges always hold.
+template <bool FAST>
+__device__ __forceinline__ void rsf_rhs(const ChainConst &c, double L, double mu, double th, double &rth,
+                                        double &dmu, double &dth, double &dV, bool &bad)
+{
+    const double f = fma(c.w, th, -1.0);
+    double lg, E, r;
+    const double dmu0 = mu - c.mu_ref;
+    if (FAST) {
+        double p = (f + TB.lp[0]) * TB.lp[1];                  // -1/6 f + 1/5
+        p = fma(p, f, TB.lp[2]);
+        p = fma(p, f, TB.lp[3]);
+        p = fma(p, f, TB.lp[4]);
+        lg = fma(f * f, p, f);                                  // log(V_ref theta / Dc)
+        const double temp = c.inv_a * fma(-c.b, lg, dmu0);      // :336
+        double q = (temp + TB.ex[0]) * TB.ex[1];                // t/5040 + 1/720
+        q = fma(q, temp, TB.ex[2]);
+        q = fma(q, temp, TB.ex[3]);
+        q = fma(q, temp, TB.ex[4]);
+        q = fma(q, temp, TB.ex[5]);
+        E = fma(temp * temp, q, temp);                          // v / V_ref - 1, :337
+        const double e0 = fma(-th, rth, 1.0);
+        r = fma(rth, e0, rth);
+        r = fma(r, fma(-th, r, 1.0), r);
+        bad = bad || !(fabs(f) < 0.001953125 && fabs(temp) < 0.015625 && fabs(e0) < 6.0e-5);
+    } else {
+        lg = log1p(f);
+        const double temp = c.inv_a * fma(-c.b, lg, dmu0);
+        E = expm1(temp);
+        r = 1.0 / th;
     }
+    dth = -(fma(E, f, E) + f);
+    const double voa = fma(c.voa0, E, c.voa0);                  // v / a
+    const double d0 = c.kV * (L - E);
+    const double s = (c.b * r) * dth;
+    const double v0 = voa * (d0 - s);
+    dmu = fma(-c.k1e, v0, d0);
+    dV = fma(-(voa * c.k1e), v0, v0);
+    rth = r;
 }
 
 __device__ __forceinline__ double root8(double x) { return sqrt(sqrt(sqrt(x))); }
 
-__device__ __forceinline__ double stage_c(int i)   // abscissa of stage i+2, i = 0..10
+// One attempted DOP853 step (stages 2..12, 8th-order solution, error forms).  Lp points at the
+// eleven stage values of L (stride ls doubles, shared memory).
+struct StepIn { double h, mu, th, V, k1m, k1t, k1v, rth, atol, rtol; };
+struct StepOut { double muN, thN, VN, errs, deno, L12, rth; };
+
+template <bool FAST>
+__device__ __forceinline__ void dop853_step_impl(const ChainConst &cc, const StepIn &I, const double *Lp, int ls,
+                                                 StepOut &O, bool &bad)
 {
-    switch (i) {
-        case 0: return DP_C2;
-        case 1: return DP_C3;
-        case 2: return DP_C4;
-        case 3: return DP_C5;
-        case 4: return DP_C6;
-        case 5: return DP_C7;
-        case 6: return DP_C8;
-        case 7: return DP_C9;
-        case 8: return DP_C10;
-        case 9: return DP_C11;
-        default: return 1.0;
+    const double h = I.h, mu = I.mu, th = I.th, k1m = I.k1m, k1t = I.k1t, k1v = I.k1v;
+    double rth = I.rth;
+    double k2m, k2t, k3m, k3t, k4m, k4t, k5m, k5t, k6m, k6t, k7m, k7t, k8m, k8t, k9m, k9t, k10m, k10t;
+    double kv, k9v, k12v, bV, eV;
+    // stages 2..5: their V-derivatives carry zero weight everywhere
+    rsf_rhs<FAST>(cc, Lp[0 * ls], mu + h * (TB.a21 * k1m), th + h * (TB.a21 * k1t), rth, k2m, k2t, kv, bad);
+    rsf_rhs<FAST>(cc, Lp[1 * ls], mu + h * (TB.a31 * k1m + TB.a32 * k2m), th + h * (TB.a31 * k1t + TB.a32 * k2t),
+                  rth, k3m, k3t, kv, bad);
+    rsf_rhs<FAST>(cc, Lp[2 * ls], mu + h * (TB.a41 * k1m + TB.a43 * k3m), th + h * (TB.a41 * k1t + TB.a43 * k3t),
+                  rth, k4m, k4t, kv, bad);
+    rsf_rhs<FAST>(cc, Lp[3 * ls], mu + h * (TB.a51 * k1m + TB.a53 * k3m + TB.a54 * k4m),
+                  th + h * (TB.a51 * k1t + TB.a53 * k3t + TB.a54 * k4t), rth, k5m, k5t, kv, bad);
+    rsf_rhs<FAST>(cc, Lp[4 * ls], mu + h * (TB.a61 * k1m + TB.a64 * k4m + TB.a65 * k5m),
+                  th + h * (TB.a61 * k1t + TB.a64 * k4t + TB.a65 * k5t), rth, k6m, k6t, kv, bad);
+    bV = TB.b1 * k1v + TB.b6 * kv;
+    eV = TB.e1 * k1v + TB.e6 * kv;
+    rsf_rhs<FAST>(cc, Lp[5 * ls], mu + h * (TB.a71 * k1m + TB.a74 * k4m + TB.a75 * k5m + TB.a76 * k6m),
+                  th + h * (TB.a71 * k1t + TB.a74 * k4t + TB.a75 * k5t + TB.a76 * k6t), rth, k7m, k7t, kv, bad);
+    bV += TB.b7 * kv; eV += TB.e7 * kv;
+    rsf_rhs<FAST>(cc, Lp[6 * ls],
+                  mu + h * (TB.a81 * k1m + TB.a84 * k4m + TB.a85 * k5m + TB.a86 * k6m + TB.a87 * k7m),
+                  th + h * (TB.a81 * k1t + TB.a84 * k4t + TB.a85 * k5t + TB.a86 * k6t + TB.a87 * k7t), rth,
+                  k8m, k8t, kv, bad);
+    bV += TB.b8 * kv; eV += TB.e8 * kv;
+    rsf_rhs<FAST>(cc, Lp[7 * ls],
+                  mu + h * (TB.a91 * k1m + TB.a94 * k4m + TB.a95 * k5m + TB.a96 * k6m + TB.a97 * k7m + TB.a98 * k8m),
+                  th + h * (TB.a91 * k1t + TB.a94 * k4t + TB.a95 * k5t + TB.a96 * k6t + TB.a97 * k7t + TB.a98 * k8t),
+                  rth, k9m, k9t, k9v, bad);
+    bV += TB.b9 * k9v; eV += TB.e9 * k9v;
+    rsf_rhs<FAST>(cc, Lp[8 * ls],
+                  mu + h * (TB.a101 * k1m + TB.a104 * k4m + TB.a105 * k5m + TB.a106 * k6m + TB.a107 * k7m +
+                            TB.a108 * k8m + TB.a109 * k9m),
+                  th + h * (TB.a101 * k1t + TB.a104 * k4t + TB.a105 * k5t + TB.a106 * k6t + TB.a107 * k7t +
+                            TB.a108 * k8t + TB.a109 * k9t),
+                  rth, k10m, k10t, kv, bad);
+    bV += TB.b10 * kv; eV += TB.e10 * kv;
+    // stage 11 -> k2 slot
+    rsf_rhs<FAST>(cc, Lp[9 * ls],
+                  mu + h * (TB.a111 * k1m + TB.a114 * k4m + TB.a115 * k5m + TB.a116 * k6m + TB.a117 * k7m +
+                            TB.a118 * k8m + TB.a119 * k9m + TB.a1110 * k10m),
+                  th + h * (TB.a111 * k1t + TB.a114 * k4t + TB.a115 * k5t + TB.a116 * k6t + TB.a117 * k7t +
+                            TB.a118 * k8t + TB.a119 * k9t + TB.a1110 * k10t),
+                  rth, k2m, k2t, kv, bad);
+    bV += TB.b11 * kv; eV += TB.e11 * kv;
+    // stage 12 -> k3 slot, at x + h
+    const double L12 = Lp[10 * ls];
+    rsf_rhs<FAST>(cc, L12,
+                  mu + h * (TB.a121 * k1m + TB.a124 * k4m + TB.a125 * k5m + TB.a126 * k6m + TB.a127 * k7m +
+                            TB.a128 * k8m + TB.a129 * k9m + TB.a1210 * k10m + TB.a1211 * k2m),
+                  th + h * (TB.a121 * k1t + TB.a124 * k4t + TB.a125 * k5t + TB.a126 * k6t + TB.a127 * k7t +
+                            TB.a128 * k8t + TB.a129 * k9t + TB.a1210 * k10t + TB.a1211 * k2t),
+                  rth, k3m, k3t, k12v, bad);
+    bV += TB.b12 * k12v; eV += TB.e12 * k12v;
+    // 8th-order solution, 5th/3rd-order error forms
+    const double bM = TB.b1 * k1m + TB.b6 * k6m + TB.b7 * k7m + TB.b8 * k8m + TB.b9 * k9m + TB.b10 * k10m +
+                      TB.b11 * k2m + TB.b12 * k3m;
+    const double bT = TB.b1 * k1t + TB.b6 * k6t + TB.b7 * k7t + TB.b8 * k8t + TB.b9 * k9t + TB.b10 * k10t +
+                      TB.b11 * k2t + TB.b12 * k3t;
+    const double muN = mu + h * bM, thN = th + h * bT, VN = I.V + h * bV;
+    const double s0 = 1.0 / (I.atol + I.rtol * fmax(fabs(mu), fabs(muN)));
+    const double s1 = 1.0 / (I.atol + I.rtol * fmax(fabs(th), fabs(thN)));
+    const double s2 = 1.0 / (I.atol + I.rtol * fmax(fabs(I.V), fabs(VN)));
+    const double e3m = (bM - TB.bhh1 * k1m - TB.bhh2 * k9m - TB.bhh3 * k3m) * s0;
+    const double e3t = (bT - TB.bhh1 * k1t - TB.bhh2 * k9t - TB.bhh3 * k3t) * s1;
+    const double e3v = (bV - TB.bhh1 * k1v - TB.bhh2 * k9v - TB.bhh3 * k12v) * s2;
+    const double e5m = (TB.e1 * k1m + TB.e6 * k6m + TB.e7 * k7m + TB.e8 * k8m + TB.e9 * k9m + TB.e10 * k10m +
+                        TB.e11 * k2m + TB.e12 * k3m) * s0;
+    const double e5t = (TB.e1 * k1t + TB.e6 * k6t + TB.e7 * k7t + TB.e8 * k8t + TB.e9 * k9t + TB.e10 * k10t +
+                        TB.e11 * k2t + TB.e12 * k3t) * s1;
+    const double e5v = eV * s2;
+    const double err2 = e3m * e3m + e3t * e3t + e3v * e3v;
+    const double errs = e5m * e5m + e5t * e5t + e5v * e5v;
+    double deno = errs + 0.01 * err2;
+    if (deno <= 0.0) deno = 1.0;
+    O.muN = muN; O.thN = thN; O.VN = VN; O.errs = errs; O.deno = deno; O.L12 = L12; O.rth = rth;
+}
+
+// out-of-line general-range step (one copy; taken only when a fast range condition failed)
+__device__ __noinline__ void dop853_step_general(const ChainConst *cc, const StepIn *I, const double *Lp, int ls,
+                                                 StepOut *O)
+{
+    bool unused = false;
+    dop853_step_impl<false>(*cc, *I, Lp, ls, *O, unused);
+}
+
+__device__ __noinline__ void rsf_rhs_general(const ChainConst *c, double L, double mu, double th, double *res)
+{
+    bool unused = false;
+    double rth = 0.0;
+    rsf_rhs<false>(*c, L, mu, th, rth, res[0], res[1], res[2], unused);
+    res[3] = rth;
+}
+
+// single evaluation with fallback (start value, hinit probe, FSAL)
+__device__ __forceinline__ void rsf_rhs_checked(const ChainConst &c, double L, double mu, double th, double &rth,
+                                                double &dmu, double &dth, double &dV)
+{
+    bool bad = false;
+    rsf_rhs<true>(c, L, mu, th, rth, dmu, dth, dV, bad);
+    if (bad) {
+        double res[4];
+        rsf_rhs_general(&c, L, mu, th, res);
+        dmu = res[0]; dth = res[1]; dV = res[2]; rth = res[3];
     }
 }
 
@@ -237,26 +409,46 @@ struct SolveOut {
     uint32_t nrhs, nstep;
 };
 
-// Integrate one chain over the whole output grid.  All 32 lanes of a warp must
-// call this together (it contains warp collectives) and all threads of a block
-// must call it together when `series.g != nullptr` (block barriers at tile
-// boundaries).  `active` = this lane owns a real chain.
+constexpr int LTAB_STRIDE = 12;     // doubles per warp in the shared stage-value table
+
+// Per-block shared scratch for the stage values of L: one shared table per warp (filled by lanes
+// 0..10, one exp + one sin per warp and step) and a private column per thread for lanes whose
+// (t, h) differs from the table's key (stiff regime).
+struct LoadScratch {
+    double *tab;     // [warps_per_block][LTAB_STRIDE]
+    double *priv;    // [11][blockDim.x]
+};
+
+// Integrate one chain over the whole output grid.  All 32 lanes of a warp must call this together
+// (it contains warp collectives) and all threads of a block must call it together when
+// `series.g != nullptr` (block barriers at tile boundaries).  `active` = this lane owns a chain.
 // acc_out / t_out (optional) are written time-major with stride `acc_stride` (= C).
-// acc_ref (optional, same layout) and xtx: if acc_ref != nullptr the solve also
-// accumulates xtx += ((acc - acc_ref[k]) / fd_den)^2  (MCMC.py:264-265).
+// acc_ref (optional, same layout): the solve also accumulates xtx += ((acc - acc_ref[k]) / fd_den)^2
+// (MCMC.py:264-265).
+// sse_limit: the partial sums of squares only grow with k, so once they exceed the Metropolis
+// threshold SS_cur - 2 sigma^2 ln U the proposal is certainly rejected (MCMC.py:327-331 with U drawn
+// first); the lane stops integrating there (`out.status |= RSFM_CHAIN_EARLY`, sse = partial > limit).
+// The accept/reject decision is exactly the one the full solve would give.  A warp leaves the
+// output loop when all its lanes are finished (resident series only: no block barriers pending).
 __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double b, double dc, bool active,
-                                               SeriesStage &series, double *acc_out, const double *acc_ref,
-                                               size_t acc_stride, double fd_den, double *xtx_out,
-                                               double *t_out = nullptr)
+                                               SeriesStage &series, const LoadScratch &ls, double *acc_out,
+                                               const double *acc_ref, size_t acc_stride, double fd_den,
+                                               double *xtx_out, double *t_out = nullptr,
+                                               double sse_limit = INFINITY)
 {
     const int lane = threadIdx.x & 31;
-    const ChainConst cc = make_chain_const(a, b, dc);
+    const int nthr = blockDim.x;
+    double *wtab = ls.tab + (threadIdx.x >> 5) * LTAB_STRIDE;
+    double *ptab = ls.priv + threadIdx.x;
+    const ChainConst cc = make_chain_const(M, a, b, dc);
     const bool have_data = series.g != nullptr;
+    const bool parity = M.integ_mode == RSFM_INTEG_PARITY;
     const double uround = 2.3e-16, safe = 0.9;
     const double facc1 = 1.0 / 0.3, facc2 = 1.0 / 6.0;
 
     double t = M.t_start;
     double mu = M.mu_t_zero, th = dc / M.V_ref, V = M.V_ref;       // :367-370,377
+    double rth = 1.0 / th;
     double k1m, k1t, k1v;
     SolveOut out;
     out.status = RSFM_CHAIN_OK;
@@ -268,11 +460,30 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
     if (t_out && active) t_out[0] = t;
     if (acc_ref && active) { const double x0 = (0.0 - acc_ref[0]) / fd_den; xtx = x0 * x0; }
 
-    rsf_rhs(M, cc, loading_of(M, t), mu, th, k1m, k1t, k1v);
+    rsf_rhs_checked(cc, loading_of(M, t), mu, th, rth, k1m, k1t, k1v);
     out.nrhs++;
     bool failed = false;
     double vprev = V;
     double h_carry = 0.0;
+
+    // Key (tab_t, tab_h) of the warp's shared table.  It is rebuilt when some lane misses and at
+    // least two lanes would share the new key (always, outside the stiff regime).
+    double tab_t = 0.0, tab_h = -1.0;
+    auto ensure_table = [&](bool want, double hk) {
+        const bool miss = want && !(t == tab_t && hk == tab_h);
+        const unsigned mm = __ballot_sync(FULL_MASK, miss);
+        if (mm != 0) {
+            const int src = __ffs(mm) - 1;
+            const double nt = __shfl_sync(FULL_MASK, t, src), nh = __shfl_sync(FULL_MASK, hk, src);
+            const unsigned share = __ballot_sync(FULL_MASK, want && t == nt && hk == nh);
+            if (__popc(share) >= 2) {
+                tab_t = nt; tab_h = nh;
+                __syncwarp();                                      // readers of the old table are done
+                if (lane < 11) wtab[lane] = loading_of(M, __dadd_rn(nt, __dmul_rn(TB.c[lane], nh)));
+                __syncwarp();
+            }
+        }
+    };
 
     for (int k = 1; k < M.n_out; k++) {
         const double dk = have_data ? series.at(k) : 0.0;
@@ -283,42 +494,39 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
         bool reject = false, last = false;
         double h;
 
-        // ---- hinit (dop853.f HINIT, iord = 8) or carried step ----
-        if (M.integ_mode == RSFM_INTEG_PARITY || k == 1) {
+        if (parity || k == 1) {
+            // ---- HINIT (dop853.f, iord = 8).  The common outcome h0 = h = hmax is recognised by
+            // comparisons in the squared / 16th-power domain, without sqrt or division. ----
             const double i0 = 1.0 / (M.atol + M.rtol * fabs(mu));
             const double i1 = 1.0 / (M.atol + M.rtol * fabs(th));
             const double i2 = 1.0 / (M.atol + M.rtol * fabs(V));
             const double dnf = (k1m * i0) * (k1m * i0) + (k1t * i1) * (k1t * i1) + (k1v * i2) * (k1v * i2);
             const double dny = (mu * i0) * (mu * i0) + (th * i1) * (th * i1) + (V * i2) * (V * i2);
-            double h0 = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : sqrt(dny / dnf) * 0.01;
-            h0 = fmin(h0, hmax);
-            // probe loading at t + h0: shared when the running lanes agree on (t, h0)
-            const unsigned m = __ballot_sync(FULL_MASK, running);
-            double vlp = 0.0;
-            if (m != 0) {
-                const int src = __ffs(m) - 1;
-                const double ts = __shfl_sync(FULL_MASK, t, src), hs = __shfl_sync(FULL_MASK, h0, src);
-                const bool uni = __all_sync(FULL_MASK, !running || (t == ts && h0 == hs));
-                if (uni) {
-                    if (lane == src) vlp = loading_of(M, t + h0);
-                    vlp = __shfl_sync(FULL_MASK, vlp, src);
-                } else if (running) {
-                    vlp = loading_of(M, t + h0);
-                }
-            }
-            double f1m, f1t, f1v;
-            rsf_rhs(M, cc, vlp, mu + h0 * k1m, th + h0 * k1t, f1m, f1t, f1v);
+            double h0;
+            if (dnf <= 1e-10 || dny <= 1e-10) h0 = fmin(1.0e-6, hmax);
+            else if (dny >= dnf * (1.0e4 * hmax * hmax)) h0 = hmax;            // sqrt(dny/dnf)*0.01 >= hmax
+            else h0 = fmin(sqrt(dny / dnf) * 0.01, hmax);
+            // the probe point t + h0 is stage 12 of the step (t, hmax): speculate on that table
+            ensure_table(running, hmax);
+            double Lp = wtab[10];
+            if (running && !(t == tab_t && h0 == tab_h)) Lp = loading_of(M, t + h0);
+            double f1m, f1t, f1v, rprobe = rth;
+            rsf_rhs_checked(cc, Lp, mu + h0 * k1m, th + h0 * k1t, rprobe, f1m, f1t, f1v);
             if (running) out.nrhs++;
             const double e0 = (f1m - k1m) * i0, e1 = (f1t - k1t) * i1, e2 = (f1v - k1v) * i2;
-            const double der2 = sqrt(e0 * e0 + e1 * e1 + e2 * e2) / h0;
-            const double der12 = fmax(fabs(der2), sqrt(dnf));
-            const double h1 = (der12 <= 1e-15) ? fmax(1.0e-6, fabs(h0) * 1.0e-3) : root8(0.01 / der12);
+            const double der2sq = (e0 * e0 + e1 * e1 + e2 * e2) / (h0 * h0);
+            const double d12sq = fmax(der2sq, dnf);                             // der12^2
+            const double hm2 = hmax * hmax, hm4 = hm2 * hm2, hm8 = hm4 * hm4;
+            double h1;
+            if (d12sq <= 1e-30) h1 = fmax(1.0e-6, fabs(h0) * 1.0e-3);
+            else if (d12sq * (hm8 * hm8) <= 1.0e-4) h1 = hmax;                  // (0.01/der12)^(1/8) >= hmax
+            else h1 = root8(0.01 / sqrt(d12sq));
             h = fmin(fmin(100.0 * fabs(h0), h1), hmax);
         } else {
             h = fmin(h_carry, hmax);
         }
 
-        // ---- dp86co step loop ----
+        // ---- dp86co step loop: every iteration is one attempted step of all unfinished lanes ----
         bool done = !running;
         for (;;) {
             if (!done) {
@@ -329,121 +537,52 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
                     nstep_call++;
                 }
             }
-            const unsigned m = __ballot_sync(FULL_MASK, !done);
-            if (m == 0) break;
+            if (__ballot_sync(FULL_MASK, !done) == 0) break;
             const bool stepping = !done;
+            ensure_table(stepping, h);
+            const bool hit = (t == tab_t && h == tab_h);
+            if (stepping && !hit) {
+                // private stage values (this lane is not on the warp's (t, h))
+#pragma unroll 1
+                for (int i = 0; i < 11; i++) ptab[i * nthr] = loading_of(M, __dadd_rn(t, __dmul_rn(TB.c[i], h)));
+            }
+            const double *Lsrc = hit ? wtab : ptab;
+            const int lstride = hit ? 1 : nthr;
 
-            // stage-time loading table, shared across the warp when (t, h) agree
-            const int src = __ffs(m) - 1;
-            const double ts = __shfl_sync(FULL_MASK, t, src), hs = __shfl_sync(FULL_MASK, h, src);
-            const bool uni = __all_sync(FULL_MASK, !stepping || (t == ts && h == hs));
-            double vl_tab = 0.0;
-            if (uni && lane < 11) vl_tab = loading_of(M, __dadd_rn(ts, __dmul_rn(stage_c(lane), hs)));
-#define RSFM_VL(i)                                   \
-    (uni ? __shfl_sync(FULL_MASK, vl_tab, (i))      \
-         : (stepping ? loading_of(M, __dadd_rn(t, __dmul_rn(stage_c(i), h))) : 0.0))
-
-            double k2m, k2t, k3m, k3t, k4m, k4t, k5m, k5t, k6m, k6t, k7m, k7t, k8m, k8t, k9m, k9t, k10m, k10t;
-            double kv, k9v, k12v, bV, eV;
-            // stage 2..5 (their V-derivatives carry zero weight everywhere)
-            rsf_rhs(M, cc, RSFM_VL(0), mu + h * DP_A2_1 * k1m, th + h * DP_A2_1 * k1t, k2m, k2t, kv);
-            rsf_rhs(M, cc, RSFM_VL(1), mu + h * (DP_A3_1 * k1m + DP_A3_2 * k2m),
-                    th + h * (DP_A3_1 * k1t + DP_A3_2 * k2t), k3m, k3t, kv);
-            rsf_rhs(M, cc, RSFM_VL(2), mu + h * (DP_A4_1 * k1m + DP_A4_3 * k3m),
-                    th + h * (DP_A4_1 * k1t + DP_A4_3 * k3t), k4m, k4t, kv);
-            rsf_rhs(M, cc, RSFM_VL(3), mu + h * (DP_A5_1 * k1m + DP_A5_3 * k3m + DP_A5_4 * k4m),
-                    th + h * (DP_A5_1 * k1t + DP_A5_3 * k3t + DP_A5_4 * k4t), k5m, k5t, kv);
-            bV = DP_B1 * k1v;
-            eV = DP_ER1 * k1v;
-            rsf_rhs(M, cc, RSFM_VL(4), mu + h * (DP_A6_1 * k1m + DP_A6_4 * k4m + DP_A6_5 * k5m),
-                    th + h * (DP_A6_1 * k1t + DP_A6_4 * k4t + DP_A6_5 * k5t), k6m, k6t, kv);
-            bV += DP_B6 * kv; eV += DP_ER6 * kv;
-            rsf_rhs(M, cc, RSFM_VL(5), mu + h * (DP_A7_1 * k1m + DP_A7_4 * k4m + DP_A7_5 * k5m + DP_A7_6 * k6m),
-                    th + h * (DP_A7_1 * k1t + DP_A7_4 * k4t + DP_A7_5 * k5t + DP_A7_6 * k6t), k7m, k7t, kv);
-            bV += DP_B7 * kv; eV += DP_ER7 * kv;
-            rsf_rhs(M, cc, RSFM_VL(6),
-                    mu + h * (DP_A8_1 * k1m + DP_A8_4 * k4m + DP_A8_5 * k5m + DP_A8_6 * k6m + DP_A8_7 * k7m),
-                    th + h * (DP_A8_1 * k1t + DP_A8_4 * k4t + DP_A8_5 * k5t + DP_A8_6 * k6t + DP_A8_7 * k7t),
-                    k8m, k8t, kv);
-            bV += DP_B8 * kv; eV += DP_ER8 * kv;
-            rsf_rhs(M, cc, RSFM_VL(7),
-                    mu + h * (DP_A9_1 * k1m + DP_A9_4 * k4m + DP_A9_5 * k5m + DP_A9_6 * k6m + DP_A9_7 * k7m +
-                              DP_A9_8 * k8m),
-                    th + h * (DP_A9_1 * k1t + DP_A9_4 * k4t + DP_A9_5 * k5t + DP_A9_6 * k6t + DP_A9_7 * k7t +
-                              DP_A9_8 * k8t),
-                    k9m, k9t, k9v);
-            bV += DP_B9 * k9v; eV += DP_ER9 * k9v;
-            rsf_rhs(M, cc, RSFM_VL(8),
-                    mu + h * (DP_A10_1 * k1m + DP_A10_4 * k4m + DP_A10_5 * k5m + DP_A10_6 * k6m + DP_A10_7 * k7m +
-                              DP_A10_8 * k8m + DP_A10_9 * k9m),
-                    th + h * (DP_A10_1 * k1t + DP_A10_4 * k4t + DP_A10_5 * k5t + DP_A10_6 * k6t + DP_A10_7 * k7t +
-                              DP_A10_8 * k8t + DP_A10_9 * k9t),
-                    k10m, k10t, kv);
-            bV += DP_B10 * kv; eV += DP_ER10 * kv;
-            // stage 11 -> k2 slot
-            rsf_rhs(M, cc, RSFM_VL(9),
-                    mu + h * (DP_A11_1 * k1m + DP_A11_4 * k4m + DP_A11_5 * k5m + DP_A11_6 * k6m + DP_A11_7 * k7m +
-                              DP_A11_8 * k8m + DP_A11_9 * k9m + DP_A11_10 * k10m),
-                    th + h * (DP_A11_1 * k1t + DP_A11_4 * k4t + DP_A11_5 * k5t + DP_A11_6 * k6t + DP_A11_7 * k7t +
-                              DP_A11_8 * k8t + DP_A11_9 * k9t + DP_A11_10 * k10t),
-                    k2m, k2t, kv);
-            bV += DP_B11 * kv; eV += DP_ER11 * kv;
-            // stage 12 -> k3 slot, at xph = t + h
-            const double vl12 = RSFM_VL(10);
-            const double xph = t + h;
-            rsf_rhs(M, cc, vl12,
-                    mu + h * (DP_A12_1 * k1m + DP_A12_4 * k4m + DP_A12_5 * k5m + DP_A12_6 * k6m + DP_A12_7 * k7m +
-                              DP_A12_8 * k8m + DP_A12_9 * k9m + DP_A12_10 * k10m + DP_A12_11 * k2m),
-                    th + h * (DP_A12_1 * k1t + DP_A12_4 * k4t + DP_A12_5 * k5t + DP_A12_6 * k6t + DP_A12_7 * k7t +
-                              DP_A12_8 * k8t + DP_A12_9 * k9t + DP_A12_10 * k10t + DP_A12_11 * k2t),
-                    k3m, k3t, k12v);
-            bV += DP_B12 * k12v; eV += DP_ER12 * k12v;
-#undef RSFM_VL
-            // 8th-order increment and new state
-            const double bM = DP_B1 * k1m + DP_B6 * k6m + DP_B7 * k7m + DP_B8 * k8m + DP_B9 * k9m + DP_B10 * k10m +
-                              DP_B11 * k2m + DP_B12 * k3m;
-            const double bT = DP_B1 * k1t + DP_B6 * k6t + DP_B7 * k7t + DP_B8 * k8t + DP_B9 * k9t + DP_B10 * k10t +
-                              DP_B11 * k2t + DP_B12 * k3t;
-            const double muN = mu + h * bM, thN = th + h * bT, VN = V + h * bV;
-            // error estimate
-            const double s0 = 1.0 / (M.atol + M.rtol * fmax(fabs(mu), fabs(muN)));
-            const double s1 = 1.0 / (M.atol + M.rtol * fmax(fabs(th), fabs(thN)));
-            const double s2 = 1.0 / (M.atol + M.rtol * fmax(fabs(V), fabs(VN)));
-            const double e3m = (bM - DP_BHH1 * k1m - DP_BHH2 * k9m - DP_BHH3 * k3m) * s0;
-            const double e3t = (bT - DP_BHH1 * k1t - DP_BHH2 * k9t - DP_BHH3 * k3t) * s1;
-            const double e3v = (bV - DP_BHH1 * k1v - DP_BHH2 * k9v - DP_BHH3 * k12v) * s2;
-            const double e5m = (DP_ER1 * k1m + DP_ER6 * k6m + DP_ER7 * k7m + DP_ER8 * k8m + DP_ER9 * k9m +
-                                DP_ER10 * k10m + DP_ER11 * k2m + DP_ER12 * k3m) * s0;
-            const double e5t = (DP_ER1 * k1t + DP_ER6 * k6t + DP_ER7 * k7t + DP_ER8 * k8t + DP_ER9 * k9t +
-                                DP_ER10 * k10t + DP_ER11 * k2t + DP_ER12 * k3t) * s1;
-            const double e5v = eV * s2;
-            const double err2 = e3m * e3m + e3t * e3t + e3v * e3v;
-            double err = e5m * e5m + e5t * e5t + e5v * e5v;
-            double deno = err + 0.01 * err2;
-            if (deno <= 0.0) deno = 1.0;
-            err = fabs(h) * err * sqrt(1.0 / (3.0 * deno));
+            StepIn in;
+            in.h = h; in.mu = mu; in.th = th; in.V = V; in.k1m = k1m; in.k1t = k1t; in.k1v = k1v; in.rth = rth;
+            in.atol = M.atol; in.rtol = M.rtol;
+            StepOut so;
+            bool bad = false;
+            dop853_step_impl<true>(cc, in, Lsrc, lstride, so, bad);
+            if (stepping && bad) dop853_step_general(&cc, &in, Lsrc, lstride, &so);
+            // err = |h| errs sqrt(1/(3 deno)) <= 1   <=>   h^2 errs^2 <= 3 deno   (no sqrt needed)
+            const bool accept = (h * h) * (so.errs * so.errs) <= 3.0 * so.deno;
 
             if (stepping) {
                 out.nstep++;
                 out.nrhs += 11;
-                if (err <= 1.0) {
-                    // accepted: FSAL evaluation f(xph, ynew) becomes the next k1
-                    rsf_rhs(M, cc, vl12, muN, thN, k1m, k1t, k1v);
+                if (accept) {
+                    // FSAL: f(x + h, y_new) is k1 of the next step and of the next interval's restart
+                    rth = so.rth;
+                    rsf_rhs_checked(cc, so.L12, so.muN, so.thN, rth, k1m, k1t, k1v);
                     out.nrhs++;
-                    mu = muN; th = thN; V = VN; t = xph;
-                    const bool need_hnew = !last || M.integ_mode == RSFM_INTEG_CARRY;
-                    double hnew = h;
-                    if (need_hnew) {
+                    const double hold = h;
+                    mu = so.muN; th = so.thN; V = so.VN; t = t + h;
+                    // the controller's h_new is only consumed when the step does not end the
+                    // interval, or when the step size is carried across output points
+                    if (!last || !parity) {
+                        const double err = fabs(hold) * so.errs * sqrt(1.0 / (3.0 * so.deno));
                         const double fac = fmax(facc2, fmin(facc1, root8(err) / safe));
-                        hnew = h / fac;
+                        double hnew = hold / fac;
                         if (fabs(hnew) > hmax) hnew = hmax;
-                        if (reject) hnew = fmin(fabs(hnew), fabs(h));
+                        if (reject) hnew = fmin(fabs(hnew), fabs(hold));
+                        h = hnew;
                     }
                     reject = false;
-                    if (last) { done = true; h_carry = hnew; }
-                    h = hnew;
+                    if (last) { done = true; h_carry = h; }
                 } else {
-                    // rejected (also err = NaN).  SciPy 1.18.1's dop853 shrinks by 1/facc1 here.
+                    // rejected (also NaN).  SciPy 1.18.1's dop853 shrinks by exactly 1/facc1 here.
                     h = h / facc1;
                     reject = true;
                     last = false;
@@ -456,9 +595,11 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
         if (running) {
             accv = (V - vprev) / M.delta_t;
             vprev = V;
-            if (failed) out.filled = k + 1;
+            if (failed && out.filled == M.n_out) out.filled = k + 1;
         }
         if (have_data) { const double e = accv - dk; sse += e * e; }
+        if (running && sse > sse_limit) { failed = true; out.status |= RSFM_CHAIN_EARLY; }
+        if (series.resident && __all_sync(FULL_MASK, !active || (failed && (out.status & RSFM_CHAIN_EARLY)))) break;
         if (active) {
             if (acc_out) acc_out[(size_t)k * acc_stride] = accv;
             if (t_out) t_out[(size_t)k * acc_stride] = running ? t : 0.0;

@@ -11,6 +11,7 @@
 //   dfma_peak_kernel     FP64 roofline denominator
 // (a-numbers: SURVEY.md section 8a.)
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <mutex>
@@ -119,6 +120,10 @@ static ModelK make_model(const rsfm_cfg *c)
 // bound there), large batches use 128-thread blocks.
 static int pick_block(int C)
 {
+    if (const char *e = getenv("RSFM_BLOCK")) {          // tuning / experiments only
+        const int b = atoi(e);
+        if (b == 32 || b == 64 || b == 96 || b == 128) return b;
+    }
     if (C <= 148 * 32) return 32;
     if (C <= 148 * 64 * 2) return 64;
     return 128;
@@ -137,6 +142,10 @@ rsf_forward_kernel(ModelK M, int C, double a0, double b0, const double *__restri
 {
     __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ double s_ltab[4 * LTAB_STRIDE];
+    __shared__ double s_lpriv[11 * 128];
+    LoadScratch lscr;
+    lscr.tab = s_ltab; lscr.priv = s_lpriv;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = c < C;
     const int cc = active ? c : C - 1;
@@ -146,7 +155,7 @@ rsf_forward_kernel(ModelK M, int C, double a0, double b0, const double *__restri
     SeriesStage series;
     series.begin(s_tile, s_bar, data, M.n_out);
     series.start_solve();
-    SolveOut o = rsf_solve(M, a, b, dc, active, series, acc_out ? acc_out + cc : nullptr, nullptr, (size_t)C,
+    SolveOut o = rsf_solve(M, a, b, dc, active, series, lscr, acc_out ? acc_out + cc : nullptr, nullptr, (size_t)C,
                            1.0, nullptr, t_out ? t_out + cc : nullptr);
     if (active) {
         if (sse_out) sse_out[c] = o.sse;
@@ -194,6 +203,7 @@ struct SamplerDev {
     unsigned long long *nrhs;      // [C]
     unsigned long long *nstep;     // [C]
     unsigned long long *nsolve;    // [C] forward solves executed
+    unsigned long long *nearly;    // [C] of which stopped early (rejection certain)
 };
 
 struct rsfm_sampler {
@@ -242,6 +252,7 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     alloc((void **)&s->d.nrhs, sizeof(unsigned long long) * Cz);
     alloc((void **)&s->d.nstep, sizeof(unsigned long long) * Cz);
     alloc((void **)&s->d.nsolve, sizeof(unsigned long long) * Cz);
+    alloc((void **)&s->d.nearly, sizeof(unsigned long long) * Cz);
     alloc((void **)&s->totals, sizeof(unsigned long long) * 8);
     alloc((void **)&s->reduce_out, sizeof(double) * 16);
     if (!ok) {
@@ -257,7 +268,7 @@ extern "C" void rsfm_destroy(rsfm_sampler *s)
     if (!s) return;
     cudaFree(s->d.q); cudaFree(s->d.sse); cudaFree(s->d.sigma2); cudaFree(s->d.chol); cudaFree(s->d.ring);
     cudaFree(s->d.suff); cudaFree(s->d.data); cudaFree(s->d.accepted); cudaFree(s->d.status);
-    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->d.nsolve); cudaFree(s->scratch);
+    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->d.nsolve); cudaFree(s->d.nearly); cudaFree(s->scratch);
     cudaFree(s->reduce_out); cudaFree(s->totals);
     delete s;
 }
@@ -278,6 +289,10 @@ rsf_init_kernel(ModelK M, int C, int pass, double a0, double b0, int n_prior_len
 {
     __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ double s_ltab[4 * LTAB_STRIDE];
+    __shared__ double s_lpriv[11 * 128];
+    LoadScratch lscr;
+    lscr.tab = s_ltab; lscr.priv = s_lpriv;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = c < C;
     const int cc = active ? c : C - 1;
@@ -297,24 +312,21 @@ rsf_init_kernel(ModelK M, int C, int pass, double a0, double b0, int n_prior_len
     series.start_solve();
     const size_t plane = (size_t)M.n_out * C;
     double xtx = 0.0;
-    if (pass == 0) {
-        SolveOut o = rsf_solve(M, a, b, dc, active, series, scratch + cc, nullptr, (size_t)C, 1.0, nullptr);
-        if (active) {
+    // one call site (one copy of the solver): what is written / compared is chosen by pointers
+    //   pass 0          : trajectory -> scratch plane 0, SSE against the data
+    //   pass 1, d = 1   : compared on the fly with plane 0 (X'X accumulates inside the solve)
+    //   pass j, d = 3   : trajectory -> scratch plane j (combined by rsf_init_finish_kernel)
+    double *wr = (pass == 0) ? scratch + cc : (D == 1 ? nullptr : scratch + (size_t)pass * plane + cc);
+    const double *rd = (pass > 0 && D == 1) ? scratch + cc : nullptr;
+    SolveOut o = rsf_solve(M, a, b, dc, active, series, lscr, wr, rd, (size_t)C, fd_den, &xtx);
+    if (active) {
+        if (pass == 0) {
             S.sse[c] = o.sse;
             S.sigma2[c] = o.sse / (double)(M.n_out - n_prior_len);     // :261
-            S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; S.nsolve[c] += 1;
-        }
-    } else if (D == 1) {
-        SolveOut o = rsf_solve(M, a, b, dc, active, series, nullptr, scratch + cc, (size_t)C, fd_den, &xtx);
-        if (active) {
+        } else if (D == 1) {
             S.chol[c] = S.sigma2[c] * (1.0 / xtx);                     // Vstart, :265-266
-            S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; S.nsolve[c] += 1;
         }
-    } else {
-        // d = 3: write the perturbed trajectory; columns are combined by rsf_init_finish_kernel
-        SolveOut o = rsf_solve(M, a, b, dc, active, series, scratch + (size_t)pass * plane + cc, nullptr,
-                               (size_t)C, 1.0, nullptr);
-        if (active) { S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; S.nsolve[c] += 1; }
+        S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; S.nsolve[c] += 1;
     }
 }
 
@@ -379,6 +391,7 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     CUDA_TRY(cudaMemsetAsync(s->d.nrhs, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.nstep, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.nsolve, 0, sizeof(unsigned long long) * C, stream));
+    CUDA_TRY(cudaMemsetAsync(s->d.nearly, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * (d + tri(d)) * (size_t)C, stream));
     const int block = pick_block(C), grid = (C + block - 1) / block;
     const ModelK M = make_model(&s->cfg);
@@ -430,12 +443,16 @@ struct RunArgs {
     int adapt_mode, adapt_interval;
 };
 
-template <int D>
+template <int D, bool DET>
 __global__ void __launch_bounds__(128)
 rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
 {
     __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ double s_ltab[4 * LTAB_STRIDE];
+    __shared__ double s_lpriv[11 * 128];
+    LoadScratch lscr;
+    lscr.tab = s_ltab; lscr.priv = s_lpriv;
     constexpr int T = D * (D + 1) / 2;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = c < C;
@@ -450,7 +467,7 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
     double ss = S.sse[cc], s2 = S.sigma2[cc];
     unsigned int n_acc = 0;
     unsigned long long nrhs = 0, nstep = 0;
-    unsigned int nsolve = 0;
+    unsigned int nsolve = 0, nearly = 0;
     int status = 0;
     const unsigned long long gid = A.chain_id0 + (unsigned long long)cc;
     const PhiloxKey key = philox_key(A.seed);
@@ -458,16 +475,17 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
     SeriesStage series;
     series.begin(s_tile, s_bar, S.data, M.n_out);
 
+#pragma unroll 1
     for (int it = 0; it < A.n_iters; it++) {
         const unsigned int giter = (unsigned int)(A.iter0 + it);
         // ---- proposal (MCMC.py:497) ----
         double qn[D];
-        if (A.deterministic && !A.proposals_are_z) {
+        if (DET && !A.proposals_are_z) {
 #pragma unroll
             for (int j = 0; j < D; j++) qn[j] = A.proposals[((size_t)it * D + j) * Cz + cc];
         } else {
             double z[D];
-            if (A.deterministic) {
+            if (DET) {
 #pragma unroll
                 for (int j = 0; j < D; j++) z[j] = A.proposals[((size_t)it * D + j) * Cz + cc];
             } else {
@@ -490,23 +508,31 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
 #pragma unroll
         for (int j = 0; j < D; j++) inb = inb && (qn[j] > A.lo[j]) && (qn[j] < A.hi[j]);
         const bool solve = active && inb;
-        // ---- forward solve + SSE (MCMC.py:324, 381-387) ----
+        // ---- acceptance uniform first (MCMC.py:331): it fixes the rejection threshold ----
+        // accept  <=>  min(0, 0.5 (SS - SS')/s2) > ln U  <=>  SS' < SS - 2 s2 ln U   (ln U < 0)
+        double u = nan("");
+        double lnu = 0.0;
+        if (solve) {
+            if (DET) u = A.uniforms[(size_t)it * Cz + cc];
+            else u = philox_uniform(key, gid, giter, 2u);
+            lnu = log(u);
+        }
+        const double sse_limit = solve ? ss - 2.0 * s2 * lnu : INFINITY;
+        // ---- forward solve + SSE (MCMC.py:324, 381-387), stopped early once rejection is certain ----
         const double pa = (D == 3) ? qn[0] : A.a0;
         const double pb = (D == 3) ? qn[1] : A.b0;
         const double pdc = solve ? qn[D - 1] : q[D - 1];
         series.start_solve();
         SolveOut o = rsf_solve(M, solve ? pa : ((D == 3) ? q[0] : A.a0), solve ? pb : ((D == 3) ? q[1] : A.b0), pdc,
-                               solve, series, nullptr, nullptr, Cz, 1.0, nullptr);
+                               solve, series, lscr, nullptr, nullptr, Cz, 1.0, nullptr, nullptr, sse_limit);
         // ---- accept / reject (MCMC.py:327-331) ----
         bool acc = false;
-        double u = nan("");
         if (solve) {
-            nrhs += o.nrhs; nstep += o.nstep; status |= o.status; nsolve++;
-            if (A.deterministic) u = A.uniforms[(size_t)it * Cz + cc];
-            else u = philox_uniform(key, gid, giter, 2u);
+            nrhs += o.nrhs; nstep += o.nstep; status |= (o.status & ~RSFM_CHAIN_EARLY); nsolve++;
+            if (o.status & RSFM_CHAIN_EARLY) nearly++;
             double la = 0.5 * (ss - o.sse) / s2;
             if (la > 0.0) la = 0.0;
-            acc = la > log(u);
+            acc = la > lnu;
             if (acc) {
 #pragma unroll
                 for (int j = 0; j < D; j++) q[j] = qn[j];
@@ -516,7 +542,7 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
         }
         // ---- sigma^2 Gibbs draw (MCMC.py:158-160) ----
         double g0;
-        if (A.deterministic) g0 = A.gammas[(size_t)it * Cz + cc];
+        if (DET) g0 = A.gammas[(size_t)it * Cz + cc];
         else g0 = philox_gamma(key, gid, giter, gshape);
         {
             const double bval = 0.5 * (A.n0 * s2 + ss);
@@ -577,7 +603,7 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
         for (int j = 0; j < T; j++) S.chol[j * Cz + c] = L[j];
         S.sse[c] = ss; S.sigma2[c] = s2;
         S.accepted[c] += n_acc;
-        S.nrhs[c] += nrhs; S.nstep[c] += nstep; S.status[c] |= status; S.nsolve[c] += nsolve;
+        S.nrhs[c] += nrhs; S.nstep[c] += nstep; S.status[c] |= status; S.nsolve[c] += nsolve; S.nearly[c] += nearly;
         if (A.adapt_mode == RSFM_ADAPT_POOLED) {
 #pragma unroll
             for (int j = 0; j < D; j++) S.suff[j * Cz + c] += sq[j];
@@ -597,8 +623,13 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
     for (int i = 0; i < RSFM_MAX_PARAMS; i++) { A.lo[i] = s->cfg.lo[i]; A.hi[i] = s->cfg.hi[i]; }
     A.adapt_mode = s->cfg.adapt_mode; A.adapt_interval = s->cfg.adapt_interval;
     const ModelK M = make_model(&s->cfg);
-    if (s->cfg.n_params == 1) rsf_mcmc_kernel<1><<<grid, block, 0, stream>>>(M, C, s->d, A);
-    else rsf_mcmc_kernel<3><<<grid, block, 0, stream>>>(M, C, s->d, A);
+    if (s->cfg.n_params == 1) {
+        if (A.deterministic) rsf_mcmc_kernel<1, true><<<grid, block, 0, stream>>>(M, C, s->d, A);
+        else rsf_mcmc_kernel<1, false><<<grid, block, 0, stream>>>(M, C, s->d, A);
+    } else {
+        if (A.deterministic) rsf_mcmc_kernel<3, true><<<grid, block, 0, stream>>>(M, C, s->d, A);
+        else rsf_mcmc_kernel<3, false><<<grid, block, 0, stream>>>(M, C, s->d, A);
+    }
     CUDA_TRY(cudaGetLastError());
     s->iteration += A.n_iters;
     if (s->cfg.adapt_mode == RSFM_ADAPT_POOLED) s->suff_count += A.n_iters;
@@ -672,13 +703,13 @@ extern "C" int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double
 // ---------------------------------------------------------------------------
 __global__ void totals_kernel(int C, SamplerDev S, unsigned long long *__restrict__ out)
 {
-    unsigned long long v[5] = {0, 0, 0, 0, 0};
+    unsigned long long v[6] = {0, 0, 0, 0, 0, 0};
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
         v[0] += S.nsolve[c]; v[1] += S.nrhs[c]; v[2] += S.nstep[c]; v[3] += S.accepted[c];
-        v[4] += S.status[c] != 0 ? 1 : 0;
+        v[4] += S.status[c] != 0 ? 1 : 0; v[5] += S.nearly[c];
     }
 #pragma unroll
-    for (int j = 0; j < 5; j++) {
+    for (int j = 0; j < 6; j++) {
         for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_down_sync(FULL_MASK, v[j], o);
         if ((threadIdx.x & 31) == 0 && v[j]) atomicAdd(&out[j], v[j]);
     }
@@ -692,7 +723,7 @@ extern "C" int rsfm_get_totals(rsfm_sampler *s, uint64_t *out_host, void *stream
     const int grid = (s->C + 255) / 256 < 592 ? (s->C + 255) / 256 : 592;
     totals_kernel<<<grid, 256, 0, st>>>(s->C, s->d, s->totals);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(out_host, s->totals, sizeof(uint64_t) * 5, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_host, s->totals, sizeof(uint64_t) * 6, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return RSFM_OK;
 }

@@ -45,6 +45,8 @@ def chain_diagnostics(samples, max_lag=None):
         for p in range(d):
             sums = torch.zeros(8, dtype=torch.float64, device=dev)
             for h, (lo, hi) in enumerate(((0, half), (n - half, n))):
+                if half < 2:
+                    break                                   # too few draws for split-R-hat (reported as NaN)
                 _lib.check(lib.rsfm_chain_diagnostics(_lib.ptr(samples[lo:hi]), hi - lo, d, c, p, 0,
                                                       _lib.ptr(mean), _lib.ptr(var), None, stream),
                            "rsfm_chain_diagnostics")
@@ -60,7 +62,7 @@ def chain_diagnostics(samples, max_lag=None):
             sums[7] = (var * (n - 1) + n * mean * mean).sum()        # sum of x^2 over all draws
             all_reduce_sum_(sums)
             s = sums.cpu().numpy()
-            out["rhat"].append(rhat_from_sums(s[0], half, s[1], s[2], s[3]))
+            out["rhat"].append(rhat_from_sums(s[0], half, s[1], s[2], s[3]) if half >= 2 else float("nan"))
             out["ess"].append(float(s[4]))
             out["ess_per_chain_mean"].append(float(s[4] / s[5]))
             gmean = s[6] / s[5]

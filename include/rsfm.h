@@ -53,7 +53,8 @@ enum { RSFM_ADAPT_NONE = 0,        /* list-typed priors: update silently dead (q
 enum { RSFM_CHAIN_OK = 0,
        RSFM_CHAIN_NMAX = 2,        /* dop853 idid = -2, "larger nsteps is needed" (quirk q9) */
        RSFM_CHAIN_HSMALL = 3,      /* dop853 idid = -3 */
-       RSFM_CHAIN_NONFINITE = 4 };
+       RSFM_CHAIN_NONFINITE = 4,
+       RSFM_CHAIN_EARLY = 8 };     /* solver-internal: proposal rejected before the end of the series */
 
 /* Model + solver constants.  Defaults (rsfm_cfg_defaults) are the reference's
  * RateStateModel.py:5-11,167-184 and the tolerances of :374. */
@@ -148,8 +149,9 @@ int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double *sse_dev,
 int64_t rsfm_iteration(const rsfm_sampler *s);
 
 /* Work totals since rsfm_init, summed over chains on the device and copied to
- * out_host[5] = (forward solves executed, RHS evaluations, attempted steps,
- * accepted moves, chains with a non-zero status).  Synchronises the stream. */
+ * out_host[6] = (forward solves started, RHS evaluations, attempted steps,
+ * accepted moves, chains with a non-zero status, solves stopped early because
+ * rejection was already certain).  Synchronises the stream. */
 int rsfm_get_totals(rsfm_sampler *s, uint64_t *out_host, void *stream);
 
 /* Pooled adaptation (extension): local sufficient
