@@ -32,9 +32,9 @@ def proposal_from_suffstats(s, d):
     """
     n, mean, cov = moments_from_suffstats(s, d)
     v = (2.38 ** 2 / d) * cov
-    v = v + np.diag(EPS_REL * np.maximum(np.diag(v), 1e-300))
-    if not np.all(np.isfinite(v)):
-        return None
+    if not np.all(np.isfinite(v)) or np.any(np.diag(v) <= 0.0):
+        return None                      # degenerate moments: keep the current proposal (cf. quirk q4)
+    v = v + np.diag(EPS_REL * np.diag(v))
     if d == 1:
         return np.array([v[0, 0]]) if v[0, 0] > 0 else None
     try:
