@@ -290,7 +290,8 @@ __device__ __forceinline__ double root8(double x) { return sqrt(sqrt(sqrt(x))); 
 // One attempted DOP853 step (stages 2..12, 8th-order solution, error forms).  Lp points at the
 // eleven stage values of L (stride ls doubles, shared memory).
 struct StepIn { double h, mu, th, V, k1m, k1t, k1v, rth, atol, rtol; };
-struct StepOut { double muN, thN, VN, errs, deno, L12, rth; };
+// err = |h| ||e5||^2 / sqrt(3 (||e5||^2 + 0.01 ||e3||^2)) = |h| errA / sqrt(den3)   (dop853.f, n = 3)
+struct StepOut { double muN, thN, VN, errA, den3, L12, rth; };
 
 template <bool FAST>
 __device__ __forceinline__ void dop853_step_impl(const ChainConst &cc, const StepIn &I, const double *Lp, int ls,
@@ -355,22 +356,25 @@ __device__ __forceinline__ void dop853_step_impl(const ChainConst &cc, const Ste
     const double bT = TB.b1 * k1t + TB.b6 * k6t + TB.b7 * k7t + TB.b8 * k8t + TB.b9 * k9t + TB.b10 * k10t +
                       TB.b11 * k2t + TB.b12 * k3t;
     const double muN = mu + h * bM, thN = th + h * bT, VN = I.V + h * bV;
-    const double s0 = 1.0 / (I.atol + I.rtol * fmax(fabs(mu), fabs(muN)));
-    const double s1 = 1.0 / (I.atol + I.rtol * fmax(fabs(th), fabs(thN)));
-    const double s2 = 1.0 / (I.atol + I.rtol * fmax(fabs(I.V), fabs(VN)));
-    const double e3m = (bM - TB.bhh1 * k1m - TB.bhh2 * k9m - TB.bhh3 * k3m) * s0;
-    const double e3t = (bT - TB.bhh1 * k1t - TB.bhh2 * k9t - TB.bhh3 * k3t) * s1;
-    const double e3v = (bV - TB.bhh1 * k1v - TB.bhh2 * k9v - TB.bhh3 * k12v) * s2;
+    // error norms over the common denominator D = (sk0 sk1 sk2)^2 (no divisions):
+    //   ||e5/sk||^2 = A/D, ||e3/sk||^2 = B/D  with  A = sum (e5_i p_i)^2,  p_i = prod_{j != i} sk_j
+    const double k0 = I.atol + I.rtol * fmax(fabs(mu), fabs(muN));
+    const double k1 = I.atol + I.rtol * fmax(fabs(th), fabs(thN));
+    const double k2 = I.atol + I.rtol * fmax(fabs(I.V), fabs(VN));
+    const double p0 = k1 * k2, p1 = k0 * k2, p2 = k0 * k1;
+    const double dd = k0 * p0;
+    const double e3m = (bM - TB.bhh1 * k1m - TB.bhh2 * k9m - TB.bhh3 * k3m) * p0;
+    const double e3t = (bT - TB.bhh1 * k1t - TB.bhh2 * k9t - TB.bhh3 * k3t) * p1;
+    const double e3v = (bV - TB.bhh1 * k1v - TB.bhh2 * k9v - TB.bhh3 * k12v) * p2;
     const double e5m = (TB.e1 * k1m + TB.e6 * k6m + TB.e7 * k7m + TB.e8 * k8m + TB.e9 * k9m + TB.e10 * k10m +
-                        TB.e11 * k2m + TB.e12 * k3m) * s0;
+                        TB.e11 * k2m + TB.e12 * k3m) * p0;
     const double e5t = (TB.e1 * k1t + TB.e6 * k6t + TB.e7 * k7t + TB.e8 * k8t + TB.e9 * k9t + TB.e10 * k10t +
-                        TB.e11 * k2t + TB.e12 * k3t) * s1;
-    const double e5v = eV * s2;
-    const double err2 = e3m * e3m + e3t * e3t + e3v * e3v;
-    const double errs = e5m * e5m + e5t * e5t + e5v * e5v;
-    double deno = errs + 0.01 * err2;
-    if (deno <= 0.0) deno = 1.0;
-    O.muN = muN; O.thN = thN; O.VN = VN; O.errs = errs; O.deno = deno; O.L12 = L12; O.rth = rth;
+                        TB.e11 * k2t + TB.e12 * k3t) * p1;
+    const double e5v = eV * p2;
+    const double B = e3m * e3m + e3t * e3t + e3v * e3v;
+    const double A = e5m * e5m + e5t * e5t + e5v * e5v;
+    O.muN = muN; O.thN = thN; O.VN = VN; O.errA = A; O.den3 = 3.0 * (A + 0.01 * B) * (dd * dd); O.L12 = L12;
+    O.rth = rth;
 }
 
 // out-of-line general-range step (one copy; taken only when a fast range condition failed)
@@ -409,14 +413,19 @@ struct SolveOut {
     uint32_t nrhs, nstep;
 };
 
-constexpr int LTAB_STRIDE = 12;     // doubles per warp in the shared stage-value table
+constexpr int LTAB_STRIDE = 16;     // doubles per warp in the shared stage-value table (13 used)
+constexpr int NOM_STRIDE = 16;      // doubles per interval in the precomputed nominal table
 
 // Per-block shared scratch for the stage values of L: one shared table per warp (filled by lanes
 // 0..10, one exp + one sin per warp and step) and a private column per thread for lanes whose
 // (t, h) differs from the table's key (stiff regime).
 struct LoadScratch {
-    double *tab;     // [warps_per_block][LTAB_STRIDE]
-    double *priv;    // [11][blockDim.x]
+    double *tab;        // [warps_per_block][LTAB_STRIDE]
+    double *priv;       // [11][blockDim.x]
+    const double *nom;  // global [n_out][NOM_STRIDE] or nullptr: nominal table built by loading_table_kernel.
+                        // Entry k = stage values of L for the single step that covers output interval k on the
+                        // nominal time grid (t_k, h_k = (t_k + delta_t) - t_k), then the key t_k, h_k.  Outside the
+                        // stiff regime every chain walks exactly this grid, so no exp/sin is evaluated in the solve.
 };
 
 // Integrate one chain over the whole output grid.  All 32 lanes of a warp must call this together
@@ -485,9 +494,20 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
         }
     };
 
+    const double *nom = ls.nom;
+    double pre = (nom != nullptr && lane < 13 && M.n_out > 1) ? nom[NOM_STRIDE + lane] : 0.0;
+
     for (int k = 1; k < M.n_out; k++) {
         const double dk = have_data ? series.at(k) : 0.0;
         const bool running = active && !failed;
+        if (nom != nullptr) {
+            // install the nominal entry of this interval (fetched one interval ahead) as the warp's table
+            __syncwarp();
+            if (lane < 13) wtab[lane] = pre;
+            __syncwarp();
+            tab_t = wtab[11]; tab_h = wtab[12];
+            if (lane < 13 && k + 1 < M.n_out) pre = nom[(size_t)(k + 1) * NOM_STRIDE + lane];
+        }
         const double xend = t + M.delta_t;                         // :382
         const double hmax = fabs(xend - t);
         int nstep_call = 0;
@@ -497,15 +517,17 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
         if (parity || k == 1) {
             // ---- HINIT (dop853.f, iord = 8).  The common outcome h0 = h = hmax is recognised by
             // comparisons in the squared / 16th-power domain, without sqrt or division. ----
-            const double i0 = 1.0 / (M.atol + M.rtol * fabs(mu));
-            const double i1 = 1.0 / (M.atol + M.rtol * fabs(th));
-            const double i2 = 1.0 / (M.atol + M.rtol * fabs(V));
-            const double dnf = (k1m * i0) * (k1m * i0) + (k1t * i1) * (k1t * i1) + (k1v * i2) * (k1v * i2);
-            const double dny = (mu * i0) * (mu * i0) + (th * i1) * (th * i1) + (V * i2) * (V * i2);
-            double h0;
-            if (dnf <= 1e-10 || dny <= 1e-10) h0 = fmin(1.0e-6, hmax);
-            else if (dny >= dnf * (1.0e4 * hmax * hmax)) h0 = hmax;            // sqrt(dny/dnf)*0.01 >= hmax
-            else h0 = fmin(sqrt(dny / dnf) * 0.01, hmax);
+            // Norms over the common denominator D = (sk0 sk1 sk2)^2:  ||f/sk||^2 = Nf/D etc.
+            const double k0 = M.atol + M.rtol * fabs(mu), k1 = M.atol + M.rtol * fabs(th), k2 = M.atol + M.rtol * fabs(V);
+            const double p0 = k1 * k2, p1 = k0 * k2, p2 = k0 * k1;
+            const double dd = k0 * p0, D = dd * dd;
+            const double Nf = (k1m * p0) * (k1m * p0) + (k1t * p1) * (k1t * p1) + (k1v * p2) * (k1v * p2);
+            const double Ny = (mu * p0) * (mu * p0) + (th * p1) * (th * p1) + (V * p2) * (V * p2);
+            // h0 = min(0.01 sqrt(dny/dnf), hmax)  (1e-6 when either norm^2 <= 1e-10)
+            const bool tiny = (Nf <= 1e-10 * D) || (Ny <= 1e-10 * D);
+            const bool h0max = !tiny && (Ny >= Nf * (1.0e4 * hmax * hmax));
+            double h0 = hmax;
+            if (!h0max) h0 = tiny ? fmin(1.0e-6, hmax) : fmin(sqrt(Ny / Nf) * 0.01, hmax);
             // the probe point t + h0 is stage 12 of the step (t, hmax): speculate on that table
             ensure_table(running, hmax);
             double Lp = wtab[10];
@@ -513,15 +535,21 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
             double f1m, f1t, f1v, rprobe = rth;
             rsf_rhs_checked(cc, Lp, mu + h0 * k1m, th + h0 * k1t, rprobe, f1m, f1t, f1v);
             if (running) out.nrhs++;
-            const double e0 = (f1m - k1m) * i0, e1 = (f1t - k1t) * i1, e2 = (f1v - k1v) * i2;
-            const double der2sq = (e0 * e0 + e1 * e1 + e2 * e2) / (h0 * h0);
-            const double d12sq = fmax(der2sq, dnf);                             // der12^2
-            const double hm2 = hmax * hmax, hm4 = hm2 * hm2, hm8 = hm4 * hm4;
-            double h1;
-            if (d12sq <= 1e-30) h1 = fmax(1.0e-6, fabs(h0) * 1.0e-3);
-            else if (d12sq * (hm8 * hm8) <= 1.0e-4) h1 = hmax;                  // (0.01/der12)^(1/8) >= hmax
-            else h1 = root8(0.01 / sqrt(d12sq));
-            h = fmin(fmin(100.0 * fabs(h0), h1), hmax);
+            const double e0 = (f1m - k1m) * p0, e1 = (f1t - k1t) * p1, e2 = (f1v - k1v) * p2;
+            const double Ne = e0 * e0 + e1 * e1 + e2 * e2;                      // ||(f1-f0)/sk||^2 = Ne/D
+            // h = min(100 h0, (0.01/der12)^(1/8), hmax) with der12^2 = max(Ne/(D h0^2), Nf/D).
+            // (0.01/der12)^(1/8) >= hmax  <=>  der12^2 hmax^16 <= 1e-4: decided without sqrt / division
+            const double hm2 = hmax * hmax, hm4 = hm2 * hm2, hm8 = hm4 * hm4, hm16 = hm8 * hm8;
+            const double lim = 1.0e-4 * D;
+            if (h0max && Ne * hm16 <= lim * hm2 && Nf * hm16 <= lim && fmax(Ne, Nf * hm2) > 1e-30 * D * hm2) {
+                h = hmax;
+            } else {
+                const double d12sq = fmax(Ne / (D * h0 * h0), Nf / D);
+                double h1;
+                if (d12sq <= 1e-30) h1 = fmax(1.0e-6, fabs(h0) * 1.0e-3);
+                else h1 = root8(0.01 / sqrt(d12sq));
+                h = fmin(fmin(100.0 * fabs(h0), h1), hmax);
+            }
         } else {
             h = fmin(h_carry, hmax);
         }
@@ -556,8 +584,8 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
             bool bad = false;
             dop853_step_impl<true>(cc, in, Lsrc, lstride, so, bad);
             if (stepping && bad) dop853_step_general(&cc, &in, Lsrc, lstride, &so);
-            // err = |h| errs sqrt(1/(3 deno)) <= 1   <=>   h^2 errs^2 <= 3 deno   (no sqrt needed)
-            const bool accept = (h * h) * (so.errs * so.errs) <= 3.0 * so.deno;
+            // err <= 1   <=>   h^2 errA^2 <= den3   (no sqrt, no division; NaN rejects; 0 <= 0 accepts)
+            const bool accept = (h * h) * (so.errA * so.errA) <= so.den3;
 
             if (stepping) {
                 out.nstep++;
@@ -572,7 +600,7 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
                     // the controller's h_new is only consumed when the step does not end the
                     // interval, or when the step size is carried across output points
                     if (!last || !parity) {
-                        const double err = fabs(hold) * so.errs * sqrt(1.0 / (3.0 * so.deno));
+                        const double err = so.den3 > 0.0 ? fabs(hold) * so.errA / sqrt(so.den3) : 0.0;
                         const double fac = fmax(facc2, fmin(facc1, root8(err) / safe));
                         double hnew = hold / fac;
                         if (fabs(hnew) > hmax) hnew = hmax;

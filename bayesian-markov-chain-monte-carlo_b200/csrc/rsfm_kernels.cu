@@ -130,6 +130,31 @@ static int pick_block(int C)
 }
 
 // ---------------------------------------------------------------------------
+// nominal loading table: stage values of L(t) on the time grid every non-stiff chain walks
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) loading_table_kernel(ModelK M, double *__restrict__ nom)
+{
+    // keys first: the same recurrence the solver runs (t_{k+1} = t_k + ((t_k + delta_t) - t_k))
+    if (threadIdx.x == 0) {
+        double t = M.t_start;
+        for (int k = 1; k < M.n_out; k++) {
+            const double xend = t + M.delta_t;
+            const double h = xend - t;
+            nom[(size_t)k * NOM_STRIDE + 11] = t;
+            nom[(size_t)k * NOM_STRIDE + 12] = h;
+            t = t + h;
+        }
+    }
+    __syncthreads();
+    const long long total = (long long)(M.n_out - 1) * 11;
+    for (long long j = threadIdx.x; j < total; j += blockDim.x) {
+        const int k = 1 + (int)(j / 11), i = (int)(j % 11);
+        const double t = nom[(size_t)k * NOM_STRIDE + 11], h = nom[(size_t)k * NOM_STRIDE + 12];
+        nom[(size_t)k * NOM_STRIDE + i] = loading_of(M, __dadd_rn(t, __dmul_rn(TB.c[i], h)));
+    }
+}
+
+// ---------------------------------------------------------------------------
 // forward batch
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -138,14 +163,14 @@ rsf_forward_kernel(ModelK M, int C, double a0, double b0, const double *__restri
                    const double *__restrict__ data, double *__restrict__ acc_out,
                    double *__restrict__ t_out, double *__restrict__ sse_out, int32_t *__restrict__ status_out,
                    int32_t *__restrict__ filled_out, unsigned long long *__restrict__ nrhs_out,
-                   unsigned long long *__restrict__ nstep_out)
+                   unsigned long long *__restrict__ nstep_out, const double *__restrict__ nom)
 {
     __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ double s_ltab[4 * LTAB_STRIDE];
     __shared__ double s_lpriv[11 * 128];
     LoadScratch lscr;
-    lscr.tab = s_ltab; lscr.priv = s_lpriv;
+    lscr.tab = s_ltab; lscr.priv = s_lpriv; lscr.nom = nom;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = c < C;
     const int cc = active ? c : C - 1;
@@ -180,10 +205,16 @@ extern "C" int rsfm_forward_batch(const rsfm_cfg *cfg, int32_t C, const double *
     if (rc) return rc;
     const int block = pick_block(C);
     const int grid = (C + block - 1) / block;
+    const ModelK M = make_model(cfg);
+    double *nom = nullptr;                      // stream-ordered scratch for the nominal loading table
+    CUDA_TRY(cudaMallocAsync((void **)&nom, sizeof(double) * NOM_STRIDE * (size_t)cfg->n_out, (cudaStream_t)stream));
+    loading_table_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(M, nom);
     rsf_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
-        make_model(cfg), C, cfg->a, cfg->b, dc_dev, a_dev, b_dev, sse_out_dev ? data_dev : nullptr, acc_out_dev,
-        t_out_dev, sse_out_dev, status_dev, filled_dev, (unsigned long long *)nrhs_dev, (unsigned long long *)nstep_dev);
+        M, C, cfg->a, cfg->b, dc_dev, a_dev, b_dev, sse_out_dev ? data_dev : nullptr, acc_out_dev,
+        t_out_dev, sse_out_dev, status_dev, filled_dev, (unsigned long long *)nrhs_dev, (unsigned long long *)nstep_dev,
+        nom);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(nom, (cudaStream_t)stream));
     return RSFM_OK;
 }
 
@@ -198,6 +229,7 @@ struct SamplerDev {
     double *ring;       // [adapt_interval][C] last samples, COMPAT adaptation (d = 1)
     double *suff;       // [d + d(d+1)/2][C] per-chain sums for POOLED adaptation
     double *data;       // [n_out] padded to an even count
+    double *nom;        // [n_out][NOM_STRIDE] nominal loading table (loading_table_kernel)
     unsigned int *accepted;        // [C]
     int *status;                   // [C] sticky OR of RSFM_CHAIN_* of all solves
     unsigned long long *nrhs;      // [C]
@@ -247,6 +279,7 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     alloc((void **)&s->d.ring, sizeof(double) * cfg->adapt_interval * Cz);
     alloc((void **)&s->d.suff, sizeof(double) * (d + tri(d)) * Cz);
     alloc((void **)&s->d.data, sizeof(double) * ((size_t)cfg->n_out + 2));
+    alloc((void **)&s->d.nom, sizeof(double) * NOM_STRIDE * (size_t)cfg->n_out);
     alloc((void **)&s->d.accepted, sizeof(unsigned int) * Cz);
     alloc((void **)&s->d.status, sizeof(int) * Cz);
     alloc((void **)&s->d.nrhs, sizeof(unsigned long long) * Cz);
@@ -267,7 +300,7 @@ extern "C" void rsfm_destroy(rsfm_sampler *s)
 {
     if (!s) return;
     cudaFree(s->d.q); cudaFree(s->d.sse); cudaFree(s->d.sigma2); cudaFree(s->d.chol); cudaFree(s->d.ring);
-    cudaFree(s->d.suff); cudaFree(s->d.data); cudaFree(s->d.accepted); cudaFree(s->d.status);
+    cudaFree(s->d.suff); cudaFree(s->d.data); cudaFree(s->d.nom); cudaFree(s->d.accepted); cudaFree(s->d.status);
     cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->d.nsolve); cudaFree(s->d.nearly); cudaFree(s->scratch);
     cudaFree(s->reduce_out); cudaFree(s->totals);
     delete s;
@@ -292,7 +325,7 @@ rsf_init_kernel(ModelK M, int C, int pass, double a0, double b0, int n_prior_len
     __shared__ double s_ltab[4 * LTAB_STRIDE];
     __shared__ double s_lpriv[11 * 128];
     LoadScratch lscr;
-    lscr.tab = s_ltab; lscr.priv = s_lpriv;
+    lscr.tab = s_ltab; lscr.priv = s_lpriv; lscr.nom = S.nom;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = c < C;
     const int cc = active ? c : C - 1;
@@ -395,6 +428,8 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * (d + tri(d)) * (size_t)C, stream));
     const int block = pick_block(C), grid = (C + block - 1) / block;
     const ModelK M = make_model(&s->cfg);
+    loading_table_kernel<<<1, 1024, 0, stream>>>(M, s->d.nom);
+    CUDA_TRY(cudaGetLastError());
     for (int pass = 0; pass <= d; pass++) {
         if (d == 1)
             rsf_init_kernel<1><<<grid, block, 0, stream>>>(M, C, pass, s->cfg.a, s->cfg.b, s->cfg.n_prior_len, s->d, s->scratch);
@@ -452,7 +487,7 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
     __shared__ double s_ltab[4 * LTAB_STRIDE];
     __shared__ double s_lpriv[11 * 128];
     LoadScratch lscr;
-    lscr.tab = s_ltab; lscr.priv = s_lpriv;
+    lscr.tab = s_ltab; lscr.priv = s_lpriv; lscr.nom = S.nom;
     constexpr int T = D * (D + 1) / 2;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = c < C;
