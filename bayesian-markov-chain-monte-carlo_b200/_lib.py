@@ -40,7 +40,7 @@ class RsfmCfg(C.Structure):
         ("n_out", C.c_int32), ("nmax", C.c_int32), ("radiation_damping", C.c_int32),
         ("loading", C.c_int32), ("integ_mode", C.c_int32), ("n_params", C.c_int32),
         ("n_prior_len", C.c_int32), ("adapt_interval", C.c_int32), ("adapt_mode", C.c_int32),
-        ("reserved", C.c_int32),
+        ("spec_depth", C.c_int32),
     ]
 
 

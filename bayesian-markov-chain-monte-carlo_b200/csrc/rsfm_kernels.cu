@@ -63,6 +63,7 @@ extern "C" void rsfm_cfg_defaults(rsfm_cfg *c)
     c->n_prior_len = 3;
     c->adapt_interval = 10;
     c->adapt_mode = RSFM_ADAPT_NONE;
+    c->spec_depth = 0;
 }
 
 extern "C" int rsfm_device_count(void)
@@ -236,6 +237,7 @@ struct SamplerDev {
     unsigned long long *nstep;     // [C]
     unsigned long long *nsolve;    // [C] forward solves executed
     unsigned long long *nearly;    // [C] of which stopped early (rejection certain)
+    unsigned long long *nexec;     // [C] solves executed, speculative ones included
 };
 
 struct rsfm_sampler {
@@ -286,6 +288,7 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     alloc((void **)&s->d.nstep, sizeof(unsigned long long) * Cz);
     alloc((void **)&s->d.nsolve, sizeof(unsigned long long) * Cz);
     alloc((void **)&s->d.nearly, sizeof(unsigned long long) * Cz);
+    alloc((void **)&s->d.nexec, sizeof(unsigned long long) * Cz);
     alloc((void **)&s->totals, sizeof(unsigned long long) * 8);
     alloc((void **)&s->reduce_out, sizeof(double) * 16);
     if (!ok) {
@@ -301,7 +304,7 @@ extern "C" void rsfm_destroy(rsfm_sampler *s)
     if (!s) return;
     cudaFree(s->d.q); cudaFree(s->d.sse); cudaFree(s->d.sigma2); cudaFree(s->d.chol); cudaFree(s->d.ring);
     cudaFree(s->d.suff); cudaFree(s->d.data); cudaFree(s->d.nom); cudaFree(s->d.accepted); cudaFree(s->d.status);
-    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->d.nsolve); cudaFree(s->d.nearly); cudaFree(s->scratch);
+    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->d.nsolve); cudaFree(s->d.nearly); cudaFree(s->d.nexec); cudaFree(s->scratch);
     cudaFree(s->reduce_out); cudaFree(s->totals);
     delete s;
 }
@@ -359,12 +362,13 @@ rsf_init_kernel(ModelK M, int C, int pass, double a0, double b0, int n_prior_len
         } else if (D == 1) {
             S.chol[c] = S.sigma2[c] * (1.0 / xtx);                     // Vstart, :265-266
         }
-        S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; S.nsolve[c] += 1;
+        S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; S.nsolve[c] += 1; S.nexec[c] += 1;
     }
 }
 
 // d = 3: X'X from the stored trajectories, Vstart = sigma2_0 (X'X)^-1, chol(Vstart)
-__global__ void rsf_init_finish_kernel(int C, int n_out, SamplerDev S, const double *__restrict__ scratch)
+struct Box3 { double lo[3], hi[3]; };
+__global__ void rsf_init_finish_kernel(int C, int n_out, SamplerDev S, const double *__restrict__ scratch, Box3 box)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -395,6 +399,18 @@ __global__ void rsf_init_finish_kernel(int C, int n_out, SamplerDev S, const dou
     double v20 = s2 * (w20 * w22);
     double v21 = s2 * (w21 * w22);
     double v22 = s2 * (w22 * w22);
+    // (a, b) are nearly collinear in X, so Vstart can put most proposals outside the prior box.  No
+    // reference behaviour exists for d = 3; the covariance is shrunk by one common factor (shape and
+    // correlations kept) until every marginal s.d. is at most 1/20 of its prior width.
+    {
+        double gam = 1.0;
+        const double w0 = (box.hi[0] - box.lo[0]) / 20.0, w1 = (box.hi[1] - box.lo[1]) / 20.0,
+                     w2 = (box.hi[2] - box.lo[2]) / 20.0;
+        if (v00 > w0 * w0) gam = fmin(gam, w0 * w0 / v00);
+        if (v11 > w1 * w1) gam = fmin(gam, w1 * w1 / v11);
+        if (v22 > w2 * w2) gam = fmin(gam, w2 * w2 / v22);
+        v00 *= gam; v10 *= gam; v11 *= gam; v20 *= gam; v21 *= gam; v22 *= gam;
+    }
     double l00 = sqrt(v00), l10 = v10 / l00, l20 = v20 / l00;
     double l11 = sqrt(v11 - l10 * l10), l21 = (v21 - l20 * l10) / l11;
     double l22 = sqrt(v22 - l20 * l20 - l21 * l21);
@@ -425,6 +441,7 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     CUDA_TRY(cudaMemsetAsync(s->d.nstep, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.nsolve, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.nearly, 0, sizeof(unsigned long long) * C, stream));
+    CUDA_TRY(cudaMemsetAsync(s->d.nexec, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * (d + tri(d)) * (size_t)C, stream));
     const int block = pick_block(C), grid = (C + block - 1) / block;
     const ModelK M = make_model(&s->cfg);
@@ -438,7 +455,9 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
         CUDA_TRY(cudaGetLastError());
     }
     if (d == 3) {
-        rsf_init_finish_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, n, s->d, s->scratch);
+        Box3 box;
+        for (int i = 0; i < 3; i++) { box.lo[i] = s->cfg.lo[i]; box.hi[i] = s->cfg.hi[i]; }
+        rsf_init_finish_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, n, s->d, s->scratch, box);
         CUDA_TRY(cudaGetLastError());
     } else {
         fill_ring_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, s->cfg.adapt_interval, s->d);
@@ -639,6 +658,7 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
         S.sse[c] = ss; S.sigma2[c] = s2;
         S.accepted[c] += n_acc;
         S.nrhs[c] += nrhs; S.nstep[c] += nstep; S.status[c] |= status; S.nsolve[c] += nsolve; S.nearly[c] += nearly;
+        S.nexec[c] += nsolve;
         if (A.adapt_mode == RSFM_ADAPT_POOLED) {
 #pragma unroll
             for (int j = 0; j < D; j++) S.suff[j * Cz + c] += sq[j];
@@ -646,6 +666,236 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
             for (int j = 0; j < T; j++) S.suff[(D + j) * Cz + c] += sqq[j];
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------
+// speculative ("prefetching") Metropolis for small chain counts
+// ---------------------------------------------------------------------------
+// With C chains on a 148-SM part, one thread per chain leaves most SMSPs idle while every chain
+// waits a full solve latency per iteration (the loop of MCMC.py:494 is strictly sequential).  Here
+// G = 2^g lanes serve one chain: lanes 1..G-1 are the nodes of the binary tree of the next g
+// iterations.  Node j at depth l evaluates the proposal iteration it+l-1 would make if the earlier
+// iterations of the round had the accept (1) / reject (0) outcomes spelled by the bits of j below its
+// leading one (children of j: 2j after a reject, 2j+1 after an accept).  All solves of the tree run
+// concurrently; afterwards every lane of the group walks the realised path with the tree's sums of
+// squares, applying exactly the reference's accept rule and sigma^2 update in order.  Random draws
+// are Philox values keyed by (chain, iteration), so the chain is the one the sequential kernel
+// produces, bit for bit; only the wall time per iteration changes (up to g times shorter).
+//
+// Early stopping: the root knows its exact threshold SS - 2 s2 ln U.  A deeper node does not know
+// the state it will be judged against, so it stops at a generous bound H = SS + 100 s2; at
+// resolution time a stopped node counts as rejected only if H >= the true threshold (then rejection
+// is certain), otherwise it is unresolved and the round ends before it -- that iteration becomes the
+// root of the next round.  Exactness never depends on H.
+template <int D>
+__global__ void __launch_bounds__(128)
+rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
+{
+    __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ double s_ltab[4 * LTAB_STRIDE];
+    __shared__ double s_lpriv[11 * 128];
+    LoadScratch lscr;
+    lscr.tab = s_ltab; lscr.priv = s_lpriv; lscr.nom = S.nom;
+    constexpr int T = D * (D + 1) / 2;
+    const int G = 1 << g;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chain = tid >> g;
+    const int node = tid & (G - 1);                    // 0: idle helper lane; 1..G-1: tree nodes
+    const bool chain_ok = chain < C;
+    const int cc = chain_ok ? chain : C - 1;
+    const int lane = threadIdx.x & 31;
+    const int gbase = lane & ~(G - 1);
+    const size_t Cz = (size_t)C;
+    const int depth = node > 0 ? 32 - __clz(node) : 0; // level of this node (1 = root)
+    const bool writer = chain_ok && node == 1;
+
+    double q[D], L[T], sq[D], sqq[T];
+#pragma unroll
+    for (int j = 0; j < D; j++) { q[j] = S.q[j * Cz + cc]; sq[j] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < T; j++) { L[j] = S.chol[j * Cz + cc]; sqq[j] = 0.0; }
+    double ss = S.sse[cc], s2 = S.sigma2[cc];
+    unsigned int n_acc = 0, nsolve = 0, nearly = 0, nexec = 0;
+    unsigned long long nrhs = 0, nstep = 0;
+    int status = 0;
+    const unsigned long long gid = A.chain_id0 + (unsigned long long)cc;
+    const PhiloxKey key = philox_key(A.seed);
+    const double gshape = 0.5 * (A.n0 + (double)M.n_out);
+    SeriesStage series;
+    series.begin(s_tile, s_bar, S.data, M.n_out);
+
+    int it = 0;
+    while (__any_sync(FULL_MASK, chain_ok && it < A.n_iters)) {
+        const bool live = chain_ok && it < A.n_iters;
+        const int rmax = live ? min(g, A.n_iters - it) : 0;
+        const bool mine = live && node > 0 && depth <= rmax;
+        // ---- proposal of this node: replay the path encoded in `node` ----
+        double qn[D], cur[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) { cur[j] = q[j]; qn[j] = q[j]; }
+        bool reachable = mine;
+        for (int m = 1; m <= depth; m++) {
+            const unsigned int giter = (unsigned int)(A.iter0 + it + m - 1);
+            double z[D];
+            double z0, z1;
+            philox_normal2(key, gid, giter, 0u, z0, z1);
+            z[0] = z0;
+            if (D > 1) z[1] = z1;
+            if (D > 2) { philox_normal2(key, gid, giter, 1u, z0, z1); z[2] = z0; }
+            if (D == 1) {
+                qn[0] = cur[0] + sqrt(L[0]) * z[0];
+            } else {
+                qn[0] = cur[0] + L[0] * z[0];
+                qn[1] = cur[1] + L[1] * z[0] + L[2] * z[1];
+                qn[2] = cur[2] + L[3] * z[0] + L[4] * z[1] + L[5] * z[2];
+            }
+            if (m < depth) {
+                const bool took_accept = (node >> (depth - m - 1)) & 1;
+                if (took_accept) {
+                    bool inb_a = true;
+#pragma unroll
+                    for (int j = 0; j < D; j++) inb_a = inb_a && (qn[j] > A.lo[j]) && (qn[j] < A.hi[j]);
+                    if (!inb_a) reachable = false;         // an out-of-bounds ancestor cannot have been accepted
+#pragma unroll
+                    for (int j = 0; j < D; j++) cur[j] = qn[j];
+                }
+            }
+        }
+        bool inb = true;
+#pragma unroll
+        for (int j = 0; j < D; j++) inb = inb && (qn[j] > A.lo[j]) && (qn[j] < A.hi[j]);
+        const bool solve = reachable && inb;
+        // ---- stopping bound: exact for the root, generous for speculative nodes ----
+        double limit = INFINITY;
+        if (solve) {
+            if (node == 1) {
+                const double u = philox_uniform(key, gid, (unsigned int)(A.iter0 + it), 2u);
+                limit = ss - 2.0 * s2 * log(u);
+            } else {
+                limit = ss + 100.0 * s2;
+            }
+        }
+        const double pa = (D == 3) ? qn[0] : A.a0;
+        const double pb = (D == 3) ? qn[1] : A.b0;
+        series.start_solve();
+        SolveOut o = rsf_solve(M, solve ? pa : A.a0, solve ? pb : A.b0, solve ? qn[D - 1] : q[D - 1], solve, series, lscr,
+                               nullptr, nullptr, Cz, 1.0, nullptr, nullptr, limit);
+        // executed work of this lane (speculative or not) is accounted by the writer after a group sum
+        unsigned int w_rhs = solve ? o.nrhs : 0u, w_step = solve ? o.nstep : 0u, w_exec = solve ? 1u : 0u;
+        for (int off = 1; off < G; off <<= 1) {
+            w_rhs += __shfl_xor_sync(FULL_MASK, w_rhs, off);
+            w_step += __shfl_xor_sync(FULL_MASK, w_step, off);
+            w_exec += __shfl_xor_sync(FULL_MASK, w_exec, off);
+        }
+        nrhs += w_rhs; nstep += w_step; nexec += w_exec;
+        const int oflags = (inb ? 1 : 0) | (solve ? 2 : 0) | ((o.status & RSFM_CHAIN_EARLY) ? 4 : 0) |
+                           ((o.status & ~RSFM_CHAIN_EARLY) << 4);
+
+        // ---- resolution: every lane of the group walks the realised path (identical arithmetic) ----
+        int j = 1, ndone = 0;
+        bool stopped = !live;
+        for (int m = 1; m <= g; m++) {
+            const int src = gbase + (j & (G - 1));
+            double pq[D];
+#pragma unroll
+            for (int jj = 0; jj < D; jj++) pq[jj] = __shfl_sync(FULL_MASK, qn[jj], src);
+            const double psse = __shfl_sync(FULL_MASK, o.sse, src);
+            const double plim = __shfl_sync(FULL_MASK, limit, src);
+            const int pf = __shfl_sync(FULL_MASK, oflags, src);
+            if (stopped || m > rmax) { stopped = true; continue; }
+            const unsigned int giter = (unsigned int)(A.iter0 + it + m - 1);
+            const bool p_inb = pf & 1, p_early = pf & 4;
+            bool acc = false;
+            double u = nan("");
+            if (p_inb) {
+                u = philox_uniform(key, gid, giter, 2u);
+                const double lnu = log(u);
+                const double thr = ss - 2.0 * s2 * lnu;
+                // a node stopped at its bound is decided only if that bound is at least the threshold
+                if (p_early && !(plim >= thr)) { stopped = true; continue; }
+                double la = 0.5 * (ss - psse) / s2;
+                if (la > 0.0) la = 0.0;
+                acc = la > lnu;
+                nsolve++;
+                if (p_early) nearly++;
+                status |= (pf >> 4);
+                if (acc) {
+#pragma unroll
+                    for (int jj = 0; jj < D; jj++) q[jj] = pq[jj];
+                    ss = psse;
+                    n_acc++;
+                }
+            }
+            const double g0 = philox_gamma(key, gid, giter, gshape);
+            {
+                const double bval = 0.5 * (A.n0 * s2 + ss);
+                const double scale = 1.0 / bval;
+                s2 = 1.0 / (g0 * scale);
+            }
+            if (writer) {
+                const size_t row = (size_t)(it + m - 1);
+                if (A.samples) {
+#pragma unroll
+                    for (int jj = 0; jj < D; jj++) A.samples[(row * D + jj) * Cz + chain] = q[jj];
+                }
+                if (A.sigma2_out) A.sigma2_out[row * Cz + chain] = s2;
+                if (A.accept) A.accept[row * Cz + chain] = acc ? 1 : 0;
+                if (A.draws) {
+#pragma unroll
+                    for (int jj = 0; jj < D; jj++) A.draws[(row * (D + 2) + jj) * Cz + chain] = pq[jj];
+                    A.draws[(row * (D + 2) + D) * Cz + chain] = u;
+                    A.draws[(row * (D + 2) + D + 1) * Cz + chain] = g0;
+                }
+            }
+            if (A.adapt_mode == RSFM_ADAPT_POOLED) {
+#pragma unroll
+                for (int jj = 0; jj < D; jj++) sq[jj] += q[jj];
+                int t = 0;
+#pragma unroll
+                for (int a = 0; a < D; a++)
+#pragma unroll
+                    for (int b = 0; b <= a; b++) sqq[t++] += q[a] * q[b];
+            }
+            j = acc ? 2 * j + 1 : 2 * j;
+            ndone++;
+        }
+        it += ndone;
+    }
+
+    if (writer) {
+        const int c = chain;
+#pragma unroll
+        for (int j = 0; j < D; j++) S.q[j * Cz + c] = q[j];
+        S.sse[c] = ss; S.sigma2[c] = s2;
+        S.accepted[c] += n_acc;
+        S.nrhs[c] += nrhs; S.nstep[c] += nstep; S.status[c] |= status; S.nsolve[c] += nsolve; S.nearly[c] += nearly;
+        S.nexec[c] += nexec;
+        if (A.adapt_mode == RSFM_ADAPT_POOLED) {
+#pragma unroll
+            for (int j = 0; j < D; j++) S.suff[j * Cz + c] += sq[j];
+#pragma unroll
+            for (int j = 0; j < T; j++) S.suff[(D + j) * Cz + c] += sqq[j];
+        }
+    }
+}
+
+// depth of the speculation tree for C chains: the largest g with C 2^g threads <= one warp per SMSP
+static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
+{
+    if (A.deterministic || s->cfg.adapt_mode == RSFM_ADAPT_COMPAT) return 0;
+    if (s->cfg.n_out > 2 * SERIES_TILE) return 0;          // streamed series: block barriers, no speculation
+    int want = s->cfg.spec_depth;
+    if (const char *e = getenv("RSFM_SPEC_DEPTH")) want = atoi(e);
+    if (want == 1) return 0;
+    if (want >= 2 && want <= 5) return want;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    const long long cap = (long long)sms * 4 * 32;
+    int g = 0;
+    while (g < 5 && ((long long)s->C << (g + 1)) <= cap) g++;
+    return g >= 2 ? g : 0;
 }
 
 static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
@@ -658,7 +908,14 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
     for (int i = 0; i < RSFM_MAX_PARAMS; i++) { A.lo[i] = s->cfg.lo[i]; A.hi[i] = s->cfg.hi[i]; }
     A.adapt_mode = s->cfg.adapt_mode; A.adapt_interval = s->cfg.adapt_interval;
     const ModelK M = make_model(&s->cfg);
-    if (s->cfg.n_params == 1) {
+    const int g = pick_spec_depth(s, A);
+    if (g >= 2) {
+        const long long threads = (long long)C << g;
+        const int sblock = threads <= 148 * 32 * 4 ? 32 : 128;
+        const int sgrid = (int)((threads + sblock - 1) / sblock);
+        if (s->cfg.n_params == 1) rsf_mcmc_spec_kernel<1><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);
+        else rsf_mcmc_spec_kernel<3><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);
+    } else if (s->cfg.n_params == 1) {
         if (A.deterministic) rsf_mcmc_kernel<1, true><<<grid, block, 0, stream>>>(M, C, s->d, A);
         else rsf_mcmc_kernel<1, false><<<grid, block, 0, stream>>>(M, C, s->d, A);
     } else {
@@ -738,13 +995,13 @@ extern "C" int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double
 // ---------------------------------------------------------------------------
 __global__ void totals_kernel(int C, SamplerDev S, unsigned long long *__restrict__ out)
 {
-    unsigned long long v[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long v[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
         v[0] += S.nsolve[c]; v[1] += S.nrhs[c]; v[2] += S.nstep[c]; v[3] += S.accepted[c];
-        v[4] += S.status[c] != 0 ? 1 : 0; v[5] += S.nearly[c];
+        v[4] += S.status[c] != 0 ? 1 : 0; v[5] += S.nearly[c]; v[6] += S.nexec[c];
     }
 #pragma unroll
-    for (int j = 0; j < 6; j++) {
+    for (int j = 0; j < 7; j++) {
         for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_down_sync(FULL_MASK, v[j], o);
         if ((threadIdx.x & 31) == 0 && v[j]) atomicAdd(&out[j], v[j]);
     }
@@ -758,7 +1015,7 @@ extern "C" int rsfm_get_totals(rsfm_sampler *s, uint64_t *out_host, void *stream
     const int grid = (s->C + 255) / 256 < 592 ? (s->C + 255) / 256 : 592;
     totals_kernel<<<grid, 256, 0, st>>>(s->C, s->d, s->totals);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(out_host, s->totals, sizeof(uint64_t) * 6, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_host, s->totals, sizeof(uint64_t) * 7, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return RSFM_OK;
 }

@@ -34,7 +34,7 @@ class MCMC:
     def __init__(self, model, data, dc_true, qpriors, qstart, nsamples=100, lstm_model={},
                  adapt_interval=10, verbose=True, *, n_chains=1, seed=None, device=None,
                  param_names=("Dc",), bounds=None, deterministic_inputs=None, compat_adapt=None,
-                 adapt=None, adapt_start=100, shard=False, chain_id0=0, keep_on_device=False):
+                 adapt=None, adapt_start=100, shard=False, chain_id0=0, spec_depth=0, keep_on_device=False):
         # reference attributes, MCMC.py:88-99
         self.model = model
         self.qstart = qstart
@@ -60,6 +60,7 @@ class MCMC:
         self.shard = bool(shard)
         self.chain_id0 = int(chain_id0)        # global id of chain 0 when not sharding (Philox counter)
         self.keep_on_device = bool(keep_on_device)
+        self.spec_depth = int(spec_depth)      # speculation tree depth: 0 auto, 1 off, 2..5 forced
         if self.param_names not in (("Dc",), ("a", "b", "Dc")):
             raise ValueError("param_names must be ('Dc',) or ('a', 'b', 'Dc')")
         if compat_adapt is None:
@@ -138,6 +139,7 @@ class MCMC:
         cfg.n0 = float(self.n0)
         cfg.n_prior_len = len(self.qpriors)                       # MCMC.py:261 (q5)
         cfg.adapt_interval = int(self.adapt_interval)
+        cfg.spec_depth = self.spec_depth
         cfg.adapt_mode = (_lib.ADAPT_COMPAT if self.compat_adapt else
                           _lib.ADAPT_POOLED if self.adapt == "pooled" else _lib.ADAPT_NONE)
         seed = self.seed
@@ -183,7 +185,7 @@ class MCMC:
                 nstep = torch.empty(cl, dtype=torch.int64, device=dev)
                 _lib.check(lib.rsfm_get_state(handle, None, None, None, None, _lib.ptr(acc_cnt), _lib.ptr(status),
                                               _lib.ptr(nrhs), _lib.ptr(nstep), stream), "rsfm_get_state")
-                tot = (C.c_uint64 * 6)()
+                tot = (C.c_uint64 * 7)()
                 _lib.check(lib.rsfm_get_totals(handle, tot, stream), "rsfm_get_totals")
                 torch.cuda.synchronize(dev)
             finally:
@@ -206,6 +208,7 @@ class MCMC:
         self.stats = {
             "elapsed_s": elapsed, "n_chains_local": cl, "chain_id0": id0,
             "nsolves": int(tot[0]), "nrhs": int(tot[1]), "nstep": int(tot[2]),
+            "nsolves_stopped_early": int(tot[5]), "nsolves_executed": int(tot[6]),
             "failed_chains": int((status != 0).sum().item()),
         }
         if cl == 1:

@@ -236,7 +236,7 @@ def run_b200(args):
                                     pkg._lib.ptr(accept[o:]), None, stream), "rsfm_run")
 
     def totals(h):
-        out = (C.c_uint64 * 6)()
+        out = (C.c_uint64 * 7)()
         pkg._lib.check(lib.rsfm_get_totals(h, out, stream), "rsfm_get_totals")
         return np.array(list(out), dtype=np.float64)
 
@@ -303,7 +303,7 @@ def run_b200(args):
         dist.all_reduce(red_max, op=dist.ReduceOp.MAX)
         dist.all_reduce(red_sum, op=dist.ReduceOp.SUM)
     dev_s_max, wall_max, e2e_wall_max = red_max.tolist()
-    solves, nrhs, nstep, n_accepted, n_failed, n_early, e2e_solves_all = red_sum.tolist()
+    solves, nrhs, nstep, n_accepted, n_failed, n_early, n_exec, e2e_solves_all = red_sum.tolist()
 
     if rank == 0:
         peaks = {}
@@ -337,7 +337,8 @@ def run_b200(args):
             "ess": {"total": diag["ess"][0], "per_chain": diag["ess_per_chain_mean"][0], "rhat": diag["rhat"][0],
                     "draws_per_chain": int(diag["n"]), "posterior_mean": diag["mean"][0], "posterior_sd": diag["sd"][0],
                     "accept_rate": acc_rate},
-            "work": {"forward_solves": solves, "of_which_stopped_early": n_early, "rhs_evals": nrhs,
+            "work": {"forward_solves": solves, "of_which_stopped_early": n_early,
+                     "solves_executed_incl_speculative": n_exec, "rhs_evals": nrhs,
                      "ode_steps": nstep, "failed_chains": n_failed,
                      "wall_s_timed_region": wall_max},
             "e2e": {"value": e2e_solves_all / e2e_wall_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),

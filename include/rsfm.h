@@ -77,7 +77,8 @@ typedef struct rsfm_cfg {
     int32_t n_prior_len;                 /* len(qpriors): 3 list form, 2 dict form, MCMC.py:261 (q5) */
     int32_t adapt_interval;              /* MCMC.py:58 */
     int32_t adapt_mode;                  /* RSFM_ADAPT_* */
-    int32_t reserved;
+    int32_t spec_depth;                  /* speculation tree depth of rsfm_run: 0 auto (by chain count),
+                                            1 off, 2..5 forced; results never depend on it */
 } rsfm_cfg;
 
 typedef struct rsfm_sampler rsfm_sampler;   /* opaque; owns per-chain device state */
@@ -149,9 +150,10 @@ int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double *sse_dev,
 int64_t rsfm_iteration(const rsfm_sampler *s);
 
 /* Work totals since rsfm_init, summed over chains on the device and copied to
- * out_host[6] = (forward solves started, RHS evaluations, attempted steps,
- * accepted moves, chains with a non-zero status, solves stopped early because
- * rejection was already certain).  Synchronises the stream. */
+ * out_host[7] = (forward solves of the chains = in-bounds proposals decided, RHS
+ * evaluations executed, steps attempted, accepted moves, chains with a non-zero
+ * status, solves stopped early because rejection was already certain, solves
+ * executed including speculative ones).  Synchronises the stream. */
 int rsfm_get_totals(rsfm_sampler *s, uint64_t *out_host, void *stream);
 
 /* Pooled adaptation (extension): local sufficient

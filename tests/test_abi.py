@@ -31,7 +31,7 @@ def test_abi_version_and_defaults(built_lib, pkg):
     assert (cfg.t_start, cfg.t_final, cfg.n_out, cfg.delta_t) == (0.0, 50.0, 500, 0.1)
     assert (cfg.rtol, cfg.atol, cfg.nmax, cfg.n0) == (1e-6, 1e-10, 500, 0.01)
     assert cfg.radiation_damping == 1 and cfg.loading == 0 and cfg.integ_mode == 0
-    assert cfg.reserved == 0 and cfg.adapt_interval == 10
+    assert cfg.spec_depth == 0 and cfg.adapt_interval == 10
 
 
 def test_sass_is_sm100a_with_tma_bulk_copy(built_lib, pkg):
