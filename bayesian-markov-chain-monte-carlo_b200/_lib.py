@@ -21,7 +21,7 @@ CHAIN_OK, CHAIN_NMAX, CHAIN_HSMALL, CHAIN_NONFINITE = 0, 2, 3, 4
 EXPORTED_SYMBOLS = (
     "rsfm_abi_version", "rsfm_last_error", "rsfm_cfg_defaults", "rsfm_device_count",
     "rsfm_forward_batch", "rsfm_create", "rsfm_destroy", "rsfm_init", "rsfm_run",
-    "rsfm_run_deterministic", "rsfm_get_state", "rsfm_set_state", "rsfm_iteration",
+    "rsfm_run_deterministic", "rsfm_spec_depth", "rsfm_get_state", "rsfm_set_state", "rsfm_iteration",
     "rsfm_get_totals", "rsfm_get_suffstats", "rsfm_set_proposal_chol", "rsfm_chain_diagnostics",
     "rsfm_measure_fp64_peak",
 )
@@ -78,6 +78,8 @@ def load():
     lib.rsfm_init.restype = C.c_int
     lib.rsfm_run.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.rsfm_run.restype = C.c_int
+    lib.rsfm_spec_depth.argtypes = [vp]
+    lib.rsfm_spec_depth.restype = C.c_int
     lib.rsfm_run_deterministic.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.rsfm_run_deterministic.restype = C.c_int
     lib.rsfm_get_state.argtypes = [vp] + [vp] * 8 + [vp]

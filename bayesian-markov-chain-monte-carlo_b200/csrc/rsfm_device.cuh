@@ -141,6 +141,7 @@ struct SeriesStage {
     // value data[k]; in streaming mode entering a tile recycles the buffer two tiles back
     __device__ __forceinline__ double at(int k)
     {
+        if (resident && loaded) return buf[k];             // both tiles are in place and contiguous
         const int tile = k / SERIES_TILE;
         const int off = k - tile * SERIES_TILE;
         if (off == 0 && !(resident && loaded)) {
@@ -495,25 +496,89 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
     };
 
     const double *nom = ls.nom;
-    double pre = (nom != nullptr && lane < 13 && M.n_out > 1) ? nom[NOM_STRIDE + lane] : 0.0;
+    double pre = (nom != nullptr && lane < 11 && M.n_out > 1) ? nom[NOM_STRIDE + lane] : 0.0;
+    double pre_t = (nom != nullptr && M.n_out > 1) ? nom[NOM_STRIDE + 11] : 0.0;
+    double pre_h = (nom != nullptr && M.n_out > 1) ? nom[NOM_STRIDE + 12] : -1.0;
+    double acc_pending = 0.0, dk_pending = 0.0;      // output point whose SSE term is folded in one interval late
+    bool have_pending = false;
+    int fast_resume = 0;
 
     for (int k = 1; k < M.n_out; k++) {
         const double dk = have_data ? series.at(k) : 0.0;
-        const bool running = active && !failed;
         if (nom != nullptr) {
             // install the nominal entry of this interval (fetched one interval ahead) as the warp's table
             __syncwarp();
-            if (lane < 13) wtab[lane] = pre;
+            if (lane < 11) wtab[lane] = pre;
             __syncwarp();
-            tab_t = wtab[11]; tab_h = wtab[12];
-            if (lane < 13 && k + 1 < M.n_out) pre = nom[(size_t)(k + 1) * NOM_STRIDE + lane];
+            tab_t = pre_t; tab_h = pre_h;
+            if (k + 1 < M.n_out) {
+                if (lane < 11) pre = nom[(size_t)(k + 1) * NOM_STRIDE + lane];
+                pre_t = nom[(size_t)(k + 1) * NOM_STRIDE + 11];
+                pre_h = nom[(size_t)(k + 1) * NOM_STRIDE + 12];
+            }
         }
+        // SSE term of the previous output point (its division overlaps this interval's first stages)
+        if (have_pending) {
+            const double e = acc_pending - dk_pending;
+            sse += e * e;
+            if (active && !failed && sse > sse_limit) { failed = true; out.status |= RSFM_CHAIN_EARLY; }
+        }
+        const bool running = active && !failed;
         const double xend = t + M.delta_t;                         // :382
         const double hmax = fabs(xend - t);
         int nstep_call = 0;
         bool reject = false, last = false;
         double h;
 
+        // ---- fast interval: the whole warp is on the nominal grid ----
+        // Outside the stiff regime every SciPy call of the reference does the same thing: hinit returns
+        // hmax, dp86co clamps it to xend - t, the single step is accepted.  That case is executed as one
+        // branch-free block (hinit's Euler probe and the twelve stages are independent given (t, y, k1)
+        // and interleave), verified by ONE warp vote; any lane that deviates (h0 or h below hmax,
+        // rejected step, argument outside the fast ranges) sends the warp through the general path
+        // below for this interval, which recomputes it from the same state.
+        bool fast_done = false;
+        if (parity && k > 1 && k >= fast_resume && nom != nullptr) {
+            const bool cand = (t == tab_t) && (hmax == tab_h);
+            const unsigned rmask = __ballot_sync(FULL_MASK, running);
+            if (rmask != 0 && __all_sync(FULL_MASK, !running || cand)) {
+                const double k0 = M.atol + M.rtol * fabs(mu), k1 = M.atol + M.rtol * fabs(th), k2 = M.atol + M.rtol * fabs(V);
+                const double p0 = k1 * k2, p1 = k0 * k2, p2 = k0 * k1;
+                const double dd = k0 * p0, D = dd * dd;
+                const double Nf = (k1m * p0) * (k1m * p0) + (k1t * p1) * (k1t * p1) + (k1v * p2) * (k1v * p2);
+                const double Ny = (mu * p0) * (mu * p0) + (th * p1) * (th * p1) + (V * p2) * (V * p2);
+                const bool h0max = !((Nf <= 1e-10 * D) || (Ny <= 1e-10 * D)) && (Ny >= Nf * (1.0e4 * hmax * hmax));
+                bool bad = false;
+                double f1m, f1t, f1v, rprobe = rth;
+                rsf_rhs<true>(cc, wtab[10], mu + hmax * k1m, th + hmax * k1t, rprobe, f1m, f1t, f1v, bad);
+                StepIn in;
+                in.h = xend - t; in.mu = mu; in.th = th; in.V = V; in.k1m = k1m; in.k1t = k1t; in.k1v = k1v; in.rth = rth;
+                in.atol = M.atol; in.rtol = M.rtol;
+                StepOut so;
+                dop853_step_impl<true>(cc, in, wtab, 1, so, bad);
+                const double e0 = (f1m - k1m) * p0, e1 = (f1t - k1t) * p1, e2 = (f1v - k1v) * p2;
+                const double Ne = e0 * e0 + e1 * e1 + e2 * e2;
+                const double hm2 = hmax * hmax, hm4 = hm2 * hm2, hm8 = hm4 * hm4, hm16 = hm8 * hm8;
+                const double lim = 1.0e-4 * D;
+                const bool h1max = Ne * hm16 <= lim * hm2 && Nf * hm16 <= lim && fmax(Ne, Nf * hm2) > 1e-30 * D * hm2;
+                const bool entry = !(0.1 * hmax <= fabs(t) * uround) && ((t + 1.01 * hmax - xend) > 0.0);
+                const bool accept = (in.h * in.h) * (so.errA * so.errA) <= so.den3;
+                const bool ok = h0max && h1max && entry && accept && !bad;
+                if (__all_sync(FULL_MASK, !running || ok)) {
+                    if (running) {
+                        rth = so.rth;
+                        rsf_rhs_checked(cc, so.L12, so.muN, so.thN, rth, k1m, k1t, k1v);
+                        mu = so.muN; th = so.thN; V = so.VN; t = t + in.h;
+                        out.nrhs += 13; out.nstep++;
+                    }
+                    fast_done = true;
+                } else {
+                    fast_resume = k + 8;       // back off: this warp is (partly) off the nominal regime
+                }
+            }
+        }
+
+        if (!fast_done) {
         if (parity || k == 1) {
             // ---- HINIT (dop853.f, iord = 8).  The common outcome h0 = h = hmax is recognised by
             // comparisons in the squared / 16th-power domain, without sqrt or division. ----
@@ -599,7 +664,11 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
                     mu = so.muN; th = so.thN; V = so.VN; t = t + h;
                     // the controller's h_new is only consumed when the step does not end the
                     // interval, or when the step size is carried across output points
-                    if (!last || !parity) {
+                    // (h_new = h / max(1/6, min(1/0.3, err^(1/8)/0.9)) >= h when err <= 0.9^8; with h = hmax it is
+                    //  clamped back to hmax, so the 8th root is skipped)
+                    const bool keeps_hmax = (hold == hmax) && !reject &&
+                                            (hold * hold) * (so.errA * so.errA) <= 0.185302018885184 * so.den3;
+                    if ((!last || !parity) && !keeps_hmax) {
                         const double err = so.den3 > 0.0 ? fabs(hold) * so.errA / sqrt(so.den3) : 0.0;
                         const double fac = fmax(facc2, fmin(facc1, root8(err) / safe));
                         double hnew = hold / fac;
@@ -617,6 +686,7 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
                 }
             }
         }
+        }   // !fast_done
 
         // ---- output point k: RateStateModel.py:384-388, MCMC.py:387 ----
         double accv = 0.0;
@@ -625,8 +695,7 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
             vprev = V;
             if (failed && out.filled == M.n_out) out.filled = k + 1;
         }
-        if (have_data) { const double e = accv - dk; sse += e * e; }
-        if (running && sse > sse_limit) { failed = true; out.status |= RSFM_CHAIN_EARLY; }
+        acc_pending = accv; dk_pending = dk; have_pending = have_data;
         if (series.resident && __all_sync(FULL_MASK, !active || (failed && (out.status & RSFM_CHAIN_EARLY)))) break;
         if (active) {
             if (acc_out) acc_out[(size_t)k * acc_stride] = accv;
@@ -634,6 +703,7 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
             if (acc_ref) { const double x = (accv - acc_ref[(size_t)k * acc_stride]) / fd_den; xtx += x * x; }
         }
     }
+    if (have_pending) { const double e = acc_pending - dk_pending; sse += e * e; }
     out.sse = sse;
     if (xtx_out) *xtx_out = xtx;
     return out;

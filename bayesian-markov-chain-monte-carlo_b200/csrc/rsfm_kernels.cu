@@ -155,6 +155,55 @@ __global__ void __launch_bounds__(1024) loading_table_kernel(ModelK M, double *_
     }
 }
 
+// Small per-process cache of nominal tables for the stateless rsfm_forward_batch (a sampler owns its
+// own).  Entries are keyed by the model constants and the device; they are immutable once built, so
+// concurrent readers on any stream only need to wait for the build event.
+struct NomEntry { ModelK M; int device; double *ptr; cudaEvent_t ready; unsigned long long stamp; };
+static NomEntry g_nom[8];
+static int g_nom_n = 0;
+static unsigned long long g_nom_clock = 0;
+static std::mutex g_nom_mu;
+
+static int get_nominal_table(const ModelK &M, cudaStream_t stream, const double **out)
+{
+    std::lock_guard<std::mutex> lock(g_nom_mu);
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    for (int i = 0; i < g_nom_n; i++) {
+        if (g_nom[i].device == dev && memcmp(&g_nom[i].M, &M, sizeof(ModelK)) == 0) {
+            g_nom[i].stamp = ++g_nom_clock;
+            CUDA_TRY(cudaStreamWaitEvent(stream, g_nom[i].ready, 0));
+            *out = g_nom[i].ptr;
+            return RSFM_OK;
+        }
+    }
+    int slot = g_nom_n;
+    if (g_nom_n == 8) {                       // evict the least recently used entry (rare: needs a full sync)
+        slot = 0;
+        for (int i = 1; i < 8; i++) if (g_nom[i].stamp < g_nom[slot].stamp) slot = i;
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(g_nom[slot].ptr);
+        cudaEventDestroy(g_nom[slot].ready);
+    } else {
+        g_nom_n++;
+    }
+    NomEntry &e = g_nom[slot];
+    memset(&e, 0, sizeof(e));
+    memcpy(&e.M, &M, sizeof(ModelK));
+    e.device = dev; e.stamp = ++g_nom_clock;
+    if (cudaMalloc((void **)&e.ptr, sizeof(double) * NOM_STRIDE * (size_t)M.n_out) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming) != cudaSuccess) {
+        g_nom_n = slot == g_nom_n - 1 ? g_nom_n - 1 : g_nom_n;
+        e.device = -1;
+        return set_err(RSFM_ERR_CUDA, "nominal table allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    loading_table_kernel<<<1, 1024, 0, stream>>>(M, e.ptr);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e.ready, stream));
+    *out = e.ptr;
+    return RSFM_OK;
+}
+
 // ---------------------------------------------------------------------------
 // forward batch
 // ---------------------------------------------------------------------------
@@ -207,15 +256,14 @@ extern "C" int rsfm_forward_batch(const rsfm_cfg *cfg, int32_t C, const double *
     const int block = pick_block(C);
     const int grid = (C + block - 1) / block;
     const ModelK M = make_model(cfg);
-    double *nom = nullptr;                      // stream-ordered scratch for the nominal loading table
-    CUDA_TRY(cudaMallocAsync((void **)&nom, sizeof(double) * NOM_STRIDE * (size_t)cfg->n_out, (cudaStream_t)stream));
-    loading_table_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(M, nom);
+    const double *nom = nullptr;
+    rc = get_nominal_table(M, (cudaStream_t)stream, &nom);
+    if (rc) return rc;
     rsf_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
         M, C, cfg->a, cfg->b, dc_dev, a_dev, b_dev, sse_out_dev ? data_dev : nullptr, acc_out_dev,
         t_out_dev, sse_out_dev, status_dev, filled_dev, (unsigned long long *)nrhs_dev, (unsigned long long *)nstep_dev,
         nom);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaFreeAsync(nom, (cudaStream_t)stream));
     return RSFM_OK;
 }
 
@@ -238,6 +286,8 @@ struct SamplerDev {
     unsigned long long *nsolve;    // [C] forward solves executed
     unsigned long long *nearly;    // [C] of which stopped early (rejection certain)
     unsigned long long *nexec;     // [C] solves executed, speculative ones included
+    unsigned long long *urhs;      // [C] RHS evaluations of the solves that decided a proposal (no speculation waste)
+    unsigned long long *ustep;     // [C] steps of those solves
 };
 
 struct rsfm_sampler {
@@ -289,7 +339,9 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     alloc((void **)&s->d.nsolve, sizeof(unsigned long long) * Cz);
     alloc((void **)&s->d.nearly, sizeof(unsigned long long) * Cz);
     alloc((void **)&s->d.nexec, sizeof(unsigned long long) * Cz);
-    alloc((void **)&s->totals, sizeof(unsigned long long) * 8);
+    alloc((void **)&s->d.urhs, sizeof(unsigned long long) * Cz);
+    alloc((void **)&s->d.ustep, sizeof(unsigned long long) * Cz);
+    alloc((void **)&s->totals, sizeof(unsigned long long) * 16);
     alloc((void **)&s->reduce_out, sizeof(double) * 16);
     if (!ok) {
         set_err(RSFM_ERR_CUDA, "rsfm_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -304,7 +356,7 @@ extern "C" void rsfm_destroy(rsfm_sampler *s)
     if (!s) return;
     cudaFree(s->d.q); cudaFree(s->d.sse); cudaFree(s->d.sigma2); cudaFree(s->d.chol); cudaFree(s->d.ring);
     cudaFree(s->d.suff); cudaFree(s->d.data); cudaFree(s->d.nom); cudaFree(s->d.accepted); cudaFree(s->d.status);
-    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->d.nsolve); cudaFree(s->d.nearly); cudaFree(s->d.nexec); cudaFree(s->scratch);
+    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->d.nsolve); cudaFree(s->d.nearly); cudaFree(s->d.nexec); cudaFree(s->d.urhs); cudaFree(s->d.ustep); cudaFree(s->scratch);
     cudaFree(s->reduce_out); cudaFree(s->totals);
     delete s;
 }
@@ -362,7 +414,7 @@ rsf_init_kernel(ModelK M, int C, int pass, double a0, double b0, int n_prior_len
         } else if (D == 1) {
             S.chol[c] = S.sigma2[c] * (1.0 / xtx);                     // Vstart, :265-266
         }
-        S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; S.nsolve[c] += 1; S.nexec[c] += 1;
+        S.nrhs[c] += o.nrhs; S.nstep[c] += o.nstep; S.status[c] |= o.status; S.nsolve[c] += 1; S.nexec[c] += 1; S.urhs[c] += o.nrhs; S.ustep[c] += o.nstep;
     }
 }
 
@@ -442,6 +494,8 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     CUDA_TRY(cudaMemsetAsync(s->d.nsolve, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.nearly, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.nexec, 0, sizeof(unsigned long long) * C, stream));
+    CUDA_TRY(cudaMemsetAsync(s->d.urhs, 0, sizeof(unsigned long long) * C, stream));
+    CUDA_TRY(cudaMemsetAsync(s->d.ustep, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * (d + tri(d)) * (size_t)C, stream));
     const int block = pick_block(C), grid = (C + block - 1) / block;
     const ModelK M = make_model(&s->cfg);
@@ -658,7 +712,7 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
         S.sse[c] = ss; S.sigma2[c] = s2;
         S.accepted[c] += n_acc;
         S.nrhs[c] += nrhs; S.nstep[c] += nstep; S.status[c] |= status; S.nsolve[c] += nsolve; S.nearly[c] += nearly;
-        S.nexec[c] += nsolve;
+        S.nexec[c] += nsolve; S.urhs[c] += nrhs; S.ustep[c] += nstep;
         if (A.adapt_mode == RSFM_ADAPT_POOLED) {
 #pragma unroll
             for (int j = 0; j < D; j++) S.suff[j * Cz + c] += sq[j];
@@ -718,7 +772,7 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
     for (int j = 0; j < T; j++) { L[j] = S.chol[j * Cz + cc]; sqq[j] = 0.0; }
     double ss = S.sse[cc], s2 = S.sigma2[cc];
     unsigned int n_acc = 0, nsolve = 0, nearly = 0, nexec = 0;
-    unsigned long long nrhs = 0, nstep = 0;
+    unsigned long long nrhs = 0, nstep = 0, urhs = 0, ustep = 0;
     int status = 0;
     const unsigned long long gid = A.chain_id0 + (unsigned long long)cc;
     const PhiloxKey key = philox_key(A.seed);
@@ -804,6 +858,7 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
             const double psse = __shfl_sync(FULL_MASK, o.sse, src);
             const double plim = __shfl_sync(FULL_MASK, limit, src);
             const int pf = __shfl_sync(FULL_MASK, oflags, src);
+            const unsigned int prhs = __shfl_sync(FULL_MASK, o.nrhs, src), pstep = __shfl_sync(FULL_MASK, o.nstep, src);
             if (stopped || m > rmax) { stopped = true; continue; }
             const unsigned int giter = (unsigned int)(A.iter0 + it + m - 1);
             const bool p_inb = pf & 1, p_early = pf & 4;
@@ -819,6 +874,7 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
                 if (la > 0.0) la = 0.0;
                 acc = la > lnu;
                 nsolve++;
+                urhs += prhs; ustep += pstep;
                 if (p_early) nearly++;
                 status |= (pf >> 4);
                 if (acc) {
@@ -871,7 +927,7 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
         S.sse[c] = ss; S.sigma2[c] = s2;
         S.accepted[c] += n_acc;
         S.nrhs[c] += nrhs; S.nstep[c] += nstep; S.status[c] |= status; S.nsolve[c] += nsolve; S.nearly[c] += nearly;
-        S.nexec[c] += nexec;
+        S.nexec[c] += nexec; S.urhs[c] += urhs; S.ustep[c] += ustep;
         if (A.adapt_mode == RSFM_ADAPT_POOLED) {
 #pragma unroll
             for (int j = 0; j < D; j++) S.suff[j * Cz + c] += sq[j];
@@ -881,7 +937,7 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
     }
 }
 
-// depth of the speculation tree for C chains: the largest g with C 2^g threads <= one warp per SMSP
+// depth of the speculation tree for C chains: the largest g with C 2^g threads <= two warps per SMSP
 static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
 {
     if (A.deterministic || s->cfg.adapt_mode == RSFM_ADAPT_COMPAT) return 0;
@@ -892,10 +948,18 @@ static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
     if (want >= 2 && want <= 5) return want;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-    const long long cap = (long long)sms * 4 * 32;
+    const long long cap = (long long)sms * 4 * 32 * 2;        // up to two warps per SMSP (measured optimum)
     int g = 0;
     while (g < 5 && ((long long)s->C << (g + 1)) <= cap) g++;
     return g >= 2 ? g : 0;
+}
+
+extern "C" int rsfm_spec_depth(const rsfm_sampler *s)
+{
+    if (!s) return -1;
+    RunArgs A;
+    memset(&A, 0, sizeof(A));
+    return pick_spec_depth(s, A);
 }
 
 static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
@@ -995,13 +1059,13 @@ extern "C" int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double
 // ---------------------------------------------------------------------------
 __global__ void totals_kernel(int C, SamplerDev S, unsigned long long *__restrict__ out)
 {
-    unsigned long long v[7] = {0, 0, 0, 0, 0, 0, 0};
+    unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
         v[0] += S.nsolve[c]; v[1] += S.nrhs[c]; v[2] += S.nstep[c]; v[3] += S.accepted[c];
-        v[4] += S.status[c] != 0 ? 1 : 0; v[5] += S.nearly[c]; v[6] += S.nexec[c];
+        v[4] += S.status[c] != 0 ? 1 : 0; v[5] += S.nearly[c]; v[6] += S.nexec[c]; v[7] += S.urhs[c]; v[8] += S.ustep[c];
     }
 #pragma unroll
-    for (int j = 0; j < 7; j++) {
+    for (int j = 0; j < 9; j++) {
         for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_down_sync(FULL_MASK, v[j], o);
         if ((threadIdx.x & 31) == 0 && v[j]) atomicAdd(&out[j], v[j]);
     }
@@ -1011,11 +1075,11 @@ extern "C" int rsfm_get_totals(rsfm_sampler *s, uint64_t *out_host, void *stream
 {
     if (!s || !out_host) return set_err(RSFM_ERR_INVALID, "rsfm_get_totals: NULL argument%s", "");
     cudaStream_t st = (cudaStream_t)stream_;
-    CUDA_TRY(cudaMemsetAsync(s->totals, 0, sizeof(unsigned long long) * 8, st));
+    CUDA_TRY(cudaMemsetAsync(s->totals, 0, sizeof(unsigned long long) * 16, st));
     const int grid = (s->C + 255) / 256 < 592 ? (s->C + 255) / 256 : 592;
     totals_kernel<<<grid, 256, 0, st>>>(s->C, s->d, s->totals);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(out_host, s->totals, sizeof(uint64_t) * 7, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_host, s->totals, sizeof(uint64_t) * 9, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return RSFM_OK;
 }

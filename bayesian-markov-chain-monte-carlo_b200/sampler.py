@@ -185,7 +185,7 @@ class MCMC:
                 nstep = torch.empty(cl, dtype=torch.int64, device=dev)
                 _lib.check(lib.rsfm_get_state(handle, None, None, None, None, _lib.ptr(acc_cnt), _lib.ptr(status),
                                               _lib.ptr(nrhs), _lib.ptr(nstep), stream), "rsfm_get_state")
-                tot = (C.c_uint64 * 7)()
+                tot = (C.c_uint64 * 9)()
                 _lib.check(lib.rsfm_get_totals(handle, tot, stream), "rsfm_get_totals")
                 torch.cuda.synchronize(dev)
             finally:

@@ -236,7 +236,7 @@ def run_b200(args):
                                     pkg._lib.ptr(accept[o:]), None, stream), "rsfm_run")
 
     def totals(h):
-        out = (C.c_uint64 * 7)()
+        out = (C.c_uint64 * 9)()
         pkg._lib.check(lib.rsfm_get_totals(h, out, stream), "rsfm_get_totals")
         return np.array(list(out), dtype=np.float64)
 
@@ -249,6 +249,7 @@ def run_b200(args):
     # the timed job starts from the start values: K steps = the first K*iters iterations of every
     # chain (K = 10: cfg 2's nsamples = 2,000, burn-in phase included), data and state resident in HBM
     handle = make_sampler()
+    spec_g = int(lib.rsfm_spec_depth(handle))
     tot0 = totals(handle)
     clocks = ClockSampler(local)
     if rank == 0:
@@ -303,7 +304,7 @@ def run_b200(args):
         dist.all_reduce(red_max, op=dist.ReduceOp.MAX)
         dist.all_reduce(red_sum, op=dist.ReduceOp.SUM)
     dev_s_max, wall_max, e2e_wall_max = red_max.tolist()
-    solves, nrhs, nstep, n_accepted, n_failed, n_early, n_exec, e2e_solves_all = red_sum.tolist()
+    solves, nrhs, nstep, n_accepted, n_failed, n_early, n_exec, urhs, ustep, e2e_solves_all = red_sum.tolist()
 
     if rank == 0:
         peaks = {}
@@ -312,8 +313,11 @@ def run_b200(args):
         except (OSError, ValueError):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        flops_rank0 = FLOPS_PER_RHS * tot[1] + FLOPS_PER_STEP * tot[2]
+        # algorithmic flops of the solves that decided a proposal (speculative work that was thrown
+        # away is NOT counted as achieved; it is reported separately as `executed`)
+        flops_rank0 = FLOPS_PER_RHS * tot[7] + FLOPS_PER_STEP * tot[8]
         achieved_tf = flops_rank0 / dev_s / 1e12
+        executed_tf = (FLOPS_PER_RHS * tot[1] + FLOPS_PER_STEP * tot[2]) / dev_s / 1e12
         # algorithmic bytes per launch: state in/out 64 B/chain, per iteration 8 B sample +
         # 8 B sigma^2 + 1 B flag per chain, and the 8 N B series once per block
         nblocks = (cpg + 31) // 32 if cpg <= 148 * 32 else (cpg + 63) // 64 if cpg <= 148 * 128 else (cpg + 127) // 128
@@ -331,7 +335,7 @@ def run_b200(args):
             "config": {"workload": f"cfg2: {cpg} independent chains per GPU, Dc-only posterior, N={N_OUT}, "
                                    f"list priors U(0,1e4), {iters} Metropolis iterations per step",
                        "chains_per_gpu": cpg, "chains_total": total_chains, "iters_per_step": iters, "n_out": N_OUT,
-                       "integ_mode": args.integ_mode, "l2": "flushed between timed steps (256 MiB write)",
+                       "integ_mode": args.integ_mode, "speculation_depth": spec_g, "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
             "ess_per_s": diag["ess"][0] / dev_s_max,
             "ess": {"total": diag["ess"][0], "per_chain": diag["ess_per_chain_mean"][0], "rhat": diag["rhat"][0],
@@ -339,7 +343,8 @@ def run_b200(args):
                     "accept_rate": acc_rate},
             "work": {"forward_solves": solves, "of_which_stopped_early": n_early,
                      "solves_executed_incl_speculative": n_exec, "rhs_evals": nrhs,
-                     "ode_steps": nstep, "failed_chains": n_failed,
+                     "ode_steps": nstep, "rhs_evals_deciding": urhs, "ode_steps_deciding": ustep,
+                     "failed_chains": n_failed,
                      "wall_s_timed_region": wall_max},
             "e2e": {"value": e2e_solves_all / e2e_wall_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
@@ -348,7 +353,10 @@ def run_b200(args):
             "gpu_launches": K,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak.value / 1e12, "unit": "TFLOP/s",
                          "frac": achieved_tf / (peak.value / 1e12), "traffic": traffic,
-                         "kernel": "rsf_mcmc_kernel<1>", "peak_source": "rsfm_measure_fp64_peak (DFMA chains, live)",
+                         "executed_incl_speculative": executed_tf,
+                         "executed_frac": executed_tf / (peak.value / 1e12),
+                         "kernel": (f"rsf_mcmc_spec_kernel<1> (speculation depth {spec_g}: {1 << spec_g} lanes per chain)"
+                                    if spec_g >= 2 else "rsf_mcmc_kernel<1,false> (one thread per chain)"), "peak_source": "rsfm_measure_fp64_peak (DFMA chains, live)",
                          "flops_convention": "35 per RHS + 480 per DOP853 step (SURVEY.md 8d)",
                          "hbm": {"achieved_gbs": alg_bytes / (dev_s / K) / 1e9, "peak_gbs": hbm_peak,
                                  "frac": alg_bytes / (dev_s / K) / 1e9 / hbm_peak,

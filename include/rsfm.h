@@ -127,6 +127,11 @@ int rsfm_run(rsfm_sampler *s, int32_t n_iters,
              double *samples_out_dev, double *sigma2_out_dev, uint8_t *accept_out_dev,
              double *draws_out_dev, void *stream);
 
+/* Depth g of the speculation tree rsfm_run will use for this sampler (0 = plain
+ * one-thread-per-chain kernel; g >= 2: 2^g lanes per chain evaluate the next g
+ * iterations' proposals concurrently).  Never affects results. */
+int rsfm_spec_depth(const rsfm_sampler *s);
+
 /* Same loop with host-supplied randomness:
  * proposals_dev [n_iters][d][C] (absolute proposals, or standard normals z when
  * proposals_are_z != 0: q' = q + L z), uniforms_dev [n_iters][C] (consumed only
@@ -150,10 +155,11 @@ int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double *sse_dev,
 int64_t rsfm_iteration(const rsfm_sampler *s);
 
 /* Work totals since rsfm_init, summed over chains on the device and copied to
- * out_host[7] = (forward solves of the chains = in-bounds proposals decided, RHS
+ * out_host[9] = (forward solves of the chains = in-bounds proposals decided, RHS
  * evaluations executed, steps attempted, accepted moves, chains with a non-zero
  * status, solves stopped early because rejection was already certain, solves
- * executed including speculative ones).  Synchronises the stream. */
+ * executed including speculative ones, RHS evaluations and steps of the deciding
+ * solves only).  Synchronises the stream. */
 int rsfm_get_totals(rsfm_sampler *s, uint64_t *out_host, void *stream);
 
 /* Pooled adaptation (extension): local sufficient

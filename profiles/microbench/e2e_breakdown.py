@@ -1,0 +1,16 @@
+"""Where the wall time of one public-API call goes (cfg 2: 1024 chains x 2000 iterations)."""
+import cProfile, importlib, io, os, pstats, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+pkg = importlib.import_module("bayesian-markov-chain-monte-carlo_b200")
+m = pkg.RateStateModel(); m.Dc = 1325.0
+np.random.seed(2024)
+_, _, data = m.evaluate()
+q0 = np.random.default_rng(1).uniform(200, 5000, 1024); q0[0] = 1000.0
+def call():
+    mc = pkg.MCMC(m, data, 1325.0, ["Uniform", 0.0, 1e4], q0, nsamples=2000, n_chains=1024, verbose=False, seed=1)
+    return mc.sample(False)
+call()
+t0 = time.perf_counter(); call(); print("wall", time.perf_counter() - t0)
+pr = cProfile.Profile(); pr.enable(); call(); pr.disable()
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(18); print(s.getvalue()[:3500])

@@ -7,9 +7,13 @@ m = pkg.RateStateModel()
 m.Dc = 1325.0
 _, acc, _ = m.evaluate()
 rng = np.random.default_rng(0)
+MODES = os.environ.get("MODES", "parity").split(",")
 for blk in (os.environ.get("BLOCKS", "32,64,128").split(",")):
     os.environ["RSFM_BLOCK"] = blk
-    for c in (32, 64, 128, 256, 512, 1024, 2048, 4096, 4736, 9472, 18944, 37888, 65536, 131072, 262144):
+    for mode in MODES:
+      m.integ_mode = mode
+      for c in (32, 64, 128, 256, 512, 1024, 2048, 4096, 4736, 9472, 18944, 37888, 65536, 131072, 262144):
+       for _once in (0,):
         dc = torch.from_numpy(rng.uniform(800, 2000, c)).cuda()
         m.evaluate_batch(dc, data=acc, want_acc=False)
         torch.cuda.synchronize()
@@ -20,4 +24,4 @@ for blk in (os.environ.get("BLOCKS", "32,64,128").split(",")):
             m.evaluate_batch(dc, data=acc, want_acc=False)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print(f"block {blk:>3s} C {c:7d}: {ms:8.3f} ms  {c / ms * 1e3:12.0f} solves/s", flush=True)
+        print(f"block {blk:>3s} {mode:6s} C {c:7d}: {ms:8.3f} ms  {c / ms * 1e3:12.0f} solves/s", flush=True)
