@@ -80,6 +80,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         : "memory");
 }
 
+// 8-byte asynchronous global->shared copy (LDGSTS), used to prefetch the next interval's stage values
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src_global)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_global) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Double-buffered tile stream over data[0 .. n).  Every thread of the block calls
 // begin() once per kernel, start_solve() before each pass over the series and
 // at(k) for k = 0, 1, 2, ... in order (block-uniform k).  A series of at most two
@@ -414,7 +422,7 @@ struct SolveOut {
     uint32_t nrhs, nstep;
 };
 
-constexpr int LTAB_STRIDE = 16;     // doubles per warp in the shared stage-value table (13 used)
+constexpr int LTAB_STRIDE = 32;     // doubles per warp: two buffers of 16 (11 stage values used in each)
 constexpr int NOM_STRIDE = 16;      // doubles per interval in the precomputed nominal table
 
 // Per-block shared scratch for the stage values of L: one shared table per warp (filled by lanes
@@ -448,7 +456,8 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
 {
     const int lane = threadIdx.x & 31;
     const int nthr = blockDim.x;
-    double *wtab = ls.tab + (threadIdx.x >> 5) * LTAB_STRIDE;
+    double *const wbase = ls.tab + (threadIdx.x >> 5) * LTAB_STRIDE;
+    double *wtab = wbase;                  // current buffer (wbase or wbase + 16)
     double *ptab = ls.priv + threadIdx.x;
     const ChainConst cc = make_chain_const(M, a, b, dc);
     const bool have_data = series.g != nullptr;
@@ -495,10 +504,16 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
         }
     };
 
+    // Nominal table (global, built by loading_table_kernel): entry k is fetched one interval ahead with
+    // cp.async into the other half of the warp's double buffer, so no load latency is ever exposed.
+    // Its key (t_k, h_k) is the recurrence every lane can run itself: t_{k+1} = t_k + ((t_k + dt) - t_k).
     const double *nom = ls.nom;
-    double pre = (nom != nullptr && lane < 11 && M.n_out > 1) ? nom[NOM_STRIDE + lane] : 0.0;
-    double pre_t = (nom != nullptr && M.n_out > 1) ? nom[NOM_STRIDE + 11] : 0.0;
-    double pre_h = (nom != nullptr && M.n_out > 1) ? nom[NOM_STRIDE + 12] : -1.0;
+    double tn = M.t_start;
+    if (nom != nullptr && M.n_out > 1) {
+        if (lane < 11) cp_async8(wbase + 16 + lane, nom + NOM_STRIDE + lane);      // entry 1 -> buffer 1
+        cp_async_commit();
+    }
+    const double inv_dt = 1.0 / M.delta_t;
     double acc_pending = 0.0, dk_pending = 0.0;      // output point whose SSE term is folded in one interval late
     bool have_pending = false;
     int fast_resume = 0;
@@ -506,15 +521,16 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
     for (int k = 1; k < M.n_out; k++) {
         const double dk = have_data ? series.at(k) : 0.0;
         if (nom != nullptr) {
-            // install the nominal entry of this interval (fetched one interval ahead) as the warp's table
+            // install the nominal entry of this interval (buffer k & 1) and prefetch the next one
+            cp_async_wait_all();
             __syncwarp();
-            if (lane < 11) wtab[lane] = pre;
-            __syncwarp();
-            tab_t = pre_t; tab_h = pre_h;
+            wtab = wbase + ((k & 1) << 4);
+            const double xn = tn + M.delta_t;
+            tab_t = tn; tab_h = xn - tn;
+            tn = tn + tab_h;
             if (k + 1 < M.n_out) {
-                if (lane < 11) pre = nom[(size_t)(k + 1) * NOM_STRIDE + lane];
-                pre_t = nom[(size_t)(k + 1) * NOM_STRIDE + 11];
-                pre_h = nom[(size_t)(k + 1) * NOM_STRIDE + 12];
+                if (lane < 11) cp_async8(wbase + (((k + 1) & 1) << 4) + lane, nom + (size_t)(k + 1) * NOM_STRIDE + lane);
+                cp_async_commit();
             }
         }
         // SSE term of the previous output point (its division overlaps this interval's first stages)
@@ -691,7 +707,9 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
         // ---- output point k: RateStateModel.py:384-388, MCMC.py:387 ----
         double accv = 0.0;
         if (running) {
-            accv = (V - vprev) / M.delta_t;
+            const double dv = V - vprev;
+            const double qd = dv * inv_dt;                        // (V_k - V_{k-1}) / delta_t  (:388):
+            accv = fma(fma(-qd, M.delta_t, dv), inv_dt, qd);      // reciprocal + one correction = correctly rounded
             vprev = V;
             if (failed && out.filled == M.n_out) out.filled = k + 1;
         }

@@ -937,7 +937,7 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
     }
 }
 
-// depth of the speculation tree for C chains: the largest g with C 2^g threads <= two warps per SMSP
+// depth of the speculation tree for C chains: the largest g with C 2^g threads <= one warp per SMSP
 static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
 {
     if (A.deterministic || s->cfg.adapt_mode == RSFM_ADAPT_COMPAT) return 0;
@@ -948,7 +948,7 @@ static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
     if (want >= 2 && want <= 5) return want;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-    const long long cap = (long long)sms * 4 * 32 * 2;        // up to two warps per SMSP (measured optimum)
+    const long long cap = (long long)sms * 4 * 32;            // one warp per SMSP (measured optimum)
     int g = 0;
     while (g < 5 && ((long long)s->C << (g + 1)) <= cap) g++;
     return g >= 2 ? g : 0;
