@@ -222,6 +222,7 @@ __device__ __forceinline__ double loading_of(const ModelK &M, double t)
 
 struct ChainConst {
     double b, inv_a, w, kV, voa0, k1e, mu_ref;
+    double cq[6], qscale;      // (1+f)^q - 1 = f (cq0 + cq1 f + ... + cq5 f^5), q = -b/a; qscale = 1 + |q|
     // w = V_ref/Dc, kV = k' V_ref with k' = 0.1/Dc (RateStateModel.py:324), voa0 = V_ref/a,
     // k1e = k1 when RadiationDamping else 0 (:349)
 };
@@ -236,6 +237,14 @@ __device__ __forceinline__ ChainConst make_chain_const(const ModelK &M, double a
     c.voa0 = M.V_ref * c.inv_a;
     c.k1e = M.damping ? M.k1 : 0.0;
     c.mu_ref = M.mu_ref;
+    const double q = -b * c.inv_a;
+    c.cq[0] = q;
+    c.cq[1] = c.cq[0] * (q - 1.0) / 2.0;
+    c.cq[2] = c.cq[1] * (q - 2.0) / 3.0;
+    c.cq[3] = c.cq[2] * (q - 3.0) / 4.0;
+    c.cq[4] = c.cq[3] * (q - 4.0) / 5.0;
+    c.cq[5] = c.cq[4] * (q - 5.0) / 6.0;
+    c.qscale = 1.0 + fabs(q);
     return c;
 }
 
@@ -367,6 +376,146 @@ __device__ __forceinline__ void dop853_step_impl(const ChainConst &cc, const Ste
     const double muN = mu + h * bM, thN = th + h * bT, VN = I.V + h * bV;
     // error norms over the common denominator D = (sk0 sk1 sk2)^2 (no divisions):
     //   ||e5/sk||^2 = A/D, ||e3/sk||^2 = B/D  with  A = sum (e5_i p_i)^2,  p_i = prod_{j != i} sk_j
+    const double k0 = I.atol + I.rtol * fmax(fabs(mu), fabs(muN));
+    const double k1 = I.atol + I.rtol * fmax(fabs(th), fabs(thN));
+    const double k2 = I.atol + I.rtol * fmax(fabs(I.V), fabs(VN));
+    const double p0 = k1 * k2, p1 = k0 * k2, p2 = k0 * k1;
+    const double dd = k0 * p0;
+    const double e3m = (bM - TB.bhh1 * k1m - TB.bhh2 * k9m - TB.bhh3 * k3m) * p0;
+    const double e3t = (bT - TB.bhh1 * k1t - TB.bhh2 * k9t - TB.bhh3 * k3t) * p1;
+    const double e3v = (bV - TB.bhh1 * k1v - TB.bhh2 * k9v - TB.bhh3 * k12v) * p2;
+    const double e5m = (TB.e1 * k1m + TB.e6 * k6m + TB.e7 * k7m + TB.e8 * k8m + TB.e9 * k9m + TB.e10 * k10m +
+                        TB.e11 * k2m + TB.e12 * k3m) * p0;
+    const double e5t = (TB.e1 * k1t + TB.e6 * k6t + TB.e7 * k7t + TB.e8 * k8t + TB.e9 * k9t + TB.e10 * k10t +
+                        TB.e11 * k2t + TB.e12 * k3t) * p1;
+    const double e5v = eV * p2;
+    const double B = e3m * e3m + e3t * e3t + e3v * e3v;
+    const double A = e5m * e5m + e5t * e5t + e5v * e5v;
+    O.muN = muN; O.thN = thN; O.VN = VN; O.errA = A; O.den3 = 3.0 * (A + 0.01 * B) * (dd * dd); O.L12 = L12;
+    O.rth = rth;
+}
+
+// ---------------------------------------------------------------------------
+// Fast step: the same DOP853 step as dop853_step_impl, organised for a short dependency chain.
+// ---------------------------------------------------------------------------
+// One warp per SM sub-partition is latency-bound: a stage costs (dependent FP64 ops) x 8 cycles.  The
+// textbook order  theta_s -> f -> log1p -> temp -> expm1 -> theta'  is a 20-op chain.  Here
+//     v/V_ref = e^temp = e^A (1+f)^q,   A = (mu_s - mu_ref)/a,   q = -b/a,
+// so with u = expm1(A) (a series in A, the mu path) and g = (1+f)^q - 1 (a binomial series in f, the
+// theta path), E = v/V_ref - 1 = u + g + u g: the two series are independent and overlap.  Stage
+// arguments are formed in the scaled variables directly,
+//     f_s = f_0 + h w  sum_j a_sj theta'_j ,   A_s = A_0 + (h/a) sum_j a_sj mu'_j ,
+// with everything except the newest stage's term pre-accumulated while that stage is still being
+// evaluated, and the newest mu' split into its early part d0 = k'V_ref (L - E) and the radiation-
+// damping correction c = k1 V' (RateStateModel.py:351), which arrives later and enters through
+// e^(A + delta) - 1 = u + delta (1 + u) (exact to O(delta^2) ~ 1e-20).  Chain per stage: 13 ops.
+// Values agree with the textbook order to rounding; both are the same function of (mu_s, theta_s).
+struct StageOut { double km, kt, kv, d0, c; };
+
+__device__ __forceinline__ void rsf_stage_fast(const ChainConst &cc, double fs, double As, double dl, double th1,
+                                               double kVL, double &rth, StageOut &o, bool &bad)
+{
+    double p = fma(cc.cq[5], fs, cc.cq[4]);
+    p = fma(p, fs, cc.cq[3]);
+    p = fma(p, fs, cc.cq[2]);
+    p = fma(p, fs, cc.cq[1]);
+    p = fma(p, fs, cc.cq[0]);
+    const double g = p * fs;                                    // (1+f)^q - 1
+    double qq = (As + TB.ex[0]) * TB.ex[1];
+    qq = fma(qq, As, TB.ex[2]);
+    qq = fma(qq, As, TB.ex[3]);
+    qq = fma(qq, As, TB.ex[4]);
+    qq = fma(qq, As, TB.ex[5]);
+    const double u = fma(As * As, qq, As);                      // expm1(A)
+    const double E0 = fma(u, g, u) + g;
+    const double E = fma(dl, E0, E0) + dl;                      // v / V_ref - 1
+    o.kt = -(fma(E, fs, E) + fs);                               // theta'
+    o.d0 = fma(-cc.kV, E, kVL);                                 // k' V_ref (L - E)
+    const double voa = fma(cc.voa0, E, cc.voa0);                // v / a
+    const double e0 = fma(-th1, rth, 1.0);
+    double r = fma(rth, e0, rth);
+    r = fma(r, fma(-th1, r, 1.0), r);
+    rth = r;
+    const double sb = (cc.b * r) * o.kt;
+    const double v0 = voa * (o.d0 - sb);
+    o.c = cc.k1e * v0;
+    o.km = o.d0 - o.c;                                          // mu' with radiation damping
+    o.kv = fma(-(voa * cc.k1e), v0, v0);                        // V'
+    bad = bad || !(fabs(fs) * cc.qscale < 0.001953125 && fabs(As) < 0.015625 && fabs(e0) < 6.0e-5);
+}
+
+__device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const StepIn &I, const double *Lp, int ls,
+                                                 StepOut &O, bool &bad)
+{
+    const double h = I.h, mu = I.mu, th = I.th, k1m = I.k1m, k1t = I.k1t, k1v = I.k1v;
+    double rth = I.rth;
+    const double hw = h * cc.w, ih = h * cc.inv_a;
+    const double f0 = fma(cc.w, th, -1.0), A0 = (mu - cc.mu_ref) * cc.inv_a;
+    double k2m, k2t, k3m, k3t, k4m, k4t, k5m, k5t, k6m, k6t, k7m, k7t, k8m, k8t, k9m, k9t, k10m, k10t;
+    double k9v, k12v, bV, eV;
+    StageOut so;
+    // PT / PM: sums over the already-known stages; (NEW) the coefficient of the stage still in flight
+#define RSFM_STAGE(IDX, PT, PM, ANEW)                                                                     \
+    {                                                                                                      \
+        const double pt__ = (PT), pm__ = (PM);                                                             \
+        const double fs__ = fma(hw * (ANEW), so.kt, fma(hw, pt__, f0));                                    \
+        const double th__ = fma(h * (ANEW), so.kt, fma(h, pt__, th));                                      \
+        const double As__ = fma(ih * (ANEW), so.d0, fma(ih, pm__, A0));                                    \
+        const double dl__ = -(ih * (ANEW)) * so.c;                                                         \
+        rsf_stage_fast(cc, fs__, As__, dl__, th__, cc.kV * Lp[(IDX) * ls], rth, so, bad);                  \
+    }
+    // stage 2: the "stage in flight" is k1 itself (complete: no damping split)
+    so.kt = k1t; so.d0 = k1m; so.c = 0.0;
+    RSFM_STAGE(0, 0.0, 0.0, TB.a21);
+    k2m = so.km; k2t = so.kt;
+    RSFM_STAGE(1, TB.a31 * k1t, TB.a31 * k1m, TB.a32);
+    k3m = so.km; k3t = so.kt;
+    RSFM_STAGE(2, TB.a41 * k1t, TB.a41 * k1m, TB.a43);
+    k4m = so.km; k4t = so.kt;
+    RSFM_STAGE(3, TB.a51 * k1t + TB.a53 * k3t, TB.a51 * k1m + TB.a53 * k3m, TB.a54);
+    k5m = so.km; k5t = so.kt;
+    RSFM_STAGE(4, TB.a61 * k1t + TB.a64 * k4t, TB.a61 * k1m + TB.a64 * k4m, TB.a65);
+    k6m = so.km; k6t = so.kt;
+    bV = TB.b1 * k1v + TB.b6 * so.kv;
+    eV = TB.e1 * k1v + TB.e6 * so.kv;
+    RSFM_STAGE(5, TB.a71 * k1t + TB.a74 * k4t + TB.a75 * k5t, TB.a71 * k1m + TB.a74 * k4m + TB.a75 * k5m, TB.a76);
+    k7m = so.km; k7t = so.kt;
+    bV += TB.b7 * so.kv; eV += TB.e7 * so.kv;
+    RSFM_STAGE(6, TB.a81 * k1t + TB.a84 * k4t + TB.a85 * k5t + TB.a86 * k6t,
+               TB.a81 * k1m + TB.a84 * k4m + TB.a85 * k5m + TB.a86 * k6m, TB.a87);
+    k8m = so.km; k8t = so.kt;
+    bV += TB.b8 * so.kv; eV += TB.e8 * so.kv;
+    RSFM_STAGE(7, TB.a91 * k1t + TB.a94 * k4t + TB.a95 * k5t + TB.a96 * k6t + TB.a97 * k7t,
+               TB.a91 * k1m + TB.a94 * k4m + TB.a95 * k5m + TB.a96 * k6m + TB.a97 * k7m, TB.a98);
+    k9m = so.km; k9t = so.kt; k9v = so.kv;
+    bV += TB.b9 * k9v; eV += TB.e9 * k9v;
+    RSFM_STAGE(8, TB.a101 * k1t + TB.a104 * k4t + TB.a105 * k5t + TB.a106 * k6t + TB.a107 * k7t + TB.a108 * k8t,
+               TB.a101 * k1m + TB.a104 * k4m + TB.a105 * k5m + TB.a106 * k6m + TB.a107 * k7m + TB.a108 * k8m, TB.a109);
+    k10m = so.km; k10t = so.kt;
+    bV += TB.b10 * so.kv; eV += TB.e10 * so.kv;
+    // stage 11 -> k2 slot
+    RSFM_STAGE(9,
+               TB.a111 * k1t + TB.a114 * k4t + TB.a115 * k5t + TB.a116 * k6t + TB.a117 * k7t + TB.a118 * k8t + TB.a119 * k9t,
+               TB.a111 * k1m + TB.a114 * k4m + TB.a115 * k5m + TB.a116 * k6m + TB.a117 * k7m + TB.a118 * k8m + TB.a119 * k9m,
+               TB.a1110);
+    k2m = so.km; k2t = so.kt;
+    bV += TB.b11 * so.kv; eV += TB.e11 * so.kv;
+    // stage 12 -> k3 slot, at x + h
+    const double L12 = Lp[10 * ls];
+    RSFM_STAGE(10,
+               TB.a121 * k1t + TB.a124 * k4t + TB.a125 * k5t + TB.a126 * k6t + TB.a127 * k7t + TB.a128 * k8t + TB.a129 * k9t +
+                   TB.a1210 * k10t,
+               TB.a121 * k1m + TB.a124 * k4m + TB.a125 * k5m + TB.a126 * k6m + TB.a127 * k7m + TB.a128 * k8m + TB.a129 * k9m +
+                   TB.a1210 * k10m,
+               TB.a1211);
+    k3m = so.km; k3t = so.kt; k12v = so.kv;
+    bV += TB.b12 * k12v; eV += TB.e12 * k12v;
+#undef RSFM_STAGE
+    const double bM = TB.b1 * k1m + TB.b6 * k6m + TB.b7 * k7m + TB.b8 * k8m + TB.b9 * k9m + TB.b10 * k10m +
+                      TB.b11 * k2m + TB.b12 * k3m;
+    const double bT = TB.b1 * k1t + TB.b6 * k6t + TB.b7 * k7t + TB.b8 * k8t + TB.b9 * k9t + TB.b10 * k10t +
+                      TB.b11 * k2t + TB.b12 * k3t;
+    const double muN = mu + h * bM, thN = th + h * bT, VN = I.V + h * bV;
     const double k0 = I.atol + I.rtol * fmax(fabs(mu), fabs(muN));
     const double k1 = I.atol + I.rtol * fmax(fabs(th), fabs(thN));
     const double k2 = I.atol + I.rtol * fmax(fabs(I.V), fabs(VN));
@@ -571,7 +720,7 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
                 in.h = xend - t; in.mu = mu; in.th = th; in.V = V; in.k1m = k1m; in.k1t = k1t; in.k1v = k1v; in.rth = rth;
                 in.atol = M.atol; in.rtol = M.rtol;
                 StepOut so;
-                dop853_step_impl<true>(cc, in, wtab, 1, so, bad);
+                dop853_step_fast(cc, in, wtab, 1, so, bad);
                 const double e0 = (f1m - k1m) * p0, e1 = (f1t - k1t) * p1, e2 = (f1v - k1v) * p2;
                 const double Ne = e0 * e0 + e1 * e1 + e2 * e2;
                 const double hm2 = hmax * hmax, hm4 = hm2 * hm2, hm8 = hm4 * hm4, hm16 = hm8 * hm8;
@@ -663,7 +812,7 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
             in.atol = M.atol; in.rtol = M.rtol;
             StepOut so;
             bool bad = false;
-            dop853_step_impl<true>(cc, in, Lsrc, lstride, so, bad);
+            dop853_step_fast(cc, in, Lsrc, lstride, so, bad);
             if (stepping && bad) dop853_step_general(&cc, &in, Lsrc, lstride, &so);
             // err <= 1   <=>   h^2 errA^2 <= den3   (no sqrt, no division; NaN rejects; 0 <= 0 accepts)
             const bool accept = (h * h) * (so.errA * so.errA) <= so.den3;
