@@ -727,7 +727,7 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
                 const double lim = 1.0e-4 * D;
                 const bool h1max = Ne * hm16 <= lim * hm2 && Nf * hm16 <= lim && fmax(Ne, Nf * hm2) > 1e-30 * D * hm2;
                 const bool entry = !(0.1 * hmax <= fabs(t) * uround) && ((t + 1.01 * hmax - xend) > 0.0);
-                const bool accept = (in.h * in.h) * (so.errA * so.errA) <= so.den3;
+                const bool accept = so.errA < 1e140 && (in.h * in.h) * (so.errA * so.errA) <= so.den3;
                 const bool ok = h0max && h1max && entry && accept && !bad;
                 if (__all_sync(FULL_MASK, !running || ok)) {
                     if (running) {
@@ -814,8 +814,10 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
             bool bad = false;
             dop853_step_fast(cc, in, Lsrc, lstride, so, bad);
             if (stepping && bad) dop853_step_general(&cc, &in, Lsrc, lstride, &so);
-            // err <= 1   <=>   h^2 errA^2 <= den3   (no sqrt, no division; NaN rejects; 0 <= 0 accepts)
-            const bool accept = (h * h) * (so.errA * so.errA) <= so.den3;
+            // err <= 1   <=>   h^2 errA^2 <= den3   (no sqrt, no division; NaN rejects; 0 <= 0 accepts).
+            // errA < 1e140 keeps the squares finite: an unstable step whose error norm overflows must be
+            // rejected (dop853.f gets inf * 0 = NaN there), not pass as inf <= inf.
+            const bool accept = so.errA < 1e140 && (h * h) * (so.errA * so.errA) <= so.den3;
 
             if (stepping) {
                 out.nstep++;

@@ -1,0 +1,64 @@
+"""BASELINE.json configs 3-5 at reduced iteration counts (capability + throughput data points, not bench lines).
+
+usage: python profiles/microbench/run_configs.py cfg3|cfg4|cfg5 [iters]
+"""
+import importlib, json, os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+pkg = importlib.import_module("bayesian-markov-chain-monte-carlo_b200")
+which = sys.argv[1]
+rng = np.random.default_rng(0)
+
+
+def report(name, mc, out, wall, extra=None):
+    d = mc.diagnostics()
+    line = {"config": name, "wall_s": wall, "solves": mc.stats["nsolves"], "solves_per_s": mc.stats["nsolves"] / wall,
+            "executed_solves": mc.stats["nsolves_executed"], "accept_rate": float(np.mean(mc.acceptance_ratio)),
+            "rhat": d["rhat"], "ess_total": d["ess"], "ess_per_s": [e / wall for e in d["ess"]],
+            "post_mean": d["mean"], "post_sd": d["sd"], "failed_chains": mc.stats["failed_chains"]}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+if which == "cfg3":
+    # joint (a, b, Dc), pooled adaptive covariance, 65,536 chains
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+    c = int(os.environ.get("CHAINS", "65536"))
+    m = pkg.RateStateModel()
+    m.a, m.b, m.Dc = 0.011, 0.014, 1325.0
+    np.random.seed(2024)
+    _, _, data = m.evaluate()
+    q0 = np.stack([rng.uniform(0.009, 0.013, c), rng.uniform(0.012, 0.016, c), rng.uniform(800.0, 2500.0, c)], axis=1)
+    mc = pkg.MCMC(m, data, 1325.0, ["Uniform", 0.0, 1e4], q0, nsamples=iters, n_chains=c, verbose=False, seed=3,
+                  param_names=("a", "b", "Dc"), bounds=[[0.005, 0.02], [0.005, 0.03], [0.0, 1e4]], adapt="pooled",
+                  adapt_start=100)
+    t0 = time.perf_counter(); out = mc.sample(False); wall = time.perf_counter() - t0
+    report("cfg3: joint (a,b,Dc), pooled AM, %d chains, %d iters" % (c, iters), mc, out, wall,
+           {"n_adaptations": len(mc.adapt_history)})
+elif which == "cfg4":
+    # long series N = 1e5, VSTEP loading, stiff regime, 16,384 chains
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    c = int(os.environ.get("CHAINS", "16384"))
+    n = int(os.environ.get("NOUT", "100000"))
+    m = pkg.RateStateModel(number_time_steps=n, end_time=n * 0.1)
+    m.loading, m.vstep_period, m.vstep_factor = "vstep", 1000.0, 10.0
+    m.Dc = 0.05
+    np.random.seed(2024)
+    t0 = time.perf_counter(); _, acc, data = m.evaluate(); t_one = time.perf_counter() - t0
+    q0 = rng.uniform(0.03, 0.08, c)
+    mc = pkg.MCMC(m, data, 0.05, ["Uniform", 0.01, 1.0], q0, nsamples=iters, n_chains=c, verbose=False, seed=4)
+    t0 = time.perf_counter(); out = mc.sample(False); wall = time.perf_counter() - t0
+    report("cfg4: N=%d VSTEP stiff, %d chains, %d iters" % (n, c, iters), mc, out, wall,
+           {"single_solve_s": t_one, "rhs_per_solve": mc.stats["nrhs"] / max(mc.stats["nsolves_executed"], 1)})
+elif which == "cfg5":
+    # 131,072 chains per GPU (1M over 8 GPUs), Dc-only, R-hat / ESS at the end
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+    c = int(os.environ.get("CHAINS", "131072"))
+    m = pkg.RateStateModel(); m.Dc = 1325.0
+    np.random.seed(2024)
+    _, _, data = m.evaluate()
+    q0 = rng.uniform(200.0, 5000.0, c); q0[0] = 1000.0
+    mc = pkg.MCMC(m, data, 1325.0, ["Uniform", 0.0, 1e4], q0, nsamples=iters, n_chains=c, verbose=False, seed=5)
+    t0 = time.perf_counter(); out = mc.sample(False); wall = time.perf_counter() - t0
+    report("cfg5 shard: %d chains on one GPU, %d iters" % (c, iters), mc, out, wall)

@@ -181,3 +181,22 @@ def test_size_independent_properties_at_scale(cuda, pkg):
     assert np.all(sse[0::2] == 0.0)
     assert np.all(sse[1::2] == sse[1]) and sse[1] > 0
     assert np.all(out["status"].cpu().numpy() == 0)
+
+
+def test_unstable_step_is_rejected_after_velocity_jump(cuda, pkg, orc):
+    """Stiff regime with a 10x load-velocity jump (cfg-4 style): right after the jump the first trial step is
+    violently unstable; its error norm overflows and the step must be rejected like SciPy does (regression
+    test for the division-free accept test, which compared inf <= inf)."""
+    n, t_end = 2400, 240.0
+    kw = dict(loading=orc.LOAD_VSTEP, vstep_period=120.0, vstep_factor=10.0)
+    dcs = np.array([0.05, 0.1, 1.0])
+    m = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
+    m.loading, m.vstep_period, m.vstep_factor = "vstep", 120.0, 10.0
+    out = m.evaluate_batch(dcs)
+    assert np.all(out["status"].cpu().numpy() == 0)
+    acc_g = out["acc"].t().cpu().numpy()
+    _, acc_o, _ = orc.forward_batch(orc.make_model(number_time_steps=n, end_time=t_end, **kw), dcs, want_acc=True)
+    for i in range(len(dcs)):
+        assert np.all(np.isfinite(acc_g[i]))
+        scale = np.max(np.abs(acc_o[i]))
+        assert np.max(np.abs(acc_g[i] - acc_o[i])) <= 2e-5 * scale
