@@ -666,6 +666,7 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
     double acc_pending = 0.0, dk_pending = 0.0;      // output point whose SSE term is folded in one interval late
     bool have_pending = false;
     int fast_resume = 0;
+    bool was_bad = false;
 
     for (int k = 1; k < M.n_out; k++) {
         const double dk = have_data ? series.at(k) : 0.0;
@@ -812,8 +813,13 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
             in.atol = M.atol; in.rtol = M.rtol;
             StepOut so;
             bool bad = false;
-            dop853_step_fast(cc, in, Lsrc, lstride, so, bad);
+            // A warp whose stepping lanes all left the fast ranges on their previous step (stiff regime)
+            // goes straight to the general step; the fast one is retried every 64 steps.
+            const bool try_fast = !__all_sync(FULL_MASK, !stepping || was_bad) || (out.nstep & 63u) == 0u;
+            if (try_fast) dop853_step_fast(cc, in, Lsrc, lstride, so, bad);
+            else bad = true;
             if (stepping && bad) dop853_step_general(&cc, &in, Lsrc, lstride, &so);
+            if (stepping) was_bad = bad;
             // err <= 1   <=>   h^2 errA^2 <= den3   (no sqrt, no division; NaN rejects; 0 <= 0 accepts).
             // errA < 1e140 keeps the squares finite: an unstable step whose error norm overflows must be
             // rejected (dop853.f gets inf * 0 = NaN there), not pass as inf <= inf.
