@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "librsfm.so")
+LIB_PATH = os.environ.get("RSFM_LIB") or os.path.join(_PKG_DIR, "librsfm.so")   # RSFM_LIB: tuning builds only
 
 RSFM_MAX_PARAMS = 3
 

@@ -207,7 +207,7 @@ static int get_nominal_table(const ModelK &M, cudaStream_t stream, const double 
 // ---------------------------------------------------------------------------
 // forward batch
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 rsf_forward_kernel(ModelK M, int C, double a0, double b0, const double *__restrict__ dc_in,
                    const double *__restrict__ a_in, const double *__restrict__ b_in,
                    const double *__restrict__ data, double *__restrict__ acc_out,
@@ -551,8 +551,9 @@ struct RunArgs {
     int adapt_mode, adapt_interval;
 };
 
+// (128, 3): three resident blocks per SM (<= 168 registers); measured +5 % at saturating sizes
 template <int D, bool DET>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
 {
     __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
