@@ -8,7 +8,9 @@ from .rate_state_model import RateStateModel, A, B, MU_REF, V_REF, K1, START_TIM
 from .sampler import MCMC
 from .ndarray_json import save_object, load_object, numpy_array_encoder, numpy_array_decoder
 from .sharding import ChainShard
+from .driver import RSF, measure_execution_time
+from .posterior import gaussian_kde_pdf
 from . import _lib
 
-__all__ = ["RateStateModel", "MCMC", "save_object", "load_object", "numpy_array_encoder",
+__all__ = ["RateStateModel", "MCMC", "RSF", "measure_execution_time", "gaussian_kde_pdf", "save_object", "load_object", "numpy_array_encoder",
            "numpy_array_decoder", "ChainShard", "A", "B", "MU_REF", "V_REF", "K1", "START_TIME", "END_TIME"]

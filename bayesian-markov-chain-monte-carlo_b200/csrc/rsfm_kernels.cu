@@ -1199,6 +1199,46 @@ extern "C" int rsfm_chain_diagnostics(const double *samples_dev, int32_t n, int3
 }
 
 // ---------------------------------------------------------------------------
+// Gaussian kernel density estimate on a grid (posterior post-processing, RSF.py:734-737)
+// ---------------------------------------------------------------------------
+// pdf(x_g) = 1/(n bw sqrt(2 pi)) sum_i exp(-(x_g - x_i)^2 / (2 bw^2)); one block per grid point.
+__global__ void __launch_bounds__(256) kde_grid_kernel(const double *__restrict__ x, long long n,
+                                                        const double *__restrict__ grid, int G, double bw,
+                                                        double *__restrict__ pdf)
+{
+    const int gidx = blockIdx.x;
+    if (gidx >= G) return;
+    const double xg = grid[gidx];
+    const double inv2 = -0.5 / (bw * bw);
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const double d = xg - x[i];
+        acc += exp(d * d * inv2);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL_MASK, acc, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < 8 ? ws[threadIdx.x] : 0.0;
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(FULL_MASK, v, o);
+        if (threadIdx.x == 0) pdf[gidx] = v / ((double)n * bw * 2.5066282746310002);
+    }
+}
+
+extern "C" int rsfm_kde_grid(const double *samples_dev, int64_t n, const double *grid_dev, int32_t G, double bandwidth,
+                             double *pdf_out_dev, void *stream)
+{
+    if (!samples_dev || !grid_dev || !pdf_out_dev || n < 1 || G < 1 || !(bandwidth > 0.0))
+        return set_err(RSFM_ERR_INVALID, "rsfm_kde_grid: bad argument%s", "");
+    int rc = require_device();
+    if (rc) return rc;
+    kde_grid_kernel<<<G, 256, 0, (cudaStream_t)stream>>>(samples_dev, (long long)n, grid_dev, G, bandwidth, pdf_out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return RSFM_OK;
+}
+
+// ---------------------------------------------------------------------------
 // FP64 peak: 8 independent DFMA chains per thread, all SMs full
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double seed, double *sink)

@@ -34,7 +34,7 @@ class MCMC:
     def __init__(self, model, data, dc_true, qpriors, qstart, nsamples=100, lstm_model={},
                  adapt_interval=10, verbose=True, *, n_chains=1, seed=None, device=None,
                  param_names=("Dc",), bounds=None, deterministic_inputs=None, compat_adapt=None,
-                 adapt=None, adapt_start=100, shard=False, chain_id0=0, spec_depth=0, keep_on_device=False):
+                 adapt=None, adapt_start=100, shard=False, chain_id0=0, spec_depth=0, resume=None, keep_on_device=False):
         # reference attributes, MCMC.py:88-99
         self.model = model
         self.qstart = qstart
@@ -61,6 +61,7 @@ class MCMC:
         self.chain_id0 = int(chain_id0)        # global id of chain 0 when not sharding (Philox counter)
         self.keep_on_device = bool(keep_on_device)
         self.spec_depth = int(spec_depth)      # speculation tree depth: 0 auto, 1 off, 2..5 forced
+        self.resume = resume                   # checkpoint dict / JSON file from MCMC.checkpoint()
         if self.param_names not in (("Dc",), ("a", "b", "Dc")):
             raise ValueError("param_names must be ('Dc',) or ('a', 'b', 'Dc')")
         if compat_adapt is None:
@@ -143,6 +144,14 @@ class MCMC:
         cfg.adapt_mode = (_lib.ADAPT_COMPAT if self.compat_adapt else
                           _lib.ADAPT_POOLED if self.adapt == "pooled" else _lib.ADAPT_NONE)
         seed = self.seed
+        if self.resume is not None:
+            if isinstance(self.resume, str):
+                from .ndarray_json import load_object
+                self.resume = load_object(self.resume)
+            if self.resume is None:
+                raise ValueError("checkpoint could not be read")
+            seed = int(self.resume["seed"])            # the Philox key and chain ids are part of the state
+            id0 = int(self.resume["chain_id0"])
         if seed is None:
             # the reference draws from the global NumPy generator; derive the Philox key from it so
             # that np.random.seed(...) before the call makes runs reproducible here too
@@ -164,6 +173,8 @@ class MCMC:
                 chol0 = torch.empty((d * (d + 1) // 2, cl), dtype=torch.float64, device=dev)
                 _lib.check(lib.rsfm_get_state(handle, None, None, _lib.ptr(s2_0), _lib.ptr(chol0), None, None,
                                               None, None, stream), "rsfm_get_state")
+                if self.resume is not None:
+                    q0, s2_0 = self._apply_checkpoint(torch, lib, handle, dev, d, cl, stream)
                 ns = int(self.nsamples)
                 chain = torch.empty((ns + 1, d, cl), dtype=torch.float64, device=dev)
                 std2 = torch.empty((ns + 1, cl), dtype=torch.float64, device=dev)
@@ -187,6 +198,13 @@ class MCMC:
                                               _lib.ptr(nrhs), _lib.ptr(nstep), stream), "rsfm_get_state")
                 tot = (C.c_uint64 * 9)()
                 _lib.check(lib.rsfm_get_totals(handle, tot, stream), "rsfm_get_totals")
+                st_q = torch.empty((d, cl), dtype=torch.float64, device=dev)
+                st_sse = torch.empty(cl, dtype=torch.float64, device=dev)
+                st_s2 = torch.empty(cl, dtype=torch.float64, device=dev)
+                st_chol = torch.empty((d * (d + 1) // 2, cl), dtype=torch.float64, device=dev)
+                _lib.check(lib.rsfm_get_state(handle, _lib.ptr(st_q), _lib.ptr(st_sse), _lib.ptr(st_s2),
+                                              _lib.ptr(st_chol), None, None, None, None, stream), "rsfm_get_state")
+                self._final_state = (st_q, st_sse, st_s2, st_chol, int(lib.rsfm_iteration(handle)))
                 torch.cuda.synchronize(dev)
             finally:
                 lib.rsfm_destroy(handle)
@@ -292,6 +310,36 @@ class MCMC:
                     self.adapt_history.append((done, fac.copy()))
 
     # ------------------------------------------------------------------
+    # ------------------------------------------------------------------
+    def checkpoint(self, filename=None):
+        """State needed to continue the chains exactly where they stopped (the reference has no
+        checkpoint): current q, SSE, sigma^2, proposal factor, iteration count, seed.
+        With counter-based Philox draws, ``MCMC(..., resume=ckpt).sample()`` continues the very same
+        chains.  Returned as a dict of NumPy arrays and, if ``filename`` is given, written in the
+        reference's JSON ndarray format.  (Compat adaptation keeps a 10-sample ring that is not saved.)"""
+        if getattr(self, "_final_state", None) is None:
+            raise RuntimeError("call sample() first")
+        q, sse, s2, chol, iteration = self._final_state
+        ck = {"q": q.cpu().numpy(), "sse": sse.cpu().numpy(), "sigma2": s2.cpu().numpy(), "chol": chol.cpu().numpy(),
+              "iteration": int(iteration), "seed": int(self.seed_used), "chain_id0": int(self.stats["chain_id0"]),
+              "param_names": list(self.param_names), "n_chains_local": int(q.shape[1])}
+        if filename is not None:
+            from .ndarray_json import save_object
+            save_object(ck, filename)
+        return ck
+
+    def _apply_checkpoint(self, torch, lib, handle, dev, d, cl, stream):
+        ck = self.resume
+        if int(ck["n_chains_local"]) != cl or list(ck["param_names"]) != list(self.param_names):
+            raise ValueError("checkpoint does not match this sampler (chains / parameters)")
+        def dev_t(x, shape):
+            return torch.as_tensor(np.asarray(x, dtype=np.float64)).reshape(shape).to(dev).contiguous()
+        q = dev_t(ck["q"], (d, cl)); sse = dev_t(ck["sse"], (cl,)); s2 = dev_t(ck["sigma2"], (cl,))
+        chol = dev_t(ck["chol"], (d * (d + 1) // 2, cl))
+        _lib.check(lib.rsfm_set_state(handle, _lib.ptr(q), _lib.ptr(sse), _lib.ptr(s2), _lib.ptr(chol),
+                                      int(ck["iteration"]), stream), "rsfm_set_state")
+        return q, s2
+
     def diagnostics(self, max_lag=None):
         """Split-R-hat and bulk ESS of the post-burn-in draws, pooled over ranks."""
         from .diagnostics import chain_diagnostics

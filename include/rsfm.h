@@ -176,6 +176,12 @@ int rsfm_chain_diagnostics(const double *samples_dev, int32_t n, int32_t d, int3
                            int32_t max_lag, double *mean_dev, double *var_dev, double *ess_dev,
                            void *stream);
 
+/* Gaussian kernel density estimate of samples_dev [n] on grid_dev [G] with the given
+ * bandwidth (s.d. of the kernel); pdf_out_dev [G].  Replaces scipy.stats.gaussian_kde(...).pdf
+ * as used by RSF.plot_dist (RSF.py:734-737); the Scott bandwidth is chosen by the caller. */
+int rsfm_kde_grid(const double *samples_dev, int64_t n, const double *grid_dev, int32_t G, double bandwidth,
+                  double *pdf_out_dev, void *stream);
+
 /* FP64 roofline denominator: runs a dependent-free DFMA kernel for about
  * `millis` ms on the current device and returns the sustained FP64 FMA rate in
  * FLOP/s (2 flops per DFMA) through *flops_out.  Synchronises. */

@@ -202,3 +202,59 @@ def test_speculative_kernel_is_bit_identical(cuda, pkg, d, names, q0, bounds):
         assert stats["nsolves"] == ref[3]["nsolves"]
         assert stats["nsolves_executed"] > stats["nsolves"]          # speculation did extra work
     assert 0 < ref[2].mean() < 1
+
+
+def test_checkpoint_resume_continues_the_same_chains(cuda, pkg, tmp_path):
+    """Counter-based RNG + saved (q, SSE, sigma^2, proposal, iteration): 30 iterations == 18 + resume + 12."""
+    g = load_golden("sse_grid.json")
+    model = pkg.RateStateModel()
+    q0 = np.linspace(900.0, 2000.0, 40)
+    kw = dict(n_chains=40, verbose=False)
+    full = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=30, seed=21, **kw)
+    full.sample(False)
+    chain_full = full.samples_device.cpu().numpy()              # [31, 1, 40]
+    part1 = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=18, seed=21, **kw)
+    part1.sample(False)
+    fn = str(tmp_path / "ckpt.json")
+    part1.checkpoint(fn)
+    part2 = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=12, resume=fn, **kw)
+    part2.sample(False)
+    assert np.array_equal(part1.samples_device.cpu().numpy(), chain_full[:19])
+    assert np.array_equal(part2.samples_device.cpu().numpy()[1:], chain_full[19:])
+    assert np.array_equal(part2.std2_device.cpu().numpy()[1:], full.std2_device.cpu().numpy()[19:])
+
+
+def test_rsf_driver_facade(cuda, pkg, capsys, tmp_path, monkeypatch):
+    """main.py's flow through the RSF facade: batched data generation, JSON round trip, one MCMC per Dc,
+    inference() returns elapsed seconds (q11)."""
+    monkeypatch.chdir(tmp_path)
+    problem = pkg.RSF(number_slip_values=3, lowest_slip_value=500.0, largest_slip_value=2500.0, qstart=1000.0,
+                      qpriors=["Uniform", 0.0, 10000.0])
+    assert np.array_equal(problem.dc_list, [500.0, 1500.0, 2500.0]) and problem.num_dc == 3
+    problem.model = pkg.RateStateModel(number_time_steps=500)
+    np.random.seed(1)
+    problem.data = problem.generate_time_series()
+    assert problem.data.shape == (1500,) and problem.model.Dc == 2500.0
+    # same data as three separate evaluate() calls with the same global seed (reference layout)
+    np.random.seed(1)
+    m2 = pkg.RateStateModel(number_time_steps=500)
+    ref = []
+    for dc in problem.dc_list:
+        m2.Dc = dc
+        ref.append(m2.evaluate()[2])
+    assert np.allclose(problem.data, np.concatenate(ref), rtol=1e-12, atol=0)
+    problem.format = "json"
+    problem.mcmc_kwargs = {"verbose": False, "seed": 3}
+    elapsed = problem.inference(nsamples=40)
+    assert isinstance(elapsed, float) and elapsed > 0
+    out = capsys.readouterr().out
+    assert "--- Dc is 500.0 ---" in out and "--- Dc is 2500.0 ---" in out
+    assert (tmp_path / "data.json").exists()
+    for dc in problem.dc_list:
+        r = problem.results[dc]
+        assert r["samples"].shape == (1, 21)
+    # the 1500 chain should sit much closer to 1500 than the 500 chain
+    assert abs(problem.results[1500.0]["samples"].mean() - 1500.0) < 300.0
+    problem.format = "mysql"
+    with pytest.raises(NotImplementedError):
+        problem.prepare_data(problem.data)
