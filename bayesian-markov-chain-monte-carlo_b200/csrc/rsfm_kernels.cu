@@ -870,7 +870,8 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
                 const double lnu = log(u);
                 const double thr = ss - 2.0 * s2 * lnu;
                 // a node stopped at its bound is decided only if that bound is at least the threshold
-                if (p_early && !(plim >= thr)) { stopped = true; continue; }
+                // (the root's bound IS its threshold; m > 1 also guarantees progress if the state is NaN)
+                if (p_early && m > 1 && !(plim >= thr)) { stopped = true; continue; }
                 double la = 0.5 * (ss - psse) / s2;
                 if (la > 0.0) la = 0.0;
                 acc = la > lnu;

@@ -258,3 +258,58 @@ def test_rsf_driver_facade(cuda, pkg, capsys, tmp_path, monkeypatch):
     problem.format = "mysql"
     with pytest.raises(NotImplementedError):
         problem.prepare_data(problem.data)
+
+
+def test_joint_abdc_posterior_matches_cpu_chain(cuda, pkg, orc):
+    """d = 3 (a, b, Dc) with pooled adaptive covariance (extension: the reference is d = 1 only).  Oracle for
+    the posterior: an independent CPU random-walk Metropolis (NumPy + the C forward model) with the same
+    likelihood, sigma^2 Gibbs step and box prior.  Posterior means must agree within Monte-Carlo error."""
+    rng = np.random.default_rng(42)
+    truth = (0.011, 0.014, 1325.0)
+    om = orc.make_model(Dc=truth[2], a=truth[0], b=truth[1])
+    _, acc_true, _ = orc.forward(om)
+    data = acc_true + np.abs(acc_true) * rng.standard_normal(acc_true.size)
+    bounds = np.array([[0.0100, 0.0120], [0.0130, 0.0150], [800.0, 2200.0]])
+    n, n0 = data.size, 0.01
+
+    def sse(q):
+        m = orc.make_model(Dc=q[2], a=q[0], b=q[1])
+        return orc.sse(orc.forward(m)[1], data)
+
+    # ---- CPU reference chain ----
+    q = np.array(truth)
+    ss = sse(q)
+    s2 = ss / (n - 3)
+    step = np.array([2.5e-4, 2.5e-4, 60.0])
+    draws = []
+    for it in range(6000):
+        qn = q + step * rng.standard_normal(3)
+        if np.all((qn > bounds[:, 0]) & (qn < bounds[:, 1])):
+            ssn = sse(qn)
+            if min(0.0, 0.5 * (ss - ssn) / s2) > np.log(rng.random()):
+                q, ss = qn, ssn
+        s2 = 1.0 / (rng.gamma(0.5 * (n0 + n)) / (0.5 * (n0 * s2 + ss)))
+        if it >= 1000:
+            draws.append(q.copy())
+    draws = np.array(draws)
+    cpu_mean, cpu_sd = draws.mean(axis=0), draws.std(axis=0)
+    # batch-means MCSE of the CPU chain
+    bm = draws[: (len(draws) // 50) * 50].reshape(50, -1, 3).mean(axis=1)
+    cpu_mcse = bm.std(axis=0, ddof=1) / np.sqrt(50)
+
+    # ---- GPU: 1024 chains, pooled adaptive Metropolis ----
+    c = 1024
+    q0 = np.stack([rng.uniform(0.0105, 0.0115, c), rng.uniform(0.0135, 0.0145, c), rng.uniform(1000.0, 1800.0, c)], axis=1)
+    mc = pkg.MCMC(pkg.RateStateModel(), data, truth[2], ["Uniform", 0.0, 1e4], q0, nsamples=500, n_chains=c,
+                  verbose=False, seed=8, param_names=("a", "b", "Dc"), bounds=bounds, adapt="pooled", adapt_start=60)
+    out = mc.sample(False)                                     # [c, 3, 251]
+    assert out.shape == (c, 3, 251) and len(mc.adapt_history) > 10
+    chain_means = out.mean(axis=2)                             # [c, 3]
+    gpu_mean = chain_means.mean(axis=0)
+    gpu_mcse = chain_means.std(axis=0, ddof=1) / np.sqrt(c)
+    gpu_sd = out.transpose(1, 0, 2).reshape(3, -1).std(axis=1)
+    for j in range(3):
+        tol = 5.0 * np.hypot(cpu_mcse[j], gpu_mcse[j]) + 0.02 * cpu_sd[j]
+        assert abs(gpu_mean[j] - cpu_mean[j]) < tol, (j, gpu_mean[j], cpu_mean[j], tol)
+        assert 0.8 < gpu_sd[j] / cpu_sd[j] < 1.25, (j, gpu_sd[j], cpu_sd[j])
+    assert 0.1 < mc.acceptance_ratio.mean() < 0.7
