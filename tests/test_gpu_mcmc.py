@@ -313,3 +313,17 @@ def test_joint_abdc_posterior_matches_cpu_chain(cuda, pkg, orc):
         assert abs(gpu_mean[j] - cpu_mean[j]) < tol, (j, gpu_mean[j], cpu_mean[j], tol)
         assert 0.8 < gpu_sd[j] / cpu_sd[j] < 1.25, (j, gpu_sd[j], cpu_sd[j])
     assert 0.1 < mc.acceptance_ratio.mean() < 0.7
+
+
+@pytest.mark.timeout(120)
+def test_non_finite_state_terminates(cuda, pkg):
+    """A NaN in the observed series makes every sum of squares NaN: nothing can be accepted, and both the
+    one-thread-per-chain and the speculative kernel must still finish (no spin on an undecidable round)."""
+    data = np.zeros(500)
+    data[17] = np.nan
+    for depth in (1, 0):
+        mc = pkg.MCMC(pkg.RateStateModel(), data, 1000.0, ["Uniform", 0.0, 1e4], 1000.0, nsamples=8, n_chains=8,
+                      verbose=False, seed=1, spec_depth=depth)
+        out = mc.sample(False)
+        assert out.shape == (8, 1, 5)
+        assert np.all(out == 1000.0) and mc.accepts.sum() == 0
