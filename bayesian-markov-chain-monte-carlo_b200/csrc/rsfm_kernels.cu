@@ -953,6 +953,9 @@ static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
     const long long cap = (long long)sms * 4 * 32;            // one warp per SMSP (measured optimum)
     int g = 0;
     while (g < 5 && ((long long)s->C << (g + 1)) <= cap) g++;
+    // measured: a 3-node tree (4 lanes per chain) still pays at up to two warps per sub-partition
+    // (C = 8,192: 13.0 M vs 9.1 M solves/s), deeper trees do not
+    if (g < 2 && ((long long)s->C << 2) <= 2 * cap) g = 2;
     return g >= 2 ? g : 0;
 }
 
