@@ -217,6 +217,10 @@ __device__ __noinline__ double loading_rel(int loading, double t_start, double p
 
 __device__ __forceinline__ double loading_of(const ModelK &M, double t)
 {
+    if (M.loading == RSFM_LOAD_VSTEP) {            // piecewise constant: cheap enough to inline
+        const long long i = (long long)floor((t - M.t_start) / M.vstep_period);
+        return (i & 1) ? M.vstep_factor - 1.0 : 0.0;
+    }
     return loading_rel(M.loading, M.t_start, M.vstep_period, M.vstep_factor, t);
 }
 
@@ -288,10 +292,21 @@ __device__ __forceinline__ void rsf_rhs(const ChainConst &c, double L, double mu
         r = fma(r, fma(-th, r, 1.0), r);
         bad = bad || !(fabs(f) < 0.001953125 && fabs(temp) < 0.015625 && fabs(e0) < 6.0e-5);
     } else {
-        lg = log1p(f);
-        const double temp = c.inv_a * fma(-c.b, lg, dmu0);
-        E = expm1(temp);
+        // general range (stiff regime, large excursions): the reference's formulas as written,
+        // v = V_ref exp((mu - mu_ref - b log(V_ref theta/Dc))/a), RateStateModel.py:336-346
+        const double x = c.w * th;
+        const double temp = c.inv_a * fma(-c.b, log(x), dmu0);
+        const double ev = exp(temp);                                // v / V_ref
         r = 1.0 / th;
+        dth = 1.0 - ev * x;
+        const double voa_g = c.voa0 * ev;
+        const double d0_g = c.kV * ((L + 1.0) - ev);
+        const double s_g = (c.b * r) * dth;
+        const double v0_g = voa_g * (d0_g - s_g);
+        dmu = fma(-c.k1e, v0_g, d0_g);
+        dV = fma(-(voa_g * c.k1e), v0_g, v0_g);
+        rth = r;
+        return;
     }
     dth = -(fma(E, f, E) + f);
     const double voa = fma(c.voa0, E, c.voa0);                  // v / a
