@@ -5,19 +5,20 @@
 // ode('dop853') as the reference drives it (RateStateModel.py:374-389, SURVEY.md
 // Appendix B): a fresh call per output interval, hinit, err/accept, controller.
 //
-// B200-specific structure (not present in any form in the reference):
-//   * V (y[2]) never feeds back into the RHS (RateStateModel.py:336-346 use only
-//     mu, theta), so its stage values are not stored: the three linear forms that
-//     need them (8th-order sum, 5th- and 3rd-order error forms) are accumulated
-//     as the stages are produced.  Stage storage is 10 x (mu, theta) registers.
-//   * the load-point velocity V_l(t) depends on time only.  Whenever all lanes of
-//     a warp are at the same (t, h) -- always, outside the stiff regime -- lanes
-//     0..10 evaluate the eleven stage abscissae once and every lane fetches its
-//     stage value with a shuffle: one exp + one sin per step instead of eleven.
-//   * the observed series streams through shared memory in 4 KB tiles fetched by
-//     the TMA bulk-copy engine (cp.async.bulk + mbarrier), double-buffered.
-//   * restarting k1 = f(t, y) at every interval is skipped: it is bit-identical
-//     to the FSAL evaluation that closed the previous interval.
+// B200-specific structure (not present in any form in the reference; details at each definition):
+//   * V (y[2]) never feeds back into the RHS (RateStateModel.py:336-346 use only mu, theta): its stage
+//     values are not stored, the three linear forms that need them are accumulated on the fly.
+//   * the load-point term L(t) depends on time only: it is tabulated once per sampler on the nominal time
+//     grid (loading_table_kernel), prefetched per interval with cp.async into a per-warp shared table;
+//     lanes off that grid share an on-the-fly table per warp, or fill a private column (stiff regime).
+//   * the fast interval: hinit's probe + the twelve stages + FSAL as one branch-free block verified by a
+//     single warp vote (dop853_step_fast: short dependency chain, mu / theta series evaluated in parallel);
+//     a state-by-state general path (dop853_step_impl<false>, reference formulas) covers everything else.
+//   * the observed series streams through shared memory in 4 KB tiles fetched by the TMA bulk-copy engine
+//     (cp.async.bulk + mbarrier), double-buffered; series of <= 1024 points stay resident.
+//   * restarting k1 = f(t, y) at every interval is skipped: it is bit-identical to the FSAL evaluation that
+//     closed the previous interval.
+//   * sqrt- and division-free accept / hinit decisions; exact early rejection against an SSE bound.
 #pragma once
 
 #include <cstdint>
