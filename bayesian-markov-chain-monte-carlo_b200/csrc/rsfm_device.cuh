@@ -683,6 +683,7 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
     bool have_pending = false;
     int fast_resume = 0;
     bool was_bad = false;
+    unsigned int stiff_steps = 0;          // warp-uniform count of steps taken on the general path
 
     for (int k = 1; k < M.n_out; k++) {
         const double dk = have_data ? series.at(k) : 0.0;
@@ -817,9 +818,17 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
             ensure_table(stepping, h);
             const bool hit = (t == tab_t && h == tab_h);
             if (stepping && !hit) {
-                // private stage values (this lane is not on the warp's (t, h))
+                // private stage values (this lane is not on the warp's (t, h)).  A piecewise-constant load
+                // that does not switch between t and t + h has one value for the whole step.
+                const double La = loading_of(M, t), Lb = loading_of(M, t + h);
+                if (M.loading == RSFM_LOAD_VSTEP && La == Lb &&
+                    floor((t - M.t_start) / M.vstep_period) == floor((t + h - M.t_start) / M.vstep_period)) {
+#pragma unroll
+                    for (int i = 0; i < 11; i++) ptab[i * nthr] = La;
+                } else {
 #pragma unroll 1
-                for (int i = 0; i < 11; i++) ptab[i * nthr] = loading_of(M, __dadd_rn(t, __dmul_rn(TB.c[i], h)));
+                    for (int i = 0; i < 11; i++) ptab[i * nthr] = loading_of(M, __dadd_rn(t, __dmul_rn(TB.c[i], h)));
+                }
             }
             const double *Lsrc = hit ? wtab : ptab;
             const int lstride = hit ? 1 : nthr;
@@ -831,7 +840,7 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
             bool bad = false;
             // A warp whose stepping lanes all left the fast ranges on their previous step (stiff regime)
             // goes straight to the general step; the fast one is retried every 64 steps.
-            const bool try_fast = !__all_sync(FULL_MASK, !stepping || was_bad) || (out.nstep & 63u) == 0u;
+            const bool try_fast = !__all_sync(FULL_MASK, !stepping || was_bad) || (++stiff_steps & 63u) == 0u;
             if (try_fast) dop853_step_fast(cc, in, Lsrc, lstride, so, bad);
             else bad = true;
             if (stepping && bad) dop853_step_general(&cc, &in, Lsrc, lstride, &so);
