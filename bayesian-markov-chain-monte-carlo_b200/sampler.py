@@ -34,7 +34,7 @@ class MCMC:
     def __init__(self, model, data, dc_true, qpriors, qstart, nsamples=100, lstm_model={},
                  adapt_interval=10, verbose=True, *, n_chains=1, seed=None, device=None,
                  param_names=("Dc",), bounds=None, deterministic_inputs=None, compat_adapt=None,
-                 adapt=None, adapt_start=100, shard=False, chain_id0=0, spec_depth=0, resume=None, keep_on_device=False):
+                 adapt=None, adapt_start=100, shard=False, chain_id0=0, spec_depth=0, resume=None):
         # reference attributes, MCMC.py:88-99
         self.model = model
         self.qstart = qstart
@@ -59,7 +59,6 @@ class MCMC:
         self.adapt_start = int(adapt_start)
         self.shard = bool(shard)
         self.chain_id0 = int(chain_id0)        # global id of chain 0 when not sharding (Philox counter)
-        self.keep_on_device = bool(keep_on_device)
         self.spec_depth = int(spec_depth)      # speculation tree depth: 0 auto, 1 off, 2..5 forced
         self.resume = resume                   # checkpoint dict / JSON file from MCMC.checkpoint()
         if self.param_names not in (("Dc",), ("a", "b", "Dc")):
