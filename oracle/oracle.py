@@ -44,8 +44,12 @@ class OrcStats(C.Structure):
 def build(force: bool = False) -> str:
     """Compile the oracle library if needed and return its path."""
     src = os.path.join(_HERE, "rsf_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    import shutil
+    stale = not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src)
+    if (force or stale) and shutil.which("make") and shutil.which("gcc"):
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    if not os.path.exists(_SO):
+        raise RuntimeError("oracle library missing and no compiler available to build it")
     return _SO
 
 
