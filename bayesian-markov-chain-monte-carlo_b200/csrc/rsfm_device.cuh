@@ -613,11 +613,11 @@ struct LoadScratch {
 // first); the lane stops integrating there (`out.status |= RSFM_CHAIN_EARLY`, sse = partial > limit).
 // The accept/reject decision is exactly the one the full solve would give.  A warp leaves the
 // output loop when all its lanes are finished (resident series only: no block barriers pending).
-__device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double b, double dc, bool active,
-                                               SeriesStage &series, const LoadScratch &ls, double *acc_out,
-                                               const double *acc_ref, size_t acc_stride, double fd_den,
-                                               double *xtx_out, double *t_out = nullptr,
-                                               double sse_limit = INFINITY)
+template <bool PARITY>
+__device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, double b, double dc, bool active,
+                                                    SeriesStage &series, const LoadScratch &ls, double *acc_out,
+                                                    const double *acc_ref, size_t acc_stride, double fd_den,
+                                                    double *xtx_out, double *t_out, double sse_limit)
 {
     const int lane = threadIdx.x & 31;
     const int nthr = blockDim.x;
@@ -626,7 +626,7 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
     double *ptab = ls.priv + threadIdx.x;
     const ChainConst cc = make_chain_const(M, a, b, dc);
     const bool have_data = series.g != nullptr;
-    const bool parity = M.integ_mode == RSFM_INTEG_PARITY;
+    constexpr bool parity = PARITY;      // compile-time: keeps the fast interval one branch-free block
     const double uround = 2.3e-16, safe = 0.9;
     const double facc1 = 1.0 / 0.3, facc2 = 1.0 / 6.0;
 
@@ -721,8 +721,9 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
         // rejected step, argument outside the fast ranges) sends the warp through the general path
         // below for this interval, which recomputes it from the same state.
         bool fast_done = false;
-        if (parity && k > 1 && k >= fast_resume && nom != nullptr) {
-            const bool cand = (t == tab_t) && (hmax == tab_h);
+        if (k > 1 && k >= fast_resume && nom != nullptr) {
+            // (CARRY mode: no hinit; the carried step must already be hmax and must stay hmax)
+            const bool cand = (t == tab_t) && (hmax == tab_h) && (parity || h_carry >= hmax);
             const unsigned rmask = __ballot_sync(FULL_MASK, running);
             if (rmask != 0 && __all_sync(FULL_MASK, !running || cand)) {
                 const double k0 = M.atol + M.rtol * fabs(mu), k1 = M.atol + M.rtol * fabs(th), k2 = M.atol + M.rtol * fabs(V);
@@ -730,10 +731,11 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
                 const double dd = k0 * p0, D = dd * dd;
                 const double Nf = (k1m * p0) * (k1m * p0) + (k1t * p1) * (k1t * p1) + (k1v * p2) * (k1v * p2);
                 const double Ny = (mu * p0) * (mu * p0) + (th * p1) * (th * p1) + (V * p2) * (V * p2);
-                const bool h0max = !((Nf <= 1e-10 * D) || (Ny <= 1e-10 * D)) && (Ny >= Nf * (1.0e4 * hmax * hmax));
+                const bool h0max = !parity ||
+                                   (!((Nf <= 1e-10 * D) || (Ny <= 1e-10 * D)) && (Ny >= Nf * (1.0e4 * hmax * hmax)));
                 bool bad = false;
-                double f1m, f1t, f1v, rprobe = rth;
-                rsf_rhs<true>(cc, wtab[10], mu + hmax * k1m, th + hmax * k1t, rprobe, f1m, f1t, f1v, bad);
+                double f1m = k1m, f1t = k1t, f1v = k1v, rprobe = rth;
+                if (parity) rsf_rhs<true>(cc, wtab[10], mu + hmax * k1m, th + hmax * k1t, rprobe, f1m, f1t, f1v, bad);
                 StepIn in;
                 in.h = xend - t; in.mu = mu; in.th = th; in.V = V; in.k1m = k1m; in.k1t = k1t; in.k1v = k1v; in.rth = rth;
                 in.atol = M.atol; in.rtol = M.rtol;
@@ -743,16 +745,21 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
                 const double Ne = e0 * e0 + e1 * e1 + e2 * e2;
                 const double hm2 = hmax * hmax, hm4 = hm2 * hm2, hm8 = hm4 * hm4, hm16 = hm8 * hm8;
                 const double lim = 1.0e-4 * D;
-                const bool h1max = Ne * hm16 <= lim * hm2 && Nf * hm16 <= lim && fmax(Ne, Nf * hm2) > 1e-30 * D * hm2;
+                const bool h1max = !parity || (Ne * hm16 <= lim * hm2 && Nf * hm16 <= lim &&
+                                               fmax(Ne, Nf * hm2) > 1e-30 * D * hm2);
                 const bool entry = !(0.1 * hmax <= fabs(t) * uround) && ((t + 1.01 * hmax - xend) > 0.0);
-                const bool accept = so.errA < 1e140 && (in.h * in.h) * (so.errA * so.errA) <= so.den3;
-                const bool ok = h0max && h1max && entry && accept && !bad;
+                const double h2a2 = (in.h * in.h) * (so.errA * so.errA);
+                const bool accept = so.errA < 1e140 && h2a2 <= so.den3;
+                // CARRY: the controller must leave h at hmax (err <= 0.9^8), else the general path decides
+                const bool keeps = parity || h2a2 <= 0.185302018885184 * so.den3;
+                const bool ok = h0max && h1max && entry && accept && keeps && !bad;
                 if (__all_sync(FULL_MASK, !running || ok)) {
                     if (running) {
                         rth = so.rth;
                         rsf_rhs_checked(cc, so.L12, so.muN, so.thN, rth, k1m, k1t, k1v);
                         mu = so.muN; th = so.thN; V = so.VN; t = t + in.h;
-                        out.nrhs += 13; out.nstep++;
+                        out.nrhs += parity ? 13 : 12; out.nstep++;
+                        h_carry = hmax;
                     }
                     fast_done = true;
                 } else {
@@ -907,6 +914,20 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
     out.sse = sse;
     if (xtx_out) *xtx_out = xtx;
     return out;
+}
+
+// integration mode is a kernel-uniform run-time choice; each mode is its own instantiation
+__device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double b, double dc, bool active,
+                                               SeriesStage &series, const LoadScratch &ls, double *acc_out,
+                                               const double *acc_ref, size_t acc_stride, double fd_den,
+                                               double *xtx_out, double *t_out = nullptr,
+                                               double sse_limit = INFINITY)
+{
+    if (M.integ_mode == RSFM_INTEG_PARITY)
+        return rsf_solve_mode<true>(M, a, b, dc, active, series, ls, acc_out, acc_ref, acc_stride, fd_den, xtx_out, t_out,
+                                    sse_limit);
+    return rsf_solve_mode<false>(M, a, b, dc, active, series, ls, acc_out, acc_ref, acc_stride, fd_den, xtx_out, t_out,
+                                 sse_limit);
 }
 
 }  // namespace rsfm
