@@ -21,7 +21,24 @@ def report(name, mc, out, wall, extra=None):
     print(json.dumps(line), flush=True)
 
 
-if which == "cfg3":
+if which == "cfg1":
+    # the reference's own default (main.py:50-56): 5 Dc values, one chain each, 500 samples, through the RSF facade
+    import contextlib, io, tempfile
+    os.chdir(tempfile.mkdtemp())
+    problem = pkg.RSF(number_slip_values=5, lowest_slip_value=100.0, largest_slip_value=5000.0, qstart=1000.0,
+                      qpriors=["Uniform", 0.0, 10000.0])
+    problem.model = pkg.RateStateModel(number_time_steps=500)
+    np.random.seed(2024)
+    t0 = time.perf_counter(); problem.data = problem.generate_time_series(); t_gen = time.perf_counter() - t0
+    problem.format = "json"
+    problem.mcmc_kwargs = {"seed": 2024}
+    with contextlib.redirect_stdout(io.StringIO()):
+        elapsed = problem.inference(nsamples=500)
+    post = {float(dc): (float(r["samples"].mean()), float(r["samples"].std()), float(r["acceptance_ratio"][0]))
+            for dc, r in problem.results.items()}
+    print(json.dumps({"config": "cfg1: main.py defaults via RSF facade (5 x 1 chain x 500 samples)",
+                      "generate_time_series_s": t_gen, "inference_s": elapsed, "posterior_mean_sd_accept": post}))
+elif which == "cfg3":
     # joint (a, b, Dc), pooled adaptive covariance, 65,536 chains
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 300
     c = int(os.environ.get("CHAINS", "65536"))
