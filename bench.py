@@ -329,6 +329,8 @@ def run_b200(args):
                        "chains_per_gpu": cpg, "chains_total": total_chains, "iters_per_step": iters, "n_out": N_OUT,
                        "integ_mode": args.integ_mode, "speculation_depth": spec_g, "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
+            # transparency: proposals whose solve ran to the end of the series (early-rejected ones excluded)
+            "value_full_length_solves_only": (solves - n_early) / dev_s_max,
             "ess_per_s": diag["ess"][0] / dev_s_max,
             "ess": {"total": diag["ess"][0], "per_chain": diag["ess_per_chain_mean"][0], "rhat": diag["rhat"][0],
                     "draws_per_chain": int(diag["n"]), "posterior_mean": diag["mean"][0], "posterior_sd": diag["sd"][0],
