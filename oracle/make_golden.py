@@ -145,6 +145,11 @@ def record_chain(rsm, mcm, data, dc_true, qpriors, qstart, nsamples, seed):
 def main():
     os.makedirs(OUT, exist_ok=True)
     rsm, mcm = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
+        data_cfg1 = make_data(rsm, 1325.0, 2024)
+        dump("chain_cfg1_full.json",
+             record_chain(rsm, mcm, data_cfg1, 1325.0, ["Uniform", 0.0, 10000.0], 1000.0, nsamples=500, seed=2024))
+        return
 
     # G1
     g1 = {"cases": []}
@@ -180,6 +185,11 @@ def main():
          record_chain(rsm, mcm, data, 1350.0, ["Uniform", 0.0, 10000.0], 1000.0, nsamples=120, seed=2024))
     dump("chain_dict_priors.json",
          record_chain(rsm, mcm, data, 1350.0, {1: 0.0, 2: 10000.0}, 1000.0, nsamples=60, seed=7))
+    # the reference's own default run in full (main.py:50-56, Dc_true = 1325): 500 iterations, data made with
+    # np.random.seed(2024) immediately before evaluate() (SURVEY 8d cfg 1)
+    data_cfg1 = make_data(rsm, 1325.0, 2024)
+    dump("chain_cfg1_full.json",
+         record_chain(rsm, mcm, data_cfg1, 1325.0, ["Uniform", 0.0, 10000.0], 1000.0, nsamples=500, seed=2024))
     # a chain that starts near the upper bound so that out-of-bounds proposals occur (q10)
     dump("chain_bounds.json",
          record_chain(rsm, mcm, data, 1350.0, ["Uniform", 900.0, 1500.0], 1450.0, nsamples=60, seed=99))

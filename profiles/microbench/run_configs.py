@@ -8,6 +8,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 pkg = importlib.import_module("bayesian-markov-chain-monte-carlo_b200")
 which = sys.argv[1]
 rng = np.random.default_rng(0)
+SHARD = int(os.environ.get("WORLD_SIZE", "1")) > 1        # under torchrun: chains sharded over ranks, NCCL all-reduces
+if SHARD:
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    sys.stdout.flush(); _saved = os.dup(1); os.dup2(2, 1)      # keep the NCCL banner off stdout
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    dist.barrier(); os.dup2(_saved, 1); os.close(_saved)
 
 
 def report(name, mc, out, wall, extra=None):
@@ -18,6 +25,9 @@ def report(name, mc, out, wall, extra=None):
             "post_mean": d["mean"], "post_sd": d["sd"], "failed_chains": mc.stats["failed_chains"]}
     if extra:
         line.update(extra)
+    if SHARD:
+        line["rank"] = dist.get_rank(); line["world"] = dist.get_world_size()
+        line["chains_local"] = mc.stats["n_chains_local"]
     print(json.dumps(line), flush=True)
 
 
@@ -49,7 +59,7 @@ elif which == "cfg3":
     q0 = np.stack([rng.uniform(0.009, 0.013, c), rng.uniform(0.012, 0.016, c), rng.uniform(800.0, 2500.0, c)], axis=1)
     mc = pkg.MCMC(m, data, 1325.0, ["Uniform", 0.0, 1e4], q0, nsamples=iters, n_chains=c, verbose=False, seed=3,
                   param_names=("a", "b", "Dc"), bounds=[[0.005, 0.02], [0.005, 0.03], [0.0, 1e4]], adapt="pooled",
-                  adapt_start=100)
+                  adapt_start=100, shard=SHARD)
     t0 = time.perf_counter(); out = mc.sample(False); wall = time.perf_counter() - t0
     report("cfg3: joint (a,b,Dc), pooled AM, %d chains, %d iters" % (c, iters), mc, out, wall,
            {"n_adaptations": len(mc.adapt_history)})

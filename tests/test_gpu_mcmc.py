@@ -12,7 +12,7 @@ def _priors(g):
     return {1: g["lo"], 2: g["hi"]} if g["qpriors_form"] == "dict" else ["Uniform", g["lo"], g["hi"]]
 
 
-@pytest.mark.parametrize("name", ["chain_list_priors.json", "chain_dict_priors.json", "chain_bounds.json"])
+@pytest.mark.parametrize("name", ["chain_list_priors.json", "chain_dict_priors.json", "chain_bounds.json", "chain_cfg1_full.json"])
 def test_deterministic_replay_of_reference_chain(cuda, pkg, name):
     """Host-supplied proposals, uniforms and gamma draws recorded from the UNMODIFIED reference:
     the kernel must take the same accept/reject decision at every step (north_star check 2)."""

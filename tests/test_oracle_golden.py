@@ -68,7 +68,7 @@ def test_sse_grid(orc):
     assert g["grid"][int(np.argmin(sse))] == 1300.0        # grid minimum at 1300
 
 
-@pytest.mark.parametrize("name", ["chain_list_priors.json", "chain_dict_priors.json", "chain_bounds.json"])
+@pytest.mark.parametrize("name", ["chain_list_priors.json", "chain_dict_priors.json", "chain_bounds.json", "chain_cfg1_full.json"])
 def test_chain_replay_bit_exact(orc, name):
     """Appendix A semantics: with the recorded draws the oracle reproduces the reference chain."""
     g = load_golden(name)
