@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     "rsfm_forward_batch", "rsfm_create", "rsfm_destroy", "rsfm_init", "rsfm_run",
     "rsfm_run_deterministic", "rsfm_spec_depth", "rsfm_get_state", "rsfm_set_state", "rsfm_iteration",
     "rsfm_get_totals", "rsfm_get_suffstats", "rsfm_set_proposal_chol", "rsfm_chain_diagnostics",
-    "rsfm_kde_grid", "rsfm_measure_fp64_peak",
+    "rsfm_kde_grid", "rsfm_measure_fp64_peak", "rsfm_trim",
 )
 
 
@@ -100,6 +100,8 @@ def load():
     lib.rsfm_kde_grid.restype = C.c_int
     lib.rsfm_measure_fp64_peak.argtypes = [dbl, C.POINTER(dbl)]
     lib.rsfm_measure_fp64_peak.restype = C.c_int
+    lib.rsfm_trim.argtypes = []
+    lib.rsfm_trim.restype = C.c_int
     if lib.rsfm_abi_version() != 1:
         raise RsfmError(f"librsfm ABI version {lib.rsfm_abi_version()} != 1")
     _lib = lib

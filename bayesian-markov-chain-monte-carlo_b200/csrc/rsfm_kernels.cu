@@ -204,6 +204,91 @@ static int get_nominal_table(const ModelK &M, cudaStream_t stream, const double 
     return RSFM_OK;
 }
 
+// Workspace cache for rsfm_init's base trajectories.  A fresh cudaMalloc/cudaFree pair of a few MB
+// goes through the driver's VM mapping path and was measured at 3-600 ms per rsfm_init on the
+// public-API call (profiles/microbench/e2e_jitter3.py); buffers up to SCRATCH_KEEP_BYTES are therefore
+// kept per process and handed out again (rsfm_trim releases them).  A buffer is only returned to the
+// cache after the stream that used it has been synchronised, so the next user may be on any stream.
+static const size_t SCRATCH_KEEP_BYTES = (size_t)256 << 20;
+struct ScratchEntry { int device; void *ptr; size_t bytes; bool busy; };
+static ScratchEntry g_scratch[4];
+static std::mutex g_scratch_mu;
+
+static int scratch_acquire(size_t bytes, double **out)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        for (ScratchEntry &e : g_scratch)
+            if (e.ptr && !e.busy && e.device == dev && e.bytes >= bytes) {
+                e.busy = true;
+                *out = (double *)e.ptr;
+                return RSFM_OK;
+            }
+    }
+    CUDA_TRY(cudaMalloc((void **)out, bytes));
+    return RSFM_OK;
+}
+
+// caller guarantees no work that touches `p` is still in flight
+static void scratch_release(double *p, size_t bytes)
+{
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    void *victim = p;
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        for (ScratchEntry &e : g_scratch)
+            if (e.ptr == p) { e.busy = false; return; }
+        if (bytes <= SCRATCH_KEEP_BYTES) {
+            ScratchEntry *slot = nullptr;
+            for (ScratchEntry &e : g_scratch) if (!e.ptr) { slot = &e; break; }
+            if (!slot)                             // replace the smallest idle buffer if this one is larger
+                for (ScratchEntry &e : g_scratch)
+                    if (!e.busy && e.bytes < bytes && (!slot || e.bytes < slot->bytes)) slot = &e;
+            if (slot) {
+                victim = slot->ptr;
+                int victim_dev = slot->device;
+                slot->device = dev; slot->ptr = p; slot->bytes = bytes; slot->busy = false;
+                if (victim && victim_dev != dev) {     // free on the owning device
+                    cudaSetDevice(victim_dev); cudaFree(victim); cudaSetDevice(dev);
+                    victim = nullptr;
+                }
+            }
+        }
+    }
+    if (victim) cudaFree(victim);
+}
+
+extern "C" int rsfm_trim(void)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        for (ScratchEntry &e : g_scratch)
+            if (e.ptr && !e.busy) {
+                cudaSetDevice(e.device); cudaFree(e.ptr);
+                e.ptr = nullptr; e.bytes = 0;
+            }
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_nom_mu);
+        for (int i = 0; i < g_nom_n; i++) {
+            if (g_nom[i].device < 0) continue;
+            cudaSetDevice(g_nom[i].device);
+            cudaDeviceSynchronize();
+            cudaFree(g_nom[i].ptr);
+            cudaEventDestroy(g_nom[i].ready);
+        }
+        g_nom_n = 0;
+    }
+    cudaSetDevice(dev);
+    return RSFM_OK;
+}
+
 // ---------------------------------------------------------------------------
 // forward batch
 // ---------------------------------------------------------------------------
@@ -307,6 +392,7 @@ struct rsfm_sampler {
     int device;
     SamplerDev d;
     double *scratch;               // [n_out][C] base trajectory for rsfm_init
+    size_t scratch_bytes;
     double *reduce_out;            // [16] device scratch for suffstats
     unsigned long long *totals;    // [8] device scratch for rsfm_get_totals
 };
@@ -363,7 +449,11 @@ extern "C" void rsfm_destroy(rsfm_sampler *s)
     if (!s) return;
     cudaFree(s->d.q); cudaFree(s->d.sse); cudaFree(s->d.sigma2); cudaFree(s->d.chol); cudaFree(s->d.ring);
     cudaFree(s->d.suff); cudaFree(s->d.data); cudaFree(s->d.nom); cudaFree(s->d.accepted); cudaFree(s->d.status);
-    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->d.nsolve); cudaFree(s->d.nearly); cudaFree(s->d.nexec); cudaFree(s->d.urhs); cudaFree(s->d.ustep); cudaFree(s->scratch);
+    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->d.nsolve); cudaFree(s->d.nearly); cudaFree(s->d.nexec); cudaFree(s->d.urhs); cudaFree(s->d.ustep);
+    if (s->scratch) {                           // only after a failed rsfm_init
+        cudaDeviceSynchronize();
+        scratch_release(s->scratch, s->scratch_bytes);
+    }
     cudaFree(s->reduce_out); cudaFree(s->totals);
     delete s;
 }
@@ -493,7 +583,12 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     CUDA_TRY(cudaMemcpyAsync(s->d.q, q0_dev, sizeof(double) * d * (size_t)C, cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(s->d.data, data_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
     const size_t planes = (d == 1) ? 1 : (size_t)(1 + d);
-    if (!s->scratch) CUDA_TRY(cudaMalloc((void **)&s->scratch, sizeof(double) * planes * n * (size_t)C));
+    const size_t scratch_bytes = sizeof(double) * planes * n * (size_t)C;
+    if (!s->scratch) {
+        int rc = scratch_acquire(scratch_bytes, &s->scratch);
+        if (rc) return rc;
+        s->scratch_bytes = scratch_bytes;
+    }
     CUDA_TRY(cudaMemsetAsync(s->d.accepted, 0, sizeof(unsigned int) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.status, 0, sizeof(int) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.nrhs, 0, sizeof(unsigned long long) * C, stream));
@@ -524,9 +619,10 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
         fill_ring_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, s->cfg.adapt_interval, s->d);
         CUDA_TRY(cudaGetLastError());
     }
-    // the base trajectory is only needed during init; release it (it can be GBs)
+    // the base trajectory is only needed during init; hand it back (small ones are cached, GB-sized
+    // ones freed)
     CUDA_TRY(cudaStreamSynchronize(stream));
-    cudaFree(s->scratch);
+    scratch_release(s->scratch, scratch_bytes);
     s->scratch = nullptr;
     s->iteration = 0;
     s->suff_count = 0;

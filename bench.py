@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--iters", type=int, default=200, help="Metropolis iterations per step")
     ap.add_argument("--integ-mode", choices=["parity", "carry"], default="parity")
     ap.add_argument("--seed", type=int, default=20240)
-    ap.add_argument("--e2e-steps", type=int, default=2, help="timed public-API calls (each = the whole job)")
+    ap.add_argument("--e2e-steps", type=int, default=3, help="timed public-API calls (each = the whole job)")
     ap.add_argument("--cpu-iters", type=int, default=12, help="iterations per chain in the cpu_baseline sample")
     ap.add_argument("--ref-iters", type=int, default=12, help="iterations per chain per step, --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")

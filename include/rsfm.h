@@ -90,6 +90,11 @@ void         rsfm_cfg_defaults(rsfm_cfg *cfg);
 /* Number of CUDA devices usable by this library (compute capability 10.x). */
 int          rsfm_device_count(void);
 
+/* Release the per-process device caches (nominal loading tables of rsfm_forward_batch, the
+ * rsfm_init workspace kept between samplers).  No reference counterpart: the reference holds no
+ * device memory.  Safe at any time no rsfm call is in flight on another thread. */
+int          rsfm_trim(void);
+
 /* Batched RateStateModel.evaluate() (RateStateModel.py:188-395) + optional SSE
  * (MCMC.py:387).  dc_dev [C] is required; a_dev, b_dev [C] may be NULL (cfg->a,
  * cfg->b are used).  Outputs, each optional (NULL to skip):

@@ -327,3 +327,27 @@ def test_non_finite_state_terminates(cuda, pkg):
         out = mc.sample(False)
         assert out.shape == (8, 1, 5)
         assert np.all(out == 1000.0) and mc.accepts.sum() == 0
+
+
+def test_init_workspace_cache_and_trim(cuda, pkg):
+    """rsfm_init's workspace is recycled between samplers (and between sizes / d); results do not
+    depend on whether the buffer came from the cache, and rsfm_trim releases everything."""
+    g = load_golden("sse_grid.json")
+    model = pkg.RateStateModel()
+    lib = pkg._lib.load()
+
+    def run(n_chains):
+        return pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], 1000.0, n_chains=n_chains, nsamples=10,
+                        verbose=False, seed=5).sample(False)
+
+    assert lib.rsfm_trim() == 0
+    first = run(96)                    # fresh allocation
+    again = run(96)                    # same buffer from the cache
+    small = run(32)                    # a larger cached buffer serves a smaller request
+    big = run(160)                     # cache miss: a new, larger buffer replaces or joins it
+    assert np.array_equal(first, again)
+    assert np.array_equal(small, first[:32]) and np.array_equal(big[:96], first)
+    assert lib.rsfm_trim() == 0
+    assert np.array_equal(run(96), first)
+    out = model.evaluate_batch(np.array([800.0, 1350.0]), data=g["data"])    # nominal-table cache rebuilt after trim
+    assert np.isfinite(out["sse"].cpu().numpy()).all()
