@@ -30,6 +30,23 @@ from . import _lib
 from .sharding import ChainShard, all_reduce_sum_
 
 
+def _to_host(torch, dev, *tensors):
+    """Device -> host copy of the result arrays through page-locked staging buffers (torch's caching
+    host allocator recycles them between calls); one synchronisation for all of them.  Pageable
+    destinations cost ~8 ms per call for the 18 MB of cfg 2 against < 1 ms pinned."""
+    outs = []
+    for t in tensors:
+        t = t.contiguous()
+        try:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        except RuntimeError:                     # locked-memory limit reached: plain pageable copy
+            h = torch.empty(t.shape, dtype=t.dtype)
+        h.copy_(t, non_blocking=True)
+        outs.append(h)
+    torch.cuda.synchronize(dev)
+    return [h.numpy() for h in outs]
+
+
 class MCMC:
     def __init__(self, model, data, dc_true, qpriors, qstart, nsamples=100, lstm_model={},
                  adapt_interval=10, verbose=True, *, n_chains=1, seed=None, device=None,
@@ -215,9 +232,8 @@ class MCMC:
         self.accept_device = accept
         in_bounds = None
         # ---- reference-shaped host outputs (device -> host copy of the results) ----
-        chain_h = chain[nb:].permute(2, 1, 0).contiguous().cpu().numpy()      # [C, d, n]
-        std2_h = std2[nb:].t().contiguous().cpu().numpy()                      # [C, n]
-        accept_h = accept.t().contiguous().cpu().numpy()                       # [C, ns]
+        chain_h, std2_h, accept_h = _to_host(torch, dev, chain[nb:].permute(2, 1, 0),      # [C, d, n]
+                                             std2[nb:].t(), accept.t())                    # [C, n], [C, ns]
         self.Vstart = self._vstart_host(chol0, d)
         self.status = status.cpu().numpy()
         n_acc = acc_cnt.cpu().numpy().astype(np.int64)

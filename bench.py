@@ -271,7 +271,9 @@ def run_b200(args):
     e2e_solves, e2e_wall, h2d, d2h = 0.0, 0.0, 0, 0
     pinned = torch.from_numpy(data).pin_memory()
     barrier()
+    out = mc = None
     for i in range(e2e_steps + 1):
+        out = mc = None                             # the previous job's host arrays are consumed, not kept
         t0 = time.perf_counter()
         mc = pkg.MCMC(model, pinned.numpy(), DC_TRUE, ["Uniform", LO, HI], q0_host, nsamples=K * iters,
                       n_chains=cpg, verbose=False, seed=args.seed, device=dev, chain_id0=first[0])
