@@ -79,13 +79,29 @@ elif which == "cfg4":
     report("cfg4: N=%d VSTEP stiff, %d chains, %d iters" % (n, c, iters), mc, out, wall,
            {"single_solve_s": t_one, "rhs_per_solve": mc.stats["nrhs"] / max(mc.stats["nsolves_executed"], 1)})
 elif which == "cfg5":
-    # 131,072 chains per GPU (1M over 8 GPUs), Dc-only, R-hat / ESS at the end
-    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 100
-    c = int(os.environ.get("CHAINS", "131072"))
+    # 131,072 chains per GPU (1,048,576 over 8 GPUs under torchrun), Dc-only, proposal variance pooled over ALL
+    # chains of ALL ranks by NCCL all-reduces of the sufficient statistics, R-hat / ESS pooled the same way
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    c = int(os.environ.get("CHAINS", "131072")) * world
     m = pkg.RateStateModel(); m.Dc = 1325.0
     np.random.seed(2024)
     _, _, data = m.evaluate()
     q0 = rng.uniform(200.0, 5000.0, c); q0[0] = 1000.0
-    mc = pkg.MCMC(m, data, 1325.0, ["Uniform", 0.0, 1e4], q0, nsamples=iters, n_chains=c, verbose=False, seed=5)
+    mc = pkg.MCMC(m, data, 1325.0, ["Uniform", 0.0, 1e4], q0, nsamples=iters, n_chains=c, verbose=False, seed=5,
+                  adapt="pooled", adapt_start=50, shard=SHARD)
+    warm = pkg.MCMC(m, data, 1325.0, ["Uniform", 0.0, 1e4], q0, nsamples=20, n_chains=c, verbose=False, seed=6,
+                    adapt="pooled", adapt_start=10, shard=SHARD)
+    warm.sample(False); del warm                      # module load, NCCL communicator, pinned staging buffers
+    if SHARD: dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter(); out = mc.sample(False); wall = time.perf_counter() - t0
-    report("cfg5 shard: %d chains on one GPU, %d iters" % (c, iters), mc, out, wall)
+    tot = torch.tensor([float(mc.stats["nsolves"]), float(mc.stats["nsolves_executed"])], dtype=torch.float64, device="cuda")
+    wmax = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    if SHARD:
+        dist.all_reduce(tot); dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+    report("cfg5: %d chains over %d GPU(s), %d iters, pooled adaptation" % (c, world, iters), mc, out, wall,
+           {"n_adaptations": len(mc.adapt_history),
+            "proposal_sd_first_last": [float(np.sqrt(mc.adapt_history[0][1][0])), float(np.sqrt(mc.adapt_history[-1][1][0]))] if mc.adapt_history else [],
+            "all_ranks": {"chains": c, "solves": tot[0].item(), "wall_max_s": wmax.item(), "solves_per_s": tot[0].item() / wmax.item(),
+                          "chain_iterations_per_s": c * iters / wmax.item()}})
