@@ -204,17 +204,19 @@ static int get_nominal_table(const ModelK &M, cudaStream_t stream, const double 
     return RSFM_OK;
 }
 
-// Workspace cache for rsfm_init's base trajectories.  A fresh cudaMalloc/cudaFree pair of a few MB
-// goes through the driver's VM mapping path and was measured at 3-600 ms per rsfm_init on the
-// public-API call (profiles/microbench/e2e_jitter3.py); buffers up to SCRATCH_KEEP_BYTES are therefore
-// kept per process and handed out again (rsfm_trim releases them).  A buffer is only returned to the
-// cache after the stream that used it has been synchronised, so the next user may be on any stream.
-static const size_t SCRATCH_KEEP_BYTES = (size_t)256 << 20;
+// Device-buffer cache for the sampler state slab (rsfm_create) and rsfm_init's base trajectories.  A
+// fresh cudaMalloc/cudaFree pair of more than a few MB goes through the driver's VM mapping path and
+// was measured at 3-600 ms (cfg 2) up to 2 s (131,072 chains) per sampler on the public-API call
+// (profiles/microbench/e2e_jitter3.py, cfg5_breakdown.py); buffers up to SCRATCH_KEEP_BYTES are
+// therefore kept per process and handed out again (rsfm_trim releases them).  A buffer is only
+// returned to the cache after the work that used it has been synchronised, so the next user may be on
+// any stream.
+static const size_t SCRATCH_KEEP_BYTES = (size_t)2 << 30;
 struct ScratchEntry { int device; void *ptr; size_t bytes; bool busy; };
-static ScratchEntry g_scratch[4];
+static ScratchEntry g_scratch[6];
 static std::mutex g_scratch_mu;
 
-static int scratch_acquire(size_t bytes, double **out)
+static int scratch_acquire(size_t bytes, void **out)
 {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -223,16 +225,16 @@ static int scratch_acquire(size_t bytes, double **out)
         for (ScratchEntry &e : g_scratch)
             if (e.ptr && !e.busy && e.device == dev && e.bytes >= bytes) {
                 e.busy = true;
-                *out = (double *)e.ptr;
+                *out = e.ptr;
                 return RSFM_OK;
             }
     }
-    CUDA_TRY(cudaMalloc((void **)out, bytes));
+    CUDA_TRY(cudaMalloc(out, bytes));
     return RSFM_OK;
 }
 
 // caller guarantees no work that touches `p` is still in flight
-static void scratch_release(double *p, size_t bytes)
+static void scratch_release(void *p, size_t bytes)
 {
     if (!p) return;
     int dev = 0;
@@ -393,6 +395,8 @@ struct rsfm_sampler {
     SamplerDev d;
     double *scratch;               // [n_out][C] base trajectory for rsfm_init
     size_t scratch_bytes;
+    char *slab;                    // one device buffer behind every array of `d`, `totals` and `reduce_out`
+    size_t slab_bytes;
     double *reduce_out;            // [16] device scratch for suffstats
     unsigned long long *totals;    // [8] device scratch for rsfm_get_totals
 };
@@ -411,50 +415,46 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     cudaGetDevice(&s->device);
     const int d = cfg->n_params;
     const size_t Cz = (size_t)C;
-    bool ok = true;
-    auto alloc = [&](void **p, size_t bytes) {
-        if (!ok) return;
-        if (cudaMalloc(p, bytes) != cudaSuccess) { ok = false; return; }
-        if (cudaMemset(*p, 0, bytes) != cudaSuccess) ok = false;
-    };
-    alloc((void **)&s->d.q, sizeof(double) * d * Cz);
-    alloc((void **)&s->d.sse, sizeof(double) * Cz);
-    alloc((void **)&s->d.sigma2, sizeof(double) * Cz);
-    alloc((void **)&s->d.chol, sizeof(double) * tri(d) * Cz);
-    alloc((void **)&s->d.ring, sizeof(double) * cfg->adapt_interval * Cz);
-    alloc((void **)&s->d.suff, sizeof(double) * (d + tri(d)) * Cz);
-    alloc((void **)&s->d.data, sizeof(double) * ((size_t)cfg->n_out + 2));
-    alloc((void **)&s->d.nom, sizeof(double) * NOM_STRIDE * (size_t)cfg->n_out);
-    alloc((void **)&s->d.accepted, sizeof(unsigned int) * Cz);
-    alloc((void **)&s->d.status, sizeof(int) * Cz);
-    alloc((void **)&s->d.nrhs, sizeof(unsigned long long) * Cz);
-    alloc((void **)&s->d.nstep, sizeof(unsigned long long) * Cz);
-    alloc((void **)&s->d.nsolve, sizeof(unsigned long long) * Cz);
-    alloc((void **)&s->d.nearly, sizeof(unsigned long long) * Cz);
-    alloc((void **)&s->d.nexec, sizeof(unsigned long long) * Cz);
-    alloc((void **)&s->d.urhs, sizeof(unsigned long long) * Cz);
-    alloc((void **)&s->d.ustep, sizeof(unsigned long long) * Cz);
-    alloc((void **)&s->totals, sizeof(unsigned long long) * 16);
-    alloc((void **)&s->reduce_out, sizeof(double) * 16);
-    if (!ok) {
-        set_err(RSFM_ERR_CUDA, "rsfm_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    // one slab for all per-chain state (sub-arrays 256-byte aligned): a single (cached) allocation
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_q = take(sizeof(double) * d * Cz), o_sse = take(sizeof(double) * Cz), o_s2 = take(sizeof(double) * Cz);
+    const size_t o_chol = take(sizeof(double) * tri(d) * Cz), o_ring = take(sizeof(double) * cfg->adapt_interval * Cz);
+    const size_t o_suff = take(sizeof(double) * (d + tri(d)) * Cz), o_data = take(sizeof(double) * ((size_t)cfg->n_out + 2));
+    const size_t o_nom = take(sizeof(double) * NOM_STRIDE * (size_t)cfg->n_out);
+    const size_t o_acc = take(sizeof(unsigned int) * Cz), o_status = take(sizeof(int) * Cz);
+    size_t o_cnt[7];
+    for (size_t &o : o_cnt) o = take(sizeof(unsigned long long) * Cz);
+    const size_t o_totals = take(sizeof(unsigned long long) * 16), o_reduce = take(sizeof(double) * 16);
+    s->slab_bytes = off;
+    if (scratch_acquire(off, (void **)&s->slab) != RSFM_OK || cudaMemset(s->slab, 0, off) != cudaSuccess) {
+        set_err(RSFM_ERR_CUDA, "rsfm_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         rsfm_destroy(s);
         return nullptr;
     }
+    char *b = s->slab;
+    s->d.q = (double *)(b + o_q); s->d.sse = (double *)(b + o_sse); s->d.sigma2 = (double *)(b + o_s2);
+    s->d.chol = (double *)(b + o_chol); s->d.ring = (double *)(b + o_ring); s->d.suff = (double *)(b + o_suff);
+    s->d.data = (double *)(b + o_data); s->d.nom = (double *)(b + o_nom);
+    s->d.accepted = (unsigned int *)(b + o_acc); s->d.status = (int *)(b + o_status);
+    s->d.nrhs = (unsigned long long *)(b + o_cnt[0]); s->d.nstep = (unsigned long long *)(b + o_cnt[1]);
+    s->d.nsolve = (unsigned long long *)(b + o_cnt[2]); s->d.nearly = (unsigned long long *)(b + o_cnt[3]);
+    s->d.nexec = (unsigned long long *)(b + o_cnt[4]); s->d.urhs = (unsigned long long *)(b + o_cnt[5]);
+    s->d.ustep = (unsigned long long *)(b + o_cnt[6]);
+    s->totals = (unsigned long long *)(b + o_totals); s->reduce_out = (double *)(b + o_reduce);
     return s;
 }
 
 extern "C" void rsfm_destroy(rsfm_sampler *s)
 {
     if (!s) return;
-    cudaFree(s->d.q); cudaFree(s->d.sse); cudaFree(s->d.sigma2); cudaFree(s->d.chol); cudaFree(s->d.ring);
-    cudaFree(s->d.suff); cudaFree(s->d.data); cudaFree(s->d.nom); cudaFree(s->d.accepted); cudaFree(s->d.status);
-    cudaFree(s->d.nrhs); cudaFree(s->d.nstep); cudaFree(s->d.nsolve); cudaFree(s->d.nearly); cudaFree(s->d.nexec); cudaFree(s->d.urhs); cudaFree(s->d.ustep);
-    if (s->scratch) {                           // only after a failed rsfm_init
-        cudaDeviceSynchronize();
-        scratch_release(s->scratch, s->scratch_bytes);
-    }
-    cudaFree(s->reduce_out); cudaFree(s->totals);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != s->device) cudaSetDevice(s->device);
+    if (s->slab || s->scratch) cudaDeviceSynchronize();      // nothing may still be using the buffers
+    if (s->scratch) scratch_release(s->scratch, s->scratch_bytes);     // only after a failed rsfm_init
+    if (s->slab) scratch_release(s->slab, s->slab_bytes);
+    if (cur != s->device) cudaSetDevice(cur);
     delete s;
 }
 
@@ -585,7 +585,7 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     const size_t planes = (d == 1) ? 1 : (size_t)(1 + d);
     const size_t scratch_bytes = sizeof(double) * planes * n * (size_t)C;
     if (!s->scratch) {
-        int rc = scratch_acquire(scratch_bytes, &s->scratch);
+        int rc = scratch_acquire(scratch_bytes, (void **)&s->scratch);
         if (rc) return rc;
         s->scratch_bytes = scratch_bytes;
     }
