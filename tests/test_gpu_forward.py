@@ -200,3 +200,57 @@ def test_unstable_step_is_rejected_after_velocity_jump(cuda, pkg, orc):
         assert np.all(np.isfinite(acc_g[i]))
         scale = np.max(np.abs(acc_o[i]))
         assert np.max(np.abs(acc_g[i] - acc_o[i])) <= 2e-5 * scale
+
+
+def test_batch_position_invariance_at_131072(cuda, pkg):
+    """cfg-5 shard size: 131,072 parameter sets = 128 shuffled copies of 1,024 distinct Dc values.  A
+    parameter set's SSE must not depend on its lane, warp or block, nor on the batch size."""
+    m = pkg.RateStateModel()
+    m.Dc = 1325.0
+    np.random.seed(3)
+    _, _, data = m.evaluate()
+    rng = np.random.default_rng(11)
+    base = rng.uniform(200.0, 5000.0, 1024)
+    idx = rng.permutation(np.repeat(np.arange(1024), 128))
+    big = m.evaluate_batch(base[idx], data=data)
+    small = m.evaluate_batch(base, data=data)
+    sse_small = small["sse"].cpu().numpy()
+    assert np.array_equal(big["sse"].cpu().numpy(), sse_small[idx])
+    assert np.array_equal(big["nrhs"].cpu().numpy(), small["nrhs"].cpu().numpy()[idx])
+    assert np.all(big["status"].cpu().numpy() == 0)
+
+
+def test_long_series_is_causal_and_streamed_sse_is_consistent(cuda, pkg):
+    """cfg-4 grid (N = 1e5 output points, velocity steps every 1,000 s) in the non-stiff regime: every
+    output interval restarts the integrator, so the first 1,000 points of the long solve equal the
+    solve that stops there, bit for bit; the SSE accumulated from the TMA-streamed series equals the
+    sum over the returned trajectory; the last output time is the accumulated grid of the reference."""
+    n = 100_000
+    kw = dict(loading="vstep", vstep_period=1000.0, vstep_factor=10.0)
+    long_m = pkg.RateStateModel(number_time_steps=n, end_time=n * 0.1)
+    short_m = pkg.RateStateModel(number_time_steps=1000, end_time=100.0)
+    for m in (long_m, short_m):
+        m.loading, m.vstep_period, m.vstep_factor = kw["loading"], kw["vstep_period"], kw["vstep_factor"]
+    dcs = np.array([400.0, 1000.0, 1325.0, 2500.0, 6000.0])
+    rng = np.random.default_rng(5)
+    data = rng.standard_normal(n)
+    lo = long_m.evaluate_batch(dcs, data=data, want_acc=True, want_t=True)
+    sh = short_m.evaluate_batch(dcs, want_acc=True, want_t=True)
+    acc_l, acc_s = lo["acc"].cpu().numpy(), sh["acc"].cpu().numpy()        # [n_out, C]
+    assert acc_l.shape == (n, 5) and acc_s.shape == (1000, 5)
+    assert np.array_equal(acc_l[:1000], acc_s)
+    assert np.array_equal(lo["t"].cpu().numpy()[:1000], sh["t"].cpu().numpy())
+    assert np.all(lo["status"].cpu().numpy() == 0) and np.all(lo["filled"].cpu().numpy() == n)
+    # the sampler's SSE is a plain running sum over k (MCMC.py:387 semantics, sequential order)
+    ref = np.zeros(5)
+    for k in range(n):
+        e = acc_l[k] - data[k]
+        ref += e * e
+    assert np.allclose(lo["sse"].cpu().numpy(), ref, rtol=1e-12, atol=0.0)
+    # output times are accumulated, t_{k+1} = t_k + delta_t (RateStateModel.py:382-384)
+    t = 0.0
+    for _ in range(n - 1):
+        t += long_m.delta_t
+    assert lo["t"].cpu().numpy()[-1, 0] == t
+    # the velocity steps are felt: acceleration spikes right after t = 1000 s
+    assert np.max(np.abs(acc_l[10_000:10_020, 2])) > 100 * np.max(np.abs(acc_l[9_900:9_990, 2]))
