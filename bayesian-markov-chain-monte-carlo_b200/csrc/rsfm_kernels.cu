@@ -102,6 +102,10 @@ static int check_cfg(const rsfm_cfg *c)
         return set_err(RSFM_ERR_INVALID, "bad loading selector%s", "");
     if (c->integ_mode != RSFM_INTEG_PARITY && c->integ_mode != RSFM_INTEG_CARRY)
         return set_err(RSFM_ERR_INVALID, "bad integ_mode%s", "");
+    if (c->loading == RSFM_LOAD_VSTEP && !(c->vstep_period > 0.0))
+        return set_err(RSFM_ERR_INVALID, "vstep_period must be positive%s", "");
+    if (!(c->rtol > 0.0) || !(c->atol >= 0.0)) return set_err(RSFM_ERR_INVALID, "rtol must be positive and atol non-negative%s", "");
+    if (!(c->a > 0.0) || !(c->V_ref > 0.0)) return set_err(RSFM_ERR_INVALID, "a and V_ref must be positive%s", "");
     if (c->adapt_interval < 2 || c->adapt_interval > 64) return set_err(RSFM_ERR_INVALID, "adapt_interval must be in [2, 64]%s", "");
     return RSFM_OK;
 }
@@ -109,6 +113,7 @@ static int check_cfg(const rsfm_cfg *c)
 static ModelK make_model(const rsfm_cfg *c)
 {
     ModelK M;
+    memset(&M, 0, sizeof(M));          // padding too: ModelK is a memcmp key of the nominal-table cache
     M.mu_ref = c->mu_ref; M.V_ref = c->V_ref; M.k1 = c->k1; M.t_start = c->t_start;
     M.delta_t = c->delta_t; M.mu_t_zero = c->mu_t_zero;
     M.rtol = c->rtol; M.atol = c->atol; M.vstep_period = c->vstep_period; M.vstep_factor = c->vstep_factor;
@@ -222,12 +227,14 @@ static int scratch_acquire(size_t bytes, void **out)
     CUDA_TRY(cudaGetDevice(&dev));
     {
         std::lock_guard<std::mutex> lock(g_scratch_mu);
+        ScratchEntry *best = nullptr;              // best fit: the smallest idle buffer that is large enough
         for (ScratchEntry &e : g_scratch)
-            if (e.ptr && !e.busy && e.device == dev && e.bytes >= bytes) {
-                e.busy = true;
-                *out = e.ptr;
-                return RSFM_OK;
-            }
+            if (e.ptr && !e.busy && e.device == dev && e.bytes >= bytes && (!best || e.bytes < best->bytes)) best = &e;
+        if (best) {
+            best->busy = true;
+            *out = best->ptr;
+            return RSFM_OK;
+        }
     }
     CUDA_TRY(cudaMalloc(out, bytes));
     return RSFM_OK;

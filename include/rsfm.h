@@ -9,6 +9,12 @@
  * return 0 on success and a negative rsfm_status on error, never throw, and do
  * not synchronise the stream unless stated.
  *
+ * Devices and threads: a sampler lives on the device that was current in
+ * rsfm_create; that device must be current in every later call on it
+ * (rsfm_destroy switches by itself).  A sampler is used from one thread at a
+ * time; different samplers and rsfm_forward_batch may be used concurrently.
+ * rsfm_last_error is per thread.
+ *
  * Layouts are chain-minor ("SoA") so that one warp = 32 consecutive chains reads
  * and writes 256 contiguous bytes:
  *     params   [P][C]          q0, proposals  [d][C] or [n_iters][d][C]
