@@ -66,3 +66,28 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "from oracle" not in text and "import oracle" not in text, f
                 assert "rsf_oracle" not in text, f
+
+
+def test_cfg_validation_needs_no_device(built_lib, pkg):
+    """Argument checks come before any device work: bad configurations are refused with a message,
+    with or without a GPU (rsfm_status RSFM_ERR_INVALID, like the ValueError a Python reference raises)."""
+    import ctypes as C
+    lib = pkg._lib.load()
+    cfg = pkg._lib.RsfmCfg()
+    lib.rsfm_cfg_defaults(C.byref(cfg))
+
+    def refused(**kw):
+        c = pkg._lib.RsfmCfg()
+        C.memmove(C.byref(c), C.byref(cfg), C.sizeof(c))
+        for k, v in kw.items():
+            setattr(c, k, v)
+        rc = lib.rsfm_forward_batch(C.byref(c), 4, None, None, None, None, None, None, None, None, None, None, None, None)
+        return rc, lib.rsfm_last_error().decode()
+
+    for kw, word in (({"loading": pkg._lib.LOAD_VSTEP, "vstep_period": 0.0}, "vstep_period"),
+                     ({"rtol": 0.0}, "rtol"), ({"n_params": 2}, "n_params"), ({"loading": 7}, "loading"),
+                     ({"adapt_interval": 1}, "adapt_interval"), ({"delta_t": 0.0}, "grid"), ({"a": -1.0}, "positive")):
+        rc, msg = refused(**kw)
+        assert rc < 0 and word in msg, (kw, rc, msg)
+    rc, msg = refused()                        # valid cfg, NULL parameter pointer
+    assert rc < 0 and "dc_dev" in msg
