@@ -119,7 +119,10 @@ int rsfm_forward_batch(const rsfm_cfg *cfg, int32_t C,
 
 /* Sampler object = the state of C independent MCMC.sample() runs (MCMC.py:391-544).
  * chain_id0 is the global id of local chain 0 (Philox key = seed, counter =
- * global chain id, iteration, slot), so results do not depend on the sharding. */
+ * global chain id, iteration, slot), so results do not depend on the sharding.
+ * All device state lives in one buffer taken from (and, on rsfm_destroy, returned to)
+ * the library's cache; rsfm_destroy synchronises the device first.  rsfm_init
+ * synchronises `stream` before it returns. */
 rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t seed, uint64_t chain_id0);
 void          rsfm_destroy(rsfm_sampler *s);
 
