@@ -853,7 +853,11 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
 // resolution time a stopped node counts as rejected only if H >= the true threshold (then rejection
 // is certain), otherwise it is unresolved and the round ends before it -- that iteration becomes the
 // root of the next round.  Exactness never depends on H.
-template <int D>
+//
+// COMPAT = true (d = 1, the reference's dict-prior adaptation): the proposal scale changes after every
+// adapt_interval-th sample, so a round never looks past that boundary; the writer lane keeps the
+// reference's sample ring and hands the new scale to its group when the boundary is reached.
+template <int D, bool COMPAT>
 __global__ void __launch_bounds__(128)
 rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
 {
@@ -894,7 +898,8 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
     int it = 0;
     while (__any_sync(FULL_MASK, chain_ok && it < A.n_iters)) {
         const bool live = chain_ok && it < A.n_iters;
-        const int rmax = live ? min(g, A.n_iters - it) : 0;
+        int rmax = live ? min(g, A.n_iters - it) : 0;
+        if (COMPAT) rmax = min(rmax, A.adapt_interval - (int)((A.iter0 + it) % A.adapt_interval));
         const bool mine = live && node > 0 && depth <= rmax;
         // ---- proposal of this node: replay the path encoded in `node` ----
         double qn[D], cur[D];
@@ -1026,10 +1031,32 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
 #pragma unroll
                     for (int b = 0; b <= a; b++) sqq[t++] += q[a] * q[b];
             }
+            if (COMPAT && writer) S.ring[(size_t)((A.iter0 + it + m) % A.adapt_interval) * Cz + chain] = q[0];
             j = acc ? 2 * j + 1 : 2 * j;
             ndone++;
         }
         it += ndone;
+        if (COMPAT) {
+            // MCMC.py:523-527 + 200-204 at the boundary the round just reached (same arithmetic as
+            // rsf_mcmc_kernel); every lane of the group then proposes with the new scale
+            double lnew = L[0];
+            const int W = A.adapt_interval;
+            const long long gi = A.iter0 + it;
+            if (writer && ndone > 0 && gi % W == 0) {
+                double mean = 0.0;
+                for (int w = 1; w <= W; w++) mean += S.ring[(size_t)((gi - W + w) % W) * Cz + chain];
+                mean /= W;
+                double v = 0.0;
+                for (int w = 1; w <= W; w++) {
+                    const double dlt = S.ring[(size_t)((gi - W + w) % W) * Cz + chain] - mean;
+                    v += dlt * dlt;
+                }
+                v /= (W - 1);
+                const double vnew = 2.38 * 2.38 / 2.0 * v;
+                if (vnew > 0.0) lnew = sqrt(vnew);
+            }
+            L[0] = __shfl_sync(FULL_MASK, lnew, gbase + 1);
+        }
     }
 
     if (writer) {
@@ -1037,6 +1064,7 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
 #pragma unroll
         for (int j = 0; j < D; j++) S.q[j * Cz + c] = q[j];
         S.sse[c] = ss; S.sigma2[c] = s2;
+        if (COMPAT) S.chol[c] = L[0];
         S.accepted[c] += n_acc;
         S.nrhs[c] += nrhs; S.nstep[c] += nstep; S.status[c] |= status; S.nsolve[c] += nsolve; S.nearly[c] += nearly;
         S.nexec[c] += nexec; S.urhs[c] += urhs; S.ustep[c] += ustep;
@@ -1052,7 +1080,8 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
 // depth of the speculation tree for C chains: the largest g with C 2^g threads <= one warp per SMSP
 static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
 {
-    if (A.deterministic || s->cfg.adapt_mode == RSFM_ADAPT_COMPAT) return 0;
+    if (A.deterministic) return 0;
+    if (s->cfg.adapt_mode == RSFM_ADAPT_COMPAT && s->cfg.n_params != 1) return 0;
     if (s->cfg.n_out > 2 * SERIES_TILE) return 0;          // streamed series: block barriers, no speculation
     int want = s->cfg.spec_depth;
     if (const char *e = getenv("RSFM_SPEC_DEPTH")) want = atoi(e);
@@ -1092,8 +1121,10 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
         const long long threads = (long long)C << g;
         const int sblock = threads <= 148 * 32 * 4 ? 32 : 128;
         const int sgrid = (int)((threads + sblock - 1) / sblock);
-        if (s->cfg.n_params == 1) rsf_mcmc_spec_kernel<1><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);
-        else rsf_mcmc_spec_kernel<3><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);
+        if (s->cfg.n_params == 1 && s->cfg.adapt_mode == RSFM_ADAPT_COMPAT)
+            rsf_mcmc_spec_kernel<1, true><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);
+        else if (s->cfg.n_params == 1) rsf_mcmc_spec_kernel<1, false><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);
+        else rsf_mcmc_spec_kernel<3, false><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);
     } else if (s->cfg.n_params == 1) {
         if (A.deterministic) rsf_mcmc_kernel<1, true><<<grid, block, 0, stream>>>(M, C, s->d, A);
         else rsf_mcmc_kernel<1, false><<<grid, block, 0, stream>>>(M, C, s->d, A);

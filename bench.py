@@ -351,7 +351,7 @@ def run_b200(args):
                          "frac": achieved_tf / (peak.value / 1e12), "traffic": traffic,
                          "executed_incl_speculative": executed_tf,
                          "executed_frac": executed_tf / (peak.value / 1e12),
-                         "kernel": (f"rsf_mcmc_spec_kernel<1> (speculation depth {spec_g}: {1 << spec_g} lanes per chain)"
+                         "kernel": (f"rsf_mcmc_spec_kernel<1,false> (speculation depth {spec_g}: {1 << spec_g} lanes per chain)"
                                     if spec_g >= 2 else "rsf_mcmc_kernel<1,false> (one thread per chain)"), "peak_source": "rsfm_measure_fp64_peak (DFMA chains, live)",
                          "flops_convention": "35 per RHS + 480 per DOP853 step (SURVEY.md 8d)",
                          "hbm": {"achieved_gbs": alg_bytes / (dev_s / K) / 1e9, "peak_gbs": hbm_peak,

@@ -178,27 +178,35 @@ def test_reference_api_surface(cuda, pkg, capsys):
         assert open(fn).read().count('"__ndarray__": true') == 3
 
 
-@pytest.mark.parametrize("d,names,q0,bounds", [
-    (1, ("Dc",), 1000.0, None),
-    (3, ("a", "b", "Dc"), np.array([0.0105, 0.0145, 1200.0]), [[0.005, 0.02], [0.005, 0.03], [0.0, 10000.0]]),
+@pytest.mark.parametrize("d,names,q0,bounds,priors", [
+    (1, ("Dc",), 1000.0, None, ["Uniform", 0.0, 1e4]),
+    (3, ("a", "b", "Dc"), np.array([0.0105, 0.0145, 1200.0]), [[0.005, 0.02], [0.005, 0.03], [0.0, 10000.0]],
+     ["Uniform", 0.0, 1e4]),
+    (1, ("Dc",), 1000.0, None, {1: 0.0, 2: 1e4}),         # dict priors: the reference's adaptation every 10 samples
 ])
-def test_speculative_kernel_is_bit_identical(cuda, pkg, d, names, q0, bounds):
+def test_speculative_kernel_is_bit_identical(cuda, pkg, d, names, q0, bounds, priors):
     """Speculative (prefetching) Metropolis evaluates the tree of the next g iterations in parallel; it
-    must return exactly the chains of the sequential kernel: same samples, sigma^2, accept flags."""
+    must return exactly the chains of the sequential kernel: same samples, sigma^2, accept flags --
+    also when the reference's windowed adaptation changes the proposal scale on the way (rounds stop
+    at the adaptation boundary)."""
     g = load_golden("sse_grid.json")
     model = pkg.RateStateModel()
     outs = []
     for depth in (1, 2, 3, 5, 0):
-        mc = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=23, n_chains=24, verbose=False,
-                      seed=11, param_names=names, bounds=bounds, spec_depth=depth)
+        mc = pkg.MCMC(model, g["data"], 1350.0, priors, q0, nsamples=47 if isinstance(priors, dict) else 23,
+                      n_chains=24, verbose=False, seed=11, param_names=names, bounds=bounds, spec_depth=depth)
+        assert mc.compat_adapt == isinstance(priors, dict)
         out = mc.sample(False)
-        outs.append((out, mc.std2.copy(), mc.accepts.copy(), mc.stats))
+        outs.append((out, mc.std2.copy(), mc.accepts.copy(), mc.stats, mc.checkpoint()["chol"]))
     ref = outs[0]
     assert ref[3]["nsolves_executed"] == ref[3]["nsolves"]
-    for depth, (out, s2, acc, stats) in zip((2, 3, 5, 0), outs[1:]):
+    if isinstance(priors, dict):                     # the proposal scale did move away from Vstart
+        assert not np.any(ref[4][0] == mc.Vstart[0, 0])
+    for depth, (out, s2, acc, stats, chol) in zip((2, 3, 5, 0), outs[1:]):
         assert np.array_equal(out, ref[0]), depth
         assert np.array_equal(s2, ref[1]), depth
         assert np.array_equal(acc, ref[2]), depth
+        assert np.array_equal(chol, ref[4]), depth
         assert stats["nsolves"] == ref[3]["nsolves"]
         assert stats["nsolves_executed"] > stats["nsolves"]          # speculation did extra work
     assert 0 < ref[2].mean() < 1
