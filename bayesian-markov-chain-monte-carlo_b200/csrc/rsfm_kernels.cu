@@ -694,123 +694,223 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
     SeriesStage series;
     series.begin(s_tile, s_bar, S.data, M.n_out);
 
-#pragma unroll 1
-    for (int it = 0; it < A.n_iters; it++) {
-        const unsigned int giter = (unsigned int)(A.iter0 + it);
-        // ---- proposal (MCMC.py:497) ----
-        double qn[D];
-        if (DET && !A.proposals_are_z) {
+    // d = 3, Philox-driven: a proposal outside the prior box is rejected without a solve (MCMC.py:318-320),
+    // and with a wide posterior that is every other proposal (cfg 3).  Instead of idling through the solve of
+    // its warp-mates, a lane walks on through its own out-of-bounds iterations (sigma^2 draw, outputs, pooled
+    // sums -- everything but a solve) until it holds an in-bounds proposal; the warp then solves together.
+    // Lanes get out of step in iteration count, not in results: every draw is keyed by (chain, iteration).
+    // Needs a single-tile resident series (no block barriers after the first solve).
+    constexpr bool SKIP_T = (D == 3) && !DET;
+    if constexpr (SKIP_T) {
+        const bool skip_ok = M.n_out <= SERIES_TILE;
+        auto propose = [&](int it_, double (&qn_)[D]) {
+            const unsigned int giter = (unsigned int)(A.iter0 + it_);
+            double z0, z1, z2, zz;
+            philox_normal2(key, gid, giter, 0u, z0, z1);
+            philox_normal2(key, gid, giter, 1u, z2, zz);
+            qn_[0] = q[0] + L[0] * z0;
+            qn_[1] = q[1] + L[1] * z0 + L[2] * z1;
+            qn_[2] = q[2] + L[3] * z0 + L[4] * z1 + L[5] * z2;
+            bool inb_ = true;
 #pragma unroll
-            for (int j = 0; j < D; j++) qn[j] = A.proposals[((size_t)it * D + j) * Cz + cc];
-        } else {
-            double z[D];
-            if (DET) {
-#pragma unroll
-                for (int j = 0; j < D; j++) z[j] = A.proposals[((size_t)it * D + j) * Cz + cc];
-            } else {
-                double z0, z1;
-                philox_normal2(key, gid, giter, 0u, z0, z1);
-                z[0] = z0;
-                if (D > 1) z[1] = z1;
-                if (D > 2) { philox_normal2(key, gid, giter, 1u, z0, z1); z[2] = z0; }
+            for (int j = 0; j < D; j++) inb_ = inb_ && (qn_[j] > A.lo[j]) && (qn_[j] < A.hi[j]);
+            return inb_;
+        };
+        // everything of an iteration after the accept / reject decision (sigma^2 draw, outputs, pooled sums)
+        auto finish = [&](int it_, bool acc_, const double (&qn_)[D], double u_) {
+            const unsigned int giter = (unsigned int)(A.iter0 + it_);
+            const double g0 = philox_gamma(key, gid, giter, gshape);
+            {
+                const double bval = 0.5 * (A.n0 * s2 + ss);
+                const double scale = 1.0 / bval;
+                s2 = 1.0 / (g0 * scale);
             }
-            if (D == 1) {
-                qn[0] = q[0] + sqrt(L[0]) * z[0];       // L[0] is the proposal variance for d = 1
-            } else {
-                qn[0] = q[0] + L[0] * z[0];
-                qn[1] = q[1] + L[1] * z[0] + L[2] * z[1];
-                qn[2] = q[2] + L[3] * z[0] + L[4] * z[1] + L[5] * z[2];
-            }
-        }
-        // ---- strict box prior (MCMC.py:318-320) ----
-        bool inb = true;
-#pragma unroll
-        for (int j = 0; j < D; j++) inb = inb && (qn[j] > A.lo[j]) && (qn[j] < A.hi[j]);
-        const bool solve = active && inb;
-        // ---- acceptance uniform first (MCMC.py:331): it fixes the rejection threshold ----
-        // accept  <=>  min(0, 0.5 (SS - SS')/s2) > ln U  <=>  SS' < SS - 2 s2 ln U   (ln U < 0)
-        double u = nan("");
-        double lnu = 0.0;
-        if (solve) {
-            if (DET) u = A.uniforms[(size_t)it * Cz + cc];
-            else u = philox_uniform(key, gid, giter, 2u);
-            lnu = log(u);
-        }
-        const double sse_limit = solve ? ss - 2.0 * s2 * lnu : INFINITY;
-        // ---- forward solve + SSE (MCMC.py:324, 381-387), stopped early once rejection is certain ----
-        const double pa = (D == 3) ? qn[0] : A.a0;
-        const double pb = (D == 3) ? qn[1] : A.b0;
-        const double pdc = solve ? qn[D - 1] : q[D - 1];
-        series.start_solve();
-        SolveOut o = rsf_solve(M, solve ? pa : ((D == 3) ? q[0] : A.a0), solve ? pb : ((D == 3) ? q[1] : A.b0), pdc,
-                               solve, series, lscr, nullptr, nullptr, Cz, 1.0, nullptr, nullptr, sse_limit);
-        // ---- accept / reject (MCMC.py:327-331) ----
-        bool acc = false;
-        if (solve) {
-            nrhs += o.nrhs; nstep += o.nstep; status |= (o.status & ~RSFM_CHAIN_EARLY); nsolve++;
-            if (o.status & RSFM_CHAIN_EARLY) nearly++;
-            double la = 0.5 * (ss - o.sse) / s2;
-            if (la > 0.0) la = 0.0;
-            acc = la > lnu;
-            if (acc) {
-#pragma unroll
-                for (int j = 0; j < D; j++) q[j] = qn[j];
-                ss = o.sse;
-                n_acc++;
-            }
-        }
-        // ---- sigma^2 Gibbs draw (MCMC.py:158-160) ----
-        double g0;
-        if (DET) g0 = A.gammas[(size_t)it * Cz + cc];
-        else g0 = philox_gamma(key, gid, giter, gshape);
-        {
-            const double bval = 0.5 * (A.n0 * s2 + ss);
-            const double scale = 1.0 / bval;
-            s2 = 1.0 / (g0 * scale);
-        }
-        // ---- outputs ----
-        if (active) {
             if (A.samples) {
 #pragma unroll
-                for (int j = 0; j < D; j++) A.samples[((size_t)it * D + j) * Cz + c] = q[j];
+                for (int j = 0; j < D; j++) A.samples[((size_t)it_ * D + j) * Cz + c] = q[j];
             }
-            if (A.sigma2_out) A.sigma2_out[(size_t)it * Cz + c] = s2;
-            if (A.accept) A.accept[(size_t)it * Cz + c] = acc ? 1 : 0;
+            if (A.sigma2_out) A.sigma2_out[(size_t)it_ * Cz + c] = s2;
+            if (A.accept) A.accept[(size_t)it_ * Cz + c] = acc_ ? 1 : 0;
             if (A.draws) {
 #pragma unroll
-                for (int j = 0; j < D; j++) A.draws[((size_t)it * (D + 2) + j) * Cz + c] = qn[j];
-                A.draws[((size_t)it * (D + 2) + D) * Cz + c] = u;
-                A.draws[((size_t)it * (D + 2) + D + 1) * Cz + c] = g0;
+                for (int j = 0; j < D; j++) A.draws[((size_t)it_ * (D + 2) + j) * Cz + c] = qn_[j];
+                A.draws[((size_t)it_ * (D + 2) + D) * Cz + c] = u_;
+                A.draws[((size_t)it_ * (D + 2) + D + 1) * Cz + c] = g0;
+            }
+            if (A.adapt_mode == RSFM_ADAPT_POOLED) {
+#pragma unroll
+                for (int j = 0; j < D; j++) sq[j] += q[j];
+                int t = 0;
+#pragma unroll
+                for (int i = 0; i < D; i++)
+#pragma unroll
+                    for (int j = 0; j <= i; j++) sqq[t++] += q[i] * q[j];
+            }
+        };
+        int it = 0;
+#pragma unroll 1
+        for (int trip = 0;; trip++) {
+            bool live = active && it < A.n_iters;
+            if (skip_ok) { if (trip > 0 && !__any_sync(FULL_MASK, live)) break; }
+            else if (trip >= A.n_iters) break;
+            double qn[D] = {q[0], q[1], q[2]};
+            bool inb = false;
+            while (live) {
+                inb = propose(it, qn);
+                if (inb || !skip_ok) break;
+                finish(it, false, qn, nan(""));
+                it++;
+                live = it < A.n_iters;
+            }
+            const bool solve = live && inb;
+            double u = nan("");
+            double lnu = 0.0;
+            if (solve) {
+                u = philox_uniform(key, gid, (unsigned int)(A.iter0 + it), 2u);
+                lnu = log(u);
+            }
+            const double sse_limit = solve ? ss - 2.0 * s2 * lnu : INFINITY;
+            series.start_solve();
+            SolveOut o = rsf_solve(M, solve ? qn[0] : q[0], solve ? qn[1] : q[1], solve ? qn[2] : q[2], solve, series, lscr,
+                                   nullptr, nullptr, Cz, 1.0, nullptr, nullptr, sse_limit);
+            bool acc = false;
+            if (solve) {
+                nrhs += o.nrhs; nstep += o.nstep; status |= (o.status & ~RSFM_CHAIN_EARLY); nsolve++;
+                if (o.status & RSFM_CHAIN_EARLY) nearly++;
+                double la = 0.5 * (ss - o.sse) / s2;
+                if (la > 0.0) la = 0.0;
+                acc = la > lnu;
+                if (acc) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) q[j] = qn[j];
+                    ss = o.sse;
+                    n_acc++;
+                }
+            }
+            if (live) {
+                finish(it, acc, qn, u);
+                it++;
             }
         }
-        // ---- adaptation ----
-        if (A.adapt_mode == RSFM_ADAPT_POOLED) {
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < A.n_iters; it++) {
+            const unsigned int giter = (unsigned int)(A.iter0 + it);
+            // ---- proposal (MCMC.py:497) ----
+            double qn[D];
+            if (DET && !A.proposals_are_z) {
 #pragma unroll
-            for (int j = 0; j < D; j++) sq[j] += q[j];
-            int t = 0;
+                for (int j = 0; j < D; j++) qn[j] = A.proposals[((size_t)it * D + j) * Cz + cc];
+            } else {
+                double z[D];
+                if (DET) {
 #pragma unroll
-            for (int i = 0; i < D; i++)
-#pragma unroll
-                for (int j = 0; j <= i; j++) sqq[t++] += q[i] * q[j];
-        }
-        if (D == 1 && A.adapt_mode == RSFM_ADAPT_COMPAT && active) {
-            // MCMC.py:523-527 + 200-204: V <- chol(2.38^2/len(keys) * cov(last W samples)), W = adapt_interval,
-            // len(qpriors.keys()) = 2 for the dict form.  The Cholesky FACTOR is then used as a covariance (q3).
-            const int W = A.adapt_interval;
-            const long long gi = A.iter0 + it + 1;              // chain index of the sample just appended
-            S.ring[(size_t)(gi % W) * Cz + c] = q[0];
-            if (gi % W == 0) {
-                double mean = 0.0;
-                for (int w = 1; w <= W; w++) mean += S.ring[(size_t)((gi - W + w) % W) * Cz + c];
-                mean /= W;
-                double v = 0.0;
-                for (int w = 1; w <= W; w++) {
-                    const double dlt = S.ring[(size_t)((gi - W + w) % W) * Cz + c] - mean;
-                    v += dlt * dlt;
+                    for (int j = 0; j < D; j++) z[j] = A.proposals[((size_t)it * D + j) * Cz + cc];
+                } else {
+                    double z0, z1;
+                    philox_normal2(key, gid, giter, 0u, z0, z1);
+                    z[0] = z0;
+                    if (D > 1) z[1] = z1;
+                    if (D > 2) { philox_normal2(key, gid, giter, 1u, z0, z1); z[2] = z0; }
                 }
-                v /= (W - 1);
-                const double vnew = 2.38 * 2.38 / 2.0 * v;
-                if (vnew > 0.0) L[0] = sqrt(vnew);             // cov = 0 -> cholesky raises -> unchanged (q4)
+                if (D == 1) {
+                    qn[0] = q[0] + sqrt(L[0]) * z[0];       // L[0] is the proposal variance for d = 1
+                } else {
+                    qn[0] = q[0] + L[0] * z[0];
+                    qn[1] = q[1] + L[1] * z[0] + L[2] * z[1];
+                    qn[2] = q[2] + L[3] * z[0] + L[4] * z[1] + L[5] * z[2];
+                }
+            }
+            // ---- strict box prior (MCMC.py:318-320) ----
+            bool inb = true;
+#pragma unroll
+            for (int j = 0; j < D; j++) inb = inb && (qn[j] > A.lo[j]) && (qn[j] < A.hi[j]);
+            const bool solve = active && inb;
+            // ---- acceptance uniform first (MCMC.py:331): it fixes the rejection threshold ----
+            // accept  <=>  min(0, 0.5 (SS - SS')/s2) > ln U  <=>  SS' < SS - 2 s2 ln U   (ln U < 0)
+            double u = nan("");
+            double lnu = 0.0;
+            if (solve) {
+                if (DET) u = A.uniforms[(size_t)it * Cz + cc];
+                else u = philox_uniform(key, gid, giter, 2u);
+                lnu = log(u);
+            }
+            const double sse_limit = solve ? ss - 2.0 * s2 * lnu : INFINITY;
+            // ---- forward solve + SSE (MCMC.py:324, 381-387), stopped early once rejection is certain ----
+            const double pa = (D == 3) ? qn[0] : A.a0;
+            const double pb = (D == 3) ? qn[1] : A.b0;
+            const double pdc = solve ? qn[D - 1] : q[D - 1];
+            series.start_solve();
+            SolveOut o = rsf_solve(M, solve ? pa : ((D == 3) ? q[0] : A.a0), solve ? pb : ((D == 3) ? q[1] : A.b0), pdc,
+                                   solve, series, lscr, nullptr, nullptr, Cz, 1.0, nullptr, nullptr, sse_limit);
+            // ---- accept / reject (MCMC.py:327-331) ----
+            bool acc = false;
+            if (solve) {
+                nrhs += o.nrhs; nstep += o.nstep; status |= (o.status & ~RSFM_CHAIN_EARLY); nsolve++;
+                if (o.status & RSFM_CHAIN_EARLY) nearly++;
+                double la = 0.5 * (ss - o.sse) / s2;
+                if (la > 0.0) la = 0.0;
+                acc = la > lnu;
+                if (acc) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) q[j] = qn[j];
+                    ss = o.sse;
+                    n_acc++;
+                }
+            }
+            // ---- sigma^2 Gibbs draw (MCMC.py:158-160) ----
+            double g0;
+            if (DET) g0 = A.gammas[(size_t)it * Cz + cc];
+            else g0 = philox_gamma(key, gid, giter, gshape);
+            {
+                const double bval = 0.5 * (A.n0 * s2 + ss);
+                const double scale = 1.0 / bval;
+                s2 = 1.0 / (g0 * scale);
+            }
+            // ---- outputs ----
+            if (active) {
+                if (A.samples) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) A.samples[((size_t)it * D + j) * Cz + c] = q[j];
+                }
+                if (A.sigma2_out) A.sigma2_out[(size_t)it * Cz + c] = s2;
+                if (A.accept) A.accept[(size_t)it * Cz + c] = acc ? 1 : 0;
+                if (A.draws) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) A.draws[((size_t)it * (D + 2) + j) * Cz + c] = qn[j];
+                    A.draws[((size_t)it * (D + 2) + D) * Cz + c] = u;
+                    A.draws[((size_t)it * (D + 2) + D + 1) * Cz + c] = g0;
+                }
+            }
+            // ---- adaptation ----
+            if (A.adapt_mode == RSFM_ADAPT_POOLED) {
+#pragma unroll
+                for (int j = 0; j < D; j++) sq[j] += q[j];
+                int t = 0;
+#pragma unroll
+                for (int i = 0; i < D; i++)
+#pragma unroll
+                    for (int j = 0; j <= i; j++) sqq[t++] += q[i] * q[j];
+            }
+            if (D == 1 && A.adapt_mode == RSFM_ADAPT_COMPAT && active) {
+                // MCMC.py:523-527 + 200-204: V <- chol(2.38^2/len(keys) * cov(last W samples)), W = adapt_interval,
+                // len(qpriors.keys()) = 2 for the dict form.  The Cholesky FACTOR is then used as a covariance (q3).
+                const int W = A.adapt_interval;
+                const long long gi = A.iter0 + it + 1;              // chain index of the sample just appended
+                S.ring[(size_t)(gi % W) * Cz + c] = q[0];
+                if (gi % W == 0) {
+                    double mean = 0.0;
+                    for (int w = 1; w <= W; w++) mean += S.ring[(size_t)((gi - W + w) % W) * Cz + c];
+                    mean /= W;
+                    double v = 0.0;
+                    for (int w = 1; w <= W; w++) {
+                        const double dlt = S.ring[(size_t)((gi - W + w) % W) * Cz + c] - mean;
+                        v += dlt * dlt;
+                    }
+                    v /= (W - 1);
+                    const double vnew = 2.38 * 2.38 / 2.0 * v;
+                    if (vnew > 0.0) L[0] = sqrt(vnew);             // cov = 0 -> cholesky raises -> unchanged (q4)
+                }
             }
         }
     }

@@ -183,6 +183,10 @@ def test_reference_api_surface(cuda, pkg, capsys):
     (3, ("a", "b", "Dc"), np.array([0.0105, 0.0145, 1200.0]), [[0.005, 0.02], [0.005, 0.03], [0.0, 10000.0]],
      ["Uniform", 0.0, 1e4]),
     (1, ("Dc",), 1000.0, None, {1: 0.0, 2: 1e4}),         # dict priors: the reference's adaptation every 10 samples
+    # a tight box: most proposals fall outside it, so the sequential d = 3 kernel walks lanes through
+    # different numbers of solve-free iterations between solves
+    (3, ("a", "b", "Dc"), np.array([0.0105, 0.0145, 1200.0]), [[0.0103, 0.0107], [0.0143, 0.0147], [1150.0, 1250.0]],
+     ["Uniform", 0.0, 1e4]),
 ])
 def test_speculative_kernel_is_bit_identical(cuda, pkg, d, names, q0, bounds, priors):
     """Speculative (prefetching) Metropolis evaluates the tree of the next g iterations in parallel; it
@@ -381,3 +385,29 @@ def test_shard_invariance_at_cfg5_shard_size(cuda, pkg):
     assert np.array_equal(out[:h], lo) and np.array_equal(out[h:], hi)
     moved = np.abs(out[:, 0, -1] - q0) > 0
     assert 0.2 < moved.mean() <= 1.0          # most chains accepted something within the first iterations
+
+
+def test_out_of_bounds_walk_with_idle_warps_and_pooled_sums(cuda, pkg):
+    """d = 3 sequential kernel at a size whose last 64-thread block holds one chain and one empty warp:
+    lanes that skip ahead through out-of-bounds iterations must leave every output row written, the
+    pooled sums complete, and the chains independent of the launch partition (8 = 3 + 3 + 2 iterations)."""
+    g = load_golden("sse_grid.json")
+    model = pkg.RateStateModel()
+    c = 4737
+    rng = np.random.default_rng(4)
+    q0 = np.stack([rng.uniform(0.0104, 0.0106, c), rng.uniform(0.0144, 0.0146, c), rng.uniform(1180.0, 1220.0, c)], axis=1)
+    kw = dict(n_chains=c, verbose=False, seed=21, param_names=("a", "b", "Dc"), spec_depth=1,
+              bounds=[[0.0100, 0.0110], [0.0140, 0.0150], [1100.0, 1300.0]])
+    one = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=8, **kw)
+    out = one.sample(False)
+    full = one.samples_device.cpu().numpy()                    # [9, 3, C] incl. the start values
+    assert np.isfinite(full).all() and np.all(full[:, 0] > 0.0100) and np.all(full[:, 2] < 1300.0)
+    acc = one.accept_device.cpu().numpy()
+    moved = np.any(full[1:] != full[:-1], axis=1)              # [8, C]
+    assert np.array_equal(moved, acc.astype(bool))
+    assert one.stats["nsolves"] < 8 * c + 4 * c               # out-of-bounds proposals cost no solve
+    # pooled adaptation path: launches of adapt_interval iterations, sums over every iteration of every chain
+    pooled = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=8, adapt="pooled",
+                      adapt_start=1000, adapt_interval=3, **kw)
+    out_p = pooled.sample(False)
+    assert np.array_equal(out_p, out)                          # no adaptation before adapt_start: same chains
