@@ -35,6 +35,8 @@ constexpr int SERIES_TILE = 512;          // doubles per staged tile (4 KB)
 struct ModelK {
     double mu_ref, V_ref, k1, t_start, delta_t, mu_t_zero;
     double rtol, atol, vstep_period, vstep_factor;
+    double vstep_lnf, vstep_rfac;      // log(vstep_factor), 1/vstep_factor: host-computed (re-basing, see rsf_interval_general)
+    double vstep_rper;                 // 1/vstep_period (vstep_index)
     int n_out, nmax, damping, loading, integ_mode;
 };
 
@@ -216,10 +218,23 @@ __device__ __noinline__ double loading_rel(int loading, double t_start, double p
     return exp(-t / 20.0) * sin(10.0 * t);
 }
 
+// Period index floor((t - t_start)/period) of the VSTEP load, as the correctly rounded division gives it.
+// The product with the host-computed reciprocal differs from the rounded quotient by a few ulp at most, so its
+// floor is the same unless the quotient lies within 1e-9 (relative) of an integer; only then is the division done
+// (output times that are multiples of the period: one interval end per period).
+__device__ __forceinline__ double vstep_index(const ModelK &M, double t)
+{
+    const double x = t - M.t_start;
+    const double q = x * M.vstep_rper;
+    const double n = rint(q);
+    if (fabs(q - n) <= 1e-9 * fmax(1.0, fabs(n))) return floor(x / M.vstep_period);
+    return floor(q);
+}
+
 __device__ __forceinline__ double loading_of(const ModelK &M, double t)
 {
     if (M.loading == RSFM_LOAD_VSTEP) {            // piecewise constant: cheap enough to inline
-        const long long i = (long long)floor((t - M.t_start) / M.vstep_period);
+        const long long i = (long long)vstep_index(M, t);
         return (i & 1) ? M.vstep_factor - 1.0 : 0.0;
     }
     return loading_rel(M.loading, M.t_start, M.vstep_period, M.vstep_factor, t);
@@ -327,62 +342,81 @@ struct StepIn { double h, mu, th, V, k1m, k1t, k1v, rth, atol, rtol; };
 // err = |h| ||e5||^2 / sqrt(3 (||e5||^2 + 0.01 ||e3||^2)) = |h| errA / sqrt(den3)   (dop853.f, n = 3)
 struct StepOut { double muN, thN, VN, errA, den3, L12, rth; };
 
-template <bool FAST>
+// What a fast step hands to the general step when one of its stages left the fast ranges: the stage
+// derivatives that are still exact (every stage before the first offending one).  Stages 2, 3 feed no later
+// stage than 5, so only k4..k11 (mu', theta') and the V' of stages 6..11 are kept.
+struct StepSave { double km[8], kt[8], kv[6]; };
+
+// General-range step: the reference's formulas (libdevice log / exp, true division) at every stage from
+// `first` on; the stages before it are taken from the fast step that found stage `first` outside its
+// ranges (sv).  first <= 5 (in particular 2): nothing is reused.  In the stiff regime the trial step that the
+// controller grows past the stability limit leaves the ranges at stage 9, 11 or 12 in 80 % of the cases
+// (CPU oracle statistics, profiles/microbench/stiff_paths.md), so only its last stages are evaluated twice.
+// Lc, rl: the stage values of L are re-based on the fly, L' = (L - Lc) rl (see rsf_solve_mode; 0, 1 = none).
 __device__ __forceinline__ void dop853_step_impl(const ChainConst &cc, const StepIn &I, const double *Lp, int ls,
-                                                 StepOut &O, bool &bad)
+                                                 double Lc, double rl, int first, const StepSave &sv, StepOut &O)
 {
     const double h = I.h, mu = I.mu, th = I.th, k1m = I.k1m, k1t = I.k1t, k1v = I.k1v;
     double rth = I.rth;
-    double k2m, k2t, k3m, k3t, k4m, k4t, k5m, k5t, k6m, k6t, k7m, k7t, k8m, k8t, k9m, k9t, k10m, k10t;
+    bool bad = false;
+    double k2m = 0.0, k2t = 0.0, k3m = 0.0, k3t = 0.0, k4m, k4t, k5m, k5t, k6m, k6t, k7m, k7t, k8m, k8t, k9m, k9t, k10m, k10t;
     double kv, k9v, k12v, bV, eV;
+    const bool all = first < 6;
+#define RSFM_GSTAGE(S, YM, YT, KM, KT, KV, SM, ST, SV)                                                         \
+    if (all || first <= (S)) rsf_rhs<false>(cc, (Lp[((S) - 2) * ls] - Lc) * rl, YM, YT, rth, KM, KT, KV, bad); \
+    else { KM = (SM); KT = (ST); KV = (SV); }
     // stages 2..5: their V-derivatives carry zero weight everywhere
-    rsf_rhs<FAST>(cc, Lp[0 * ls], mu + h * (TB.a21 * k1m), th + h * (TB.a21 * k1t), rth, k2m, k2t, kv, bad);
-    rsf_rhs<FAST>(cc, Lp[1 * ls], mu + h * (TB.a31 * k1m + TB.a32 * k2m), th + h * (TB.a31 * k1t + TB.a32 * k2t),
-                  rth, k3m, k3t, kv, bad);
-    rsf_rhs<FAST>(cc, Lp[2 * ls], mu + h * (TB.a41 * k1m + TB.a43 * k3m), th + h * (TB.a41 * k1t + TB.a43 * k3t),
-                  rth, k4m, k4t, kv, bad);
-    rsf_rhs<FAST>(cc, Lp[3 * ls], mu + h * (TB.a51 * k1m + TB.a53 * k3m + TB.a54 * k4m),
-                  th + h * (TB.a51 * k1t + TB.a53 * k3t + TB.a54 * k4t), rth, k5m, k5t, kv, bad);
-    rsf_rhs<FAST>(cc, Lp[4 * ls], mu + h * (TB.a61 * k1m + TB.a64 * k4m + TB.a65 * k5m),
-                  th + h * (TB.a61 * k1t + TB.a64 * k4t + TB.a65 * k5t), rth, k6m, k6t, kv, bad);
+    if (all) {
+        rsf_rhs<false>(cc, (Lp[0 * ls] - Lc) * rl, mu + h * (TB.a21 * k1m), th + h * (TB.a21 * k1t), rth, k2m, k2t, kv, bad);
+        rsf_rhs<false>(cc, (Lp[1 * ls] - Lc) * rl, mu + h * (TB.a31 * k1m + TB.a32 * k2m),
+                       th + h * (TB.a31 * k1t + TB.a32 * k2t), rth, k3m, k3t, kv, bad);
+        rsf_rhs<false>(cc, (Lp[2 * ls] - Lc) * rl, mu + h * (TB.a41 * k1m + TB.a43 * k3m),
+                       th + h * (TB.a41 * k1t + TB.a43 * k3t), rth, k4m, k4t, kv, bad);
+        rsf_rhs<false>(cc, (Lp[3 * ls] - Lc) * rl, mu + h * (TB.a51 * k1m + TB.a53 * k3m + TB.a54 * k4m),
+                       th + h * (TB.a51 * k1t + TB.a53 * k3t + TB.a54 * k4t), rth, k5m, k5t, kv, bad);
+    } else {
+        k4m = sv.km[0]; k4t = sv.kt[0]; k5m = sv.km[1]; k5t = sv.kt[1];
+    }
+    RSFM_GSTAGE(6, mu + h * (TB.a61 * k1m + TB.a64 * k4m + TB.a65 * k5m),
+                th + h * (TB.a61 * k1t + TB.a64 * k4t + TB.a65 * k5t), k6m, k6t, kv, sv.km[2], sv.kt[2], sv.kv[0]);
     bV = TB.b1 * k1v + TB.b6 * kv;
     eV = TB.e1 * k1v + TB.e6 * kv;
-    rsf_rhs<FAST>(cc, Lp[5 * ls], mu + h * (TB.a71 * k1m + TB.a74 * k4m + TB.a75 * k5m + TB.a76 * k6m),
-                  th + h * (TB.a71 * k1t + TB.a74 * k4t + TB.a75 * k5t + TB.a76 * k6t), rth, k7m, k7t, kv, bad);
+    RSFM_GSTAGE(7, mu + h * (TB.a71 * k1m + TB.a74 * k4m + TB.a75 * k5m + TB.a76 * k6m),
+                th + h * (TB.a71 * k1t + TB.a74 * k4t + TB.a75 * k5t + TB.a76 * k6t), k7m, k7t, kv, sv.km[3], sv.kt[3],
+                sv.kv[1]);
     bV += TB.b7 * kv; eV += TB.e7 * kv;
-    rsf_rhs<FAST>(cc, Lp[6 * ls],
-                  mu + h * (TB.a81 * k1m + TB.a84 * k4m + TB.a85 * k5m + TB.a86 * k6m + TB.a87 * k7m),
-                  th + h * (TB.a81 * k1t + TB.a84 * k4t + TB.a85 * k5t + TB.a86 * k6t + TB.a87 * k7t), rth,
-                  k8m, k8t, kv, bad);
+    RSFM_GSTAGE(8, mu + h * (TB.a81 * k1m + TB.a84 * k4m + TB.a85 * k5m + TB.a86 * k6m + TB.a87 * k7m),
+                th + h * (TB.a81 * k1t + TB.a84 * k4t + TB.a85 * k5t + TB.a86 * k6t + TB.a87 * k7t), k8m, k8t, kv,
+                sv.km[4], sv.kt[4], sv.kv[2]);
     bV += TB.b8 * kv; eV += TB.e8 * kv;
-    rsf_rhs<FAST>(cc, Lp[7 * ls],
-                  mu + h * (TB.a91 * k1m + TB.a94 * k4m + TB.a95 * k5m + TB.a96 * k6m + TB.a97 * k7m + TB.a98 * k8m),
-                  th + h * (TB.a91 * k1t + TB.a94 * k4t + TB.a95 * k5t + TB.a96 * k6t + TB.a97 * k7t + TB.a98 * k8t),
-                  rth, k9m, k9t, k9v, bad);
+    RSFM_GSTAGE(9, mu + h * (TB.a91 * k1m + TB.a94 * k4m + TB.a95 * k5m + TB.a96 * k6m + TB.a97 * k7m + TB.a98 * k8m),
+                th + h * (TB.a91 * k1t + TB.a94 * k4t + TB.a95 * k5t + TB.a96 * k6t + TB.a97 * k7t + TB.a98 * k8t), k9m, k9t,
+                k9v, sv.km[5], sv.kt[5], sv.kv[3]);
     bV += TB.b9 * k9v; eV += TB.e9 * k9v;
-    rsf_rhs<FAST>(cc, Lp[8 * ls],
-                  mu + h * (TB.a101 * k1m + TB.a104 * k4m + TB.a105 * k5m + TB.a106 * k6m + TB.a107 * k7m +
-                            TB.a108 * k8m + TB.a109 * k9m),
-                  th + h * (TB.a101 * k1t + TB.a104 * k4t + TB.a105 * k5t + TB.a106 * k6t + TB.a107 * k7t +
-                            TB.a108 * k8t + TB.a109 * k9t),
-                  rth, k10m, k10t, kv, bad);
+    RSFM_GSTAGE(10,
+                mu + h * (TB.a101 * k1m + TB.a104 * k4m + TB.a105 * k5m + TB.a106 * k6m + TB.a107 * k7m + TB.a108 * k8m +
+                          TB.a109 * k9m),
+                th + h * (TB.a101 * k1t + TB.a104 * k4t + TB.a105 * k5t + TB.a106 * k6t + TB.a107 * k7t + TB.a108 * k8t +
+                          TB.a109 * k9t),
+                k10m, k10t, kv, sv.km[6], sv.kt[6], sv.kv[4]);
     bV += TB.b10 * kv; eV += TB.e10 * kv;
     // stage 11 -> k2 slot
-    rsf_rhs<FAST>(cc, Lp[9 * ls],
-                  mu + h * (TB.a111 * k1m + TB.a114 * k4m + TB.a115 * k5m + TB.a116 * k6m + TB.a117 * k7m +
-                            TB.a118 * k8m + TB.a119 * k9m + TB.a1110 * k10m),
-                  th + h * (TB.a111 * k1t + TB.a114 * k4t + TB.a115 * k5t + TB.a116 * k6t + TB.a117 * k7t +
-                            TB.a118 * k8t + TB.a119 * k9t + TB.a1110 * k10t),
-                  rth, k2m, k2t, kv, bad);
+    RSFM_GSTAGE(11,
+                mu + h * (TB.a111 * k1m + TB.a114 * k4m + TB.a115 * k5m + TB.a116 * k6m + TB.a117 * k7m + TB.a118 * k8m +
+                          TB.a119 * k9m + TB.a1110 * k10m),
+                th + h * (TB.a111 * k1t + TB.a114 * k4t + TB.a115 * k5t + TB.a116 * k6t + TB.a117 * k7t + TB.a118 * k8t +
+                          TB.a119 * k9t + TB.a1110 * k10t),
+                k2m, k2t, kv, sv.km[7], sv.kt[7], sv.kv[5]);
     bV += TB.b11 * kv; eV += TB.e11 * kv;
-    // stage 12 -> k3 slot, at x + h
-    const double L12 = Lp[10 * ls];
-    rsf_rhs<FAST>(cc, L12,
-                  mu + h * (TB.a121 * k1m + TB.a124 * k4m + TB.a125 * k5m + TB.a126 * k6m + TB.a127 * k7m +
-                            TB.a128 * k8m + TB.a129 * k9m + TB.a1210 * k10m + TB.a1211 * k2m),
-                  th + h * (TB.a121 * k1t + TB.a124 * k4t + TB.a125 * k5t + TB.a126 * k6t + TB.a127 * k7t +
-                            TB.a128 * k8t + TB.a129 * k9t + TB.a1210 * k10t + TB.a1211 * k2t),
-                  rth, k3m, k3t, k12v, bad);
+#undef RSFM_GSTAGE
+    // stage 12 -> k3 slot, at x + h (always evaluated here: first <= 12)
+    const double L12 = Lp[10 * ls];                 // returned as stored (the caller re-bases it for the FSAL evaluation)
+    rsf_rhs<false>(cc, (L12 - Lc) * rl,
+                   mu + h * (TB.a121 * k1m + TB.a124 * k4m + TB.a125 * k5m + TB.a126 * k6m + TB.a127 * k7m +
+                             TB.a128 * k8m + TB.a129 * k9m + TB.a1210 * k10m + TB.a1211 * k2m),
+                   th + h * (TB.a121 * k1t + TB.a124 * k4t + TB.a125 * k5t + TB.a126 * k6t + TB.a127 * k7t +
+                             TB.a128 * k8t + TB.a129 * k9t + TB.a1210 * k10t + TB.a1211 * k2t),
+                   rth, k3m, k3t, k12v, bad);
     bV += TB.b12 * k12v; eV += TB.e12 * k12v;
     // 8th-order solution, 5th/3rd-order error forms
     const double bM = TB.b1 * k1m + TB.b6 * k6m + TB.b7 * k7m + TB.b8 * k8m + TB.b9 * k9m + TB.b10 * k10m +
@@ -428,7 +462,10 @@ __device__ __forceinline__ void dop853_step_impl(const ChainConst &cc, const Ste
 // Values agree with the textbook order to rounding; both are the same function of (mu_s, theta_s).
 struct StageOut { double km, kt, kv, d0, c; };
 
-__device__ __forceinline__ void rsf_stage_fast(const ChainConst &cc, double fs, double As, double dl, double th1,
+// (WANT_OK = false keeps the range test in the one-expression form the fast interval was tuned with: ptxas
+//  schedules the whole 1,000-instruction block ~25 % longer when the flag is also materialised.)
+template <bool WANT_OK>
+__device__ __forceinline__ bool rsf_stage_fast(const ChainConst &cc, double fs, double As, double dl, double th1,
                                                double kVL, double &rth, StageOut &o, bool &bad)
 {
     double p = fma(cc.cq[5], fs, cc.cq[4]);
@@ -457,11 +494,21 @@ __device__ __forceinline__ void rsf_stage_fast(const ChainConst &cc, double fs, 
     o.c = cc.k1e * v0;
     o.km = o.d0 - o.c;                                          // mu' with radiation damping
     o.kv = fma(-(voa * cc.k1e), v0, v0);                        // V'
+    if (WANT_OK) {
+        const bool ok = fabs(fs) * cc.qscale < 0.001953125 && fabs(As) < 0.015625 && fabs(e0) < 6.0e-5;
+        bad = bad || !ok;
+        return ok;
+    }
     bad = bad || !(fabs(fs) * cc.qscale < 0.001953125 && fabs(As) < 0.015625 && fabs(e0) < 6.0e-5);
+    return true;
 }
 
+// RB = true: re-based frame (see Rebase): cc holds the re-based constants and the stage values of L are taken
+// relative to the base level, k'V_ref' L' = kVb (L - Lc) with kVb the chain's own k'V_ref.
+template <bool RB>
 __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const StepIn &I, const double *Lp, int ls,
-                                                 StepOut &O, bool &bad)
+                                                 double kVb, double Lc, StepOut &O, bool &bad, int &first_bad,
+                                                 StepSave *sv)
 {
     const double h = I.h, mu = I.mu, th = I.th, k1m = I.k1m, k1t = I.k1t, k1v = I.k1v;
     double rth = I.rth;
@@ -478,7 +525,9 @@ __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const Ste
         const double th__ = fma(h * (ANEW), so.kt, fma(h, pt__, th));                                      \
         const double As__ = fma(ih * (ANEW), so.d0, fma(ih, pm__, A0));                                    \
         const double dl__ = -(ih * (ANEW)) * so.c;                                                         \
-        rsf_stage_fast(cc, fs__, As__, dl__, th__, cc.kV * Lp[(IDX) * ls], rth, so, bad);                  \
+        const bool ok__ = rsf_stage_fast<RB>(cc, fs__, As__, dl__, th__,                                       \
+                       RB ? kVb * (Lp[(IDX) * ls] - Lc) : cc.kV * Lp[(IDX) * ls], rth, so, bad);           \
+        if (RB) first_bad |= (ok__ ? 0 : 1) << (IDX);      /* bit IDX: stage IDX + 2 outside the ranges */    \
     }
     // stage 2: the "stage in flight" is k1 itself (complete: no damping split)
     so.kt = k1t; so.d0 = k1m; so.c = 0.0;
@@ -488,27 +537,34 @@ __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const Ste
     k3m = so.km; k3t = so.kt;
     RSFM_STAGE(2, TB.a41 * k1t, TB.a41 * k1m, TB.a43);
     k4m = so.km; k4t = so.kt;
+    if (RB) { sv->km[0] = k4m; sv->kt[0] = k4t; }
     RSFM_STAGE(3, TB.a51 * k1t + TB.a53 * k3t, TB.a51 * k1m + TB.a53 * k3m, TB.a54);
     k5m = so.km; k5t = so.kt;
+    if (RB) { sv->km[1] = k5m; sv->kt[1] = k5t; }
     RSFM_STAGE(4, TB.a61 * k1t + TB.a64 * k4t, TB.a61 * k1m + TB.a64 * k4m, TB.a65);
     k6m = so.km; k6t = so.kt;
     bV = TB.b1 * k1v + TB.b6 * so.kv;
     eV = TB.e1 * k1v + TB.e6 * so.kv;
+    if (RB) { sv->km[2] = k6m; sv->kt[2] = k6t; sv->kv[0] = so.kv; }
     RSFM_STAGE(5, TB.a71 * k1t + TB.a74 * k4t + TB.a75 * k5t, TB.a71 * k1m + TB.a74 * k4m + TB.a75 * k5m, TB.a76);
     k7m = so.km; k7t = so.kt;
     bV += TB.b7 * so.kv; eV += TB.e7 * so.kv;
+    if (RB) { sv->km[3] = k7m; sv->kt[3] = k7t; sv->kv[1] = so.kv; }
     RSFM_STAGE(6, TB.a81 * k1t + TB.a84 * k4t + TB.a85 * k5t + TB.a86 * k6t,
                TB.a81 * k1m + TB.a84 * k4m + TB.a85 * k5m + TB.a86 * k6m, TB.a87);
     k8m = so.km; k8t = so.kt;
     bV += TB.b8 * so.kv; eV += TB.e8 * so.kv;
+    if (RB) { sv->km[4] = k8m; sv->kt[4] = k8t; sv->kv[2] = so.kv; }
     RSFM_STAGE(7, TB.a91 * k1t + TB.a94 * k4t + TB.a95 * k5t + TB.a96 * k6t + TB.a97 * k7t,
                TB.a91 * k1m + TB.a94 * k4m + TB.a95 * k5m + TB.a96 * k6m + TB.a97 * k7m, TB.a98);
     k9m = so.km; k9t = so.kt; k9v = so.kv;
     bV += TB.b9 * k9v; eV += TB.e9 * k9v;
+    if (RB) { sv->km[5] = k9m; sv->kt[5] = k9t; sv->kv[3] = k9v; }
     RSFM_STAGE(8, TB.a101 * k1t + TB.a104 * k4t + TB.a105 * k5t + TB.a106 * k6t + TB.a107 * k7t + TB.a108 * k8t,
                TB.a101 * k1m + TB.a104 * k4m + TB.a105 * k5m + TB.a106 * k6m + TB.a107 * k7m + TB.a108 * k8m, TB.a109);
     k10m = so.km; k10t = so.kt;
     bV += TB.b10 * so.kv; eV += TB.e10 * so.kv;
+    if (RB) { sv->km[6] = k10m; sv->kt[6] = k10t; sv->kv[4] = so.kv; }
     // stage 11 -> k2 slot
     RSFM_STAGE(9,
                TB.a111 * k1t + TB.a114 * k4t + TB.a115 * k5t + TB.a116 * k6t + TB.a117 * k7t + TB.a118 * k8t + TB.a119 * k9t,
@@ -516,6 +572,7 @@ __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const Ste
                TB.a1110);
     k2m = so.km; k2t = so.kt;
     bV += TB.b11 * so.kv; eV += TB.e11 * so.kv;
+    if (RB) { sv->km[7] = k2m; sv->kt[7] = k2t; sv->kv[5] = so.kv; }
     // stage 12 -> k3 slot, at x + h
     const double L12 = Lp[10 * ls];
     RSFM_STAGE(10,
@@ -551,12 +608,69 @@ __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const Ste
     O.rth = rth;
 }
 
-// out-of-line general-range step (one copy; taken only when a fast range condition failed)
+// Re-based copy of the chain constants: reference velocity lam V_ref, mu_ref' = mu_ref_r (see rsf_solve_mode).
+// lam = 1 reproduces the constants bit for bit.
+__device__ __forceinline__ ChainConst rebase_const(const ChainConst &c, double lam, double mu_ref_r)
+{
+    ChainConst r = c;
+    r.w = c.w * lam; r.kV = c.kV * lam; r.voa0 = c.voa0 * lam; r.mu_ref = mu_ref_r;
+    return r;
+}
+
+// out-of-line general-range step (one copy; taken only when a fast range condition failed).  The base
+// constants are passed by address and re-based inside, so that the caller keeps no second copy in memory.
+__device__ __noinline__ void dop853_step_general(const ChainConst *cc, double lam, double mu_ref_r, const StepIn *I,
+                                                 const double *Lp, int ls, double Lc, double rl, int first,
+                                                 const StepSave *sv, StepOut *O)
+{
+    const ChainConst cr = rebase_const(*cc, lam, mu_ref_r);
+    dop853_step_impl(cr, *I, Lp, ls, Lc, rl, first, *sv, *O);
+}
+
+// out-of-line fast step in a re-based frame, for the step loop (one copy, so that the only inlined fast step
+// is the one of the fast interval and the hot path keeps its register budget).  Returns the first stage
+// whose arguments left the fast ranges, 0 if none did (then *O is the step).
+__device__ __forceinline__ int dop853_step_fast_rb(const ChainConst *cc, double lam, double mu_ref_r, const StepIn *I,
+                                                const double *Lp, int ls, double Lc, StepOut *O, StepSave *sv)
+{
+    const ChainConst cr = rebase_const(*cc, lam, mu_ref_r);
+    bool bad = false;
+    int first_bad = 0;
+    dop853_step_fast<true>(cr, *I, Lp, ls, cc->kV, Lc, *O, bad, first_bad, sv);
+    return first_bad ? __ffs(first_bad) + 1 : 0;          // stage mask -> first offending stage
+}
+
+__device__ __noinline__ void rsf_rhs_general(const ChainConst *c, double lam, double mu_ref_r, double L, double mu,
+                                             double th, double *res)
+{
+    bool unused = false;
+    double rth = 0.0;
+    const ChainConst cr = rebase_const(*c, lam, mu_ref_r);
+    rsf_rhs<false>(cr, L, mu, th, rth, res[0], res[1], res[2], unused);
+    res[3] = rth;
+}
+
+// single evaluation with fallback (start value, hinit probe, FSAL).  c = the (possibly re-based) constants
+// the fast evaluation uses; c0, lam, mu_ref_r = what they were re-based from; L is relative to c's frame.
+__device__ __forceinline__ void rsf_rhs_checked(const ChainConst &c, const ChainConst &c0, double lam, double mu_ref_r,
+                                                double L, double mu, double th, double &rth, double &dmu, double &dth,
+                                                double &dV)
+{
+    bool bad = false;
+    rsf_rhs<true>(c, L, mu, th, rth, dmu, dth, dV, bad);
+    if (bad) {
+        double res[4];
+        rsf_rhs_general(&c0, lam, mu_ref_r, L, mu, th, res);
+        dmu = res[0]; dth = res[1]; dV = res[2]; rth = res[3];
+    }
+}
+
+// Plain (un-re-based) forms with the short signatures the non-VSTEP solver uses.
 __device__ __noinline__ void dop853_step_general(const ChainConst *cc, const StepIn *I, const double *Lp, int ls,
                                                  StepOut *O)
 {
-    bool unused = false;
-    dop853_step_impl<false>(*cc, *I, Lp, ls, *O, unused);
+    StepSave none;
+    dop853_step_impl(*cc, *I, Lp, ls, 0.0, 1.0, 2, none, *O);
 }
 
 __device__ __noinline__ void rsf_rhs_general(const ChainConst *c, double L, double mu, double th, double *res)
@@ -567,7 +681,6 @@ __device__ __noinline__ void rsf_rhs_general(const ChainConst *c, double L, doub
     res[3] = rth;
 }
 
-// single evaluation with fallback (start value, hinit probe, FSAL)
 __device__ __forceinline__ void rsf_rhs_checked(const ChainConst &c, double L, double mu, double th, double &rth,
                                                 double &dmu, double &dth, double &dV)
 {
@@ -579,6 +692,31 @@ __device__ __forceinline__ void rsf_rhs_checked(const ChainConst &c, double L, d
         dmu = res[0]; dth = res[1]; dV = res[2]; rth = res[3];
     }
 }
+
+__device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const StepIn &I, const double *Lp, int ls,
+                                                 StepOut &O, bool &bad)
+{
+    int fb_unused = 0;
+    dop853_step_fast<false>(cc, I, Lp, ls, cc.kV, 0.0, O, bad, fb_unused, nullptr);
+}
+
+#ifdef RSFM_DEBUG_COUNT
+// tuning builds only (profiles/microbench/stiff_paths.py): where the step loop spends its trips
+__device__ unsigned long long g_dbg[16];
+#define RSFM_DBG(i, pred)                                                                  \
+    {                                                                                      \
+        const unsigned m__ = __ballot_sync(FULL_MASK, (pred));                             \
+        if ((threadIdx.x & 31) == 0 && m__) atomicAdd(&g_dbg[i], (unsigned long long)__popc(m__)); \
+    }
+#define RSFM_DBGW(i, pred)                                                                 \
+    {                                                                                      \
+        const unsigned m__ = __ballot_sync(FULL_MASK, (pred));                             \
+        if ((threadIdx.x & 31) == 0 && m__) atomicAdd(&g_dbg[i], 1ull);                    \
+    }
+#else
+#define RSFM_DBG(i, pred)
+#define RSFM_DBGW(i, pred)
+#endif
 
 struct SolveOut {
     double sse;
@@ -602,6 +740,217 @@ struct LoadScratch {
                         // stiff regime every chain walks exactly this grid, so no exp/sin is evaluated in the solve.
 };
 
+// Per-lane solver state that crosses an output-interval boundary (what rsf_interval_general reads and updates).
+struct IvState {
+    double t, mu, th, V, rth, k1m, k1t, k1v, h_carry, tab_t, tab_h;
+    int status, failed;
+    uint32_t nrhs, nstep;
+};
+
+// One output interval on the general path: hinit + the dp86co step loop (everything the fast interval of
+// rsf_solve_mode cannot do in one verified block: the start-up interval, the stiff regime, rejected steps,
+// arguments outside the fast ranges).  Out of line on purpose: the fast interval is the hot path of every
+// non-stiff configuration and keeps the kernel's register budget and instruction schedule to itself; this
+// function is compiled with its own.  All 32 lanes of the warp call it together.
+template <bool PARITY>
+__device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const ChainConst *ccp, IvState *S, double *wtab,
+                                                  double *ptab, int k, int running_i)
+{
+    const ModelK &M = *Mp;
+    const ChainConst &cc = *ccp;
+    constexpr bool parity = PARITY;
+    const int lane = threadIdx.x & 31;
+    const int nthr = blockDim.x;
+    const double uround = 2.3e-16, safe = 0.9;
+    const double facc1 = 1.0 / 0.3, facc2 = 1.0 / 6.0;
+    // Re-basing (VSTEP loading).  The friction law is invariant under a change of reference velocity:
+    // with V_ref' = lam V_ref and mu_ref' = mu_ref + (a - b) ln lam it reads the same in (mu, theta, v), so
+    // the RHS may be evaluated relative to the level the load point currently moves at, lam = 1 + L(t):
+    //     w' = lam w,  k'V_ref' = lam kV,  V_ref'/a = lam voa0,  1 + L' = (1 + L)/lam  =>  L' = (L - Lc)/lam.
+    // Around the sliding steady state OF THAT LEVEL (v = lam V_ref, theta = Dc/(lam V_ref)) f' and A' are small,
+    // so the short series of the fast step hold there too.  Without it every step of a raised-velocity
+    // period (f = 1/lam - 1 = -0.9 at cfg 4) runs the general-range step (libdevice log / exp, division).
+    // The base is chosen per output interval from L at its start; a load that switches inside the
+    // interval simply shows up as L' != 0 (any L' is valid; the range flags still guard the series).
+    const bool vstep = M.loading == RSFM_LOAD_VSTEP && M.vstep_factor != 1.0;
+    double t = S->t, mu = S->mu, th = S->th, V = S->V, rth = S->rth, k1m = S->k1m, k1t = S->k1t, k1v = S->k1v;
+    double h_carry = S->h_carry, tab_t = S->tab_t, tab_h = S->tab_h;
+    struct { int status; uint32_t nrhs, nstep; } out = {S->status, S->nrhs, S->nstep};
+    bool failed = S->failed != 0;
+    const bool running = running_i != 0;
+    const double xend = t + M.delta_t;                         // :382
+    const double hmax = fabs(xend - t);
+    int nstep_call = 0;
+    bool reject = false, last = false;
+    double h;
+    // Key (tab_t, tab_h) of the warp's shared table.  It is rebuilt when some lane misses and at
+    // least two lanes would share the new key (always, outside the stiff regime).
+    auto ensure_table = [&](bool want, double hk) {
+        const bool miss = want && !(t == tab_t && hk == tab_h);
+        const unsigned mm = __ballot_sync(FULL_MASK, miss);
+        if (mm != 0) {
+            const int src = __ffs(mm) - 1;
+            const double nt = __shfl_sync(FULL_MASK, t, src), nh = __shfl_sync(FULL_MASK, hk, src);
+            const unsigned share = __ballot_sync(FULL_MASK, want && t == nt && hk == nh);
+            if (__popc(share) >= 2) {
+                tab_t = nt; tab_h = nh;
+                __syncwarp();                                      // readers of the old table are done
+                if (lane < 11) wtab[lane] = loading_of(M, __dadd_rn(nt, __dmul_rn(TB.c[lane], nh)));
+                __syncwarp();
+            }
+        }
+    };
+
+    double Lc = 0.0, rl = 1.0, lam = 1.0, mu_ref_r = cc.mu_ref;
+    if (vstep && loading_of(M, t) == M.vstep_factor - 1.0) {
+        Lc = M.vstep_factor - 1.0; rl = M.vstep_rfac; lam = M.vstep_factor;
+        mu_ref_r = fma(1.0 / cc.inv_a - cc.b, M.vstep_lnf, cc.mu_ref);     // (a - b) ln lam: a, b not kept live
+    }
+    const ChainConst cr = rebase_const(cc, lam, mu_ref_r);
+    if (parity || k == 1) {
+        // ---- HINIT (dop853.f, iord = 8).  The common outcome h0 = h = hmax is recognised by
+        // comparisons in the squared / 16th-power domain, without sqrt or division. ----
+        // Norms over the common denominator D = (sk0 sk1 sk2)^2:  ||f/sk||^2 = Nf/D etc.
+        const double k0 = M.atol + M.rtol * fabs(mu), k1 = M.atol + M.rtol * fabs(th), k2 = M.atol + M.rtol * fabs(V);
+        const double p0 = k1 * k2, p1 = k0 * k2, p2 = k0 * k1;
+        const double dd = k0 * p0, D = dd * dd;
+        const double Nf = (k1m * p0) * (k1m * p0) + (k1t * p1) * (k1t * p1) + (k1v * p2) * (k1v * p2);
+        const double Ny = (mu * p0) * (mu * p0) + (th * p1) * (th * p1) + (V * p2) * (V * p2);
+        // h0 = min(0.01 sqrt(dny/dnf), hmax)  (1e-6 when either norm^2 <= 1e-10)
+        const bool tiny = (Nf <= 1e-10 * D) || (Ny <= 1e-10 * D);
+        const bool h0max = !tiny && (Ny >= Nf * (1.0e4 * hmax * hmax));
+        double h0 = hmax;
+        if (!h0max) h0 = tiny ? fmin(1.0e-6, hmax) : fmin(sqrt(Ny / Nf) * 0.01, hmax);
+        // the probe point t + h0 is stage 12 of the step (t, hmax): speculate on that table
+        ensure_table(running, hmax);
+        double Lp = wtab[10];
+        if (running && !(t == tab_t && h0 == tab_h)) Lp = loading_of(M, t + h0);
+        double f1m, f1t, f1v, rprobe = rth;
+        rsf_rhs_checked(cr, cc, lam, mu_ref_r, (Lp - Lc) * rl, mu + h0 * k1m, th + h0 * k1t, rprobe, f1m, f1t, f1v);
+        if (running) out.nrhs++;
+        const double e0 = (f1m - k1m) * p0, e1 = (f1t - k1t) * p1, e2 = (f1v - k1v) * p2;
+        const double Ne = e0 * e0 + e1 * e1 + e2 * e2;                      // ||(f1-f0)/sk||^2 = Ne/D
+        // h = min(100 h0, (0.01/der12)^(1/8), hmax) with der12^2 = max(Ne/(D h0^2), Nf/D).
+        // (0.01/der12)^(1/8) >= hmax  <=>  der12^2 hmax^16 <= 1e-4: decided without sqrt / division
+        const double hm2 = hmax * hmax, hm4 = hm2 * hm2, hm8 = hm4 * hm4, hm16 = hm8 * hm8;
+        const double lim = 1.0e-4 * D;
+        if (h0max && Ne * hm16 <= lim * hm2 && Nf * hm16 <= lim && fmax(Ne, Nf * hm2) > 1e-30 * D * hm2) {
+            h = hmax;
+        } else {
+            const double d12sq = fmax(Ne / (D * h0 * h0), Nf / D);
+            double h1;
+            if (d12sq <= 1e-30) h1 = fmax(1.0e-6, fabs(h0) * 1.0e-3);
+            else h1 = root8(0.01 / sqrt(d12sq));
+            h = fmin(fmin(100.0 * fabs(h0), h1), hmax);
+        }
+    } else {
+        h = fmin(h_carry, hmax);
+    }
+
+    // ---- dp86co step loop: every iteration is one attempted step of all unfinished lanes ----
+    bool done = !running;
+    for (;;) {
+        if (!done) {
+            if (nstep_call > M.nmax) { failed = true; done = true; out.status = RSFM_CHAIN_NMAX; }
+            else if (0.1 * fabs(h) <= fabs(t) * uround) { failed = true; done = true; out.status = RSFM_CHAIN_HSMALL; }
+            else {
+                if ((t + 1.01 * h - xend) > 0.0) { h = xend - t; last = true; }
+                nstep_call++;
+            }
+        }
+        if (__ballot_sync(FULL_MASK, !done) == 0) break;
+        const bool stepping = !done;
+        ensure_table(stepping, h);
+        const bool hit = (t == tab_t && h == tab_h);
+        if (stepping && !hit) {
+            // private stage values (this lane is not on the warp's (t, h)).  A piecewise-constant load
+            // that does not switch between t and t + h has one value for the whole step.
+            bool flat = false;
+            double La = 0.0;
+            if (M.loading == RSFM_LOAD_VSTEP) {
+                const double ia = vstep_index(M, t), ib = vstep_index(M, t + h);
+                flat = ia == ib;
+                La = ((long long)ia & 1) ? M.vstep_factor - 1.0 : 0.0;
+            }
+            if (flat) {
+#pragma unroll
+                for (int i = 0; i < 11; i++) ptab[i * nthr] = La;
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < 11; i++) ptab[i * nthr] = loading_of(M, __dadd_rn(t, __dmul_rn(TB.c[i], h)));
+            }
+        }
+        const double *Lsrc = hit ? wtab : ptab;
+        const int lstride = hit ? 1 : nthr;
+
+        StepIn in;
+        in.h = h; in.mu = mu; in.th = th; in.V = V; in.k1m = k1m; in.k1t = k1t; in.k1v = k1v; in.rth = rth;
+        in.atol = M.atol; in.rtol = M.rtol;
+        StepOut so;
+        bool bad = false;
+        // The fast step is tried when some stepping lane STARTS inside the fast ranges (with a margin).
+        // A step that starts inside and leaves them at a late stage (the trial step the controller grew
+        // past the stability limit) says nothing about the state: the next one is tried again.
+        const double f0s = fma(cr.w, th, -1.0), A0s = (mu - cr.mu_ref) * cr.inv_a;
+        const bool start_in = fabs(f0s) * cr.qscale < 0.5 * 0.001953125 && fabs(A0s) < 0.5 * 0.015625;
+        const bool try_fast = __any_sync(FULL_MASK, stepping && start_in);
+        int first_bad = 0;
+        StepSave sv;
+        if (try_fast) first_bad = dop853_step_fast_rb(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, &so, &sv);
+        else first_bad = 2;
+        bad = first_bad != 0;
+        if (first_bad < 6) first_bad = 2;
+        if (stepping && bad)
+            dop853_step_general(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, rl, first_bad, &sv, &so);
+        RSFM_DBG(0, stepping) RSFM_DBG(1, stepping && try_fast) RSFM_DBG(2, stepping && bad)
+        RSFM_DBGW(3, stepping) RSFM_DBGW(4, stepping && bad) RSFM_DBGW(5, stepping && try_fast)
+        RSFM_DBG(8, stepping && lam != 1.0) RSFM_DBG(9, stepping && bad && first_bad > 2)
+        // err <= 1   <=>   h^2 errA^2 <= den3   (no sqrt, no division; NaN rejects; 0 <= 0 accepts).
+        // errA < 1e140 keeps the squares finite: an unstable step whose error norm overflows must be
+        // rejected (dop853.f gets inf * 0 = NaN there), not pass as inf <= inf.
+        const bool accept = so.errA < 1e140 && (h * h) * (so.errA * so.errA) <= so.den3;
+
+        RSFM_DBG(6, stepping && accept) RSFM_DBG(10, stepping && !accept && bad)
+        if (stepping) {
+            out.nstep++;
+            out.nrhs += 11;
+            if (accept) {
+                // FSAL: f(x + h, y_new) is k1 of the next step and of the next interval's restart
+                rth = so.rth;
+                rsf_rhs_checked(cr, cc, lam, mu_ref_r, (so.L12 - Lc) * rl, so.muN, so.thN, rth, k1m, k1t, k1v);
+                out.nrhs++;
+                const double hold = h;
+                mu = so.muN; th = so.thN; V = so.VN; t = t + h;
+                // the controller's h_new is only consumed when the step does not end the
+                // interval, or when the step size is carried across output points
+                // (h_new = h / max(1/6, min(1/0.3, err^(1/8)/0.9)) >= h when err <= 0.9^8; with h = hmax it is
+                //  clamped back to hmax, so the 8th root is skipped)
+                const bool keeps_hmax = (hold == hmax) && !reject &&
+                                        (hold * hold) * (so.errA * so.errA) <= 0.185302018885184 * so.den3;
+                if ((!last || !parity) && !keeps_hmax) {
+                    const double err = so.den3 > 0.0 ? fabs(hold) * so.errA / sqrt(so.den3) : 0.0;
+                    const double fac = fmax(facc2, fmin(facc1, root8(err) / safe));
+                    double hnew = hold / fac;
+                    if (fabs(hnew) > hmax) hnew = hmax;
+                    if (reject) hnew = fmin(fabs(hnew), fabs(hold));
+                    h = hnew;
+                }
+                reject = false;
+                if (last) { done = true; h_carry = h; }
+            } else {
+                // rejected (also NaN).  SciPy 1.18.1's dop853 shrinks by exactly 1/facc1 here.
+                h = h / facc1;
+                reject = true;
+                last = false;
+            }
+        }
+    }
+
+    S->t = t; S->mu = mu; S->th = th; S->V = V; S->rth = rth; S->k1m = k1m; S->k1t = k1t; S->k1v = k1v;
+    S->h_carry = h_carry; S->tab_t = tab_t; S->tab_h = tab_h;
+    S->status = out.status; S->nrhs = out.nrhs; S->nstep = out.nstep; S->failed = failed ? 1 : 0;
+}
+
 // Integrate one chain over the whole output grid.  All 32 lanes of a warp must call this together
 // (it contains warp collectives) and all threads of a block must call it together when
 // `series.g != nullptr` (block barriers at tile boundaries).  `active` = this lane owns a chain.
@@ -613,7 +962,7 @@ struct LoadScratch {
 // first); the lane stops integrating there (`out.status |= RSFM_CHAIN_EARLY`, sse = partial > limit).
 // The accept/reject decision is exactly the one the full solve would give.  A warp leaves the
 // output loop when all its lanes are finished (resident series only: no block barriers pending).
-template <bool PARITY>
+template <bool PARITY, bool VS>
 __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, double b, double dc, bool active,
                                                     SeriesStage &series, const LoadScratch &ls, double *acc_out,
                                                     const double *acc_ref, size_t acc_stride, double fd_den,
@@ -762,12 +1111,27 @@ __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, do
                         h_carry = hmax;
                     }
                     fast_done = true;
+                    RSFM_DBGW(7, running)
                 } else {
                     fast_resume = k + 8;       // back off: this warp is (partly) off the nominal regime
                 }
             }
         }
 
+        if constexpr (VS) {
+        if (!fast_done) {
+            IvState S;
+            S.t = t; S.mu = mu; S.th = th; S.V = V; S.rth = rth; S.k1m = k1m; S.k1t = k1t; S.k1v = k1v;
+            S.h_carry = h_carry; S.tab_t = tab_t; S.tab_h = tab_h;
+            S.status = out.status; S.nrhs = out.nrhs; S.nstep = out.nstep; S.failed = failed ? 1 : 0;
+            rsf_interval_general<PARITY>(&M, &cc, &S, wtab, ptab, k, running ? 1 : 0);
+            t = S.t; mu = S.mu; th = S.th; V = S.V; rth = S.rth; k1m = S.k1m; k1t = S.k1t; k1v = S.k1v;
+            h_carry = S.h_carry; tab_t = S.tab_t; tab_h = S.tab_h;
+            out.status = S.status; out.nrhs = S.nrhs; out.nstep = S.nstep; failed = S.failed != 0;
+        }
+        (void)nstep_call; (void)reject; (void)last; (void)h; (void)was_bad; (void)stiff_steps; (void)nthr; (void)safe; (void)facc1; (void)facc2;
+        (void)ensure_table;
+        } else {
         if (!fast_done) {
         if (parity || k == 1) {
             // ---- HINIT (dop853.f, iord = 8).  The common outcome h0 = h = hmax is recognised by
@@ -892,6 +1256,7 @@ __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, do
             }
         }
         }   // !fast_done
+        }
 
         // ---- output point k: RateStateModel.py:384-388, MCMC.py:387 ----
         double accv = 0.0;
@@ -917,6 +1282,7 @@ __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, do
 }
 
 // integration mode is a kernel-uniform run-time choice; each mode is its own instantiation
+template <bool VS>
 __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double b, double dc, bool active,
                                                SeriesStage &series, const LoadScratch &ls, double *acc_out,
                                                const double *acc_ref, size_t acc_stride, double fd_den,
@@ -924,9 +1290,9 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
                                                double sse_limit = INFINITY)
 {
     if (M.integ_mode == RSFM_INTEG_PARITY)
-        return rsf_solve_mode<true>(M, a, b, dc, active, series, ls, acc_out, acc_ref, acc_stride, fd_den, xtx_out, t_out,
+        return rsf_solve_mode<true, VS>(M, a, b, dc, active, series, ls, acc_out, acc_ref, acc_stride, fd_den, xtx_out, t_out,
                                     sse_limit);
-    return rsf_solve_mode<false>(M, a, b, dc, active, series, ls, acc_out, acc_ref, acc_stride, fd_den, xtx_out, t_out,
+    return rsf_solve_mode<false, VS>(M, a, b, dc, active, series, ls, acc_out, acc_ref, acc_stride, fd_den, xtx_out, t_out,
                                  sse_limit);
 }
 

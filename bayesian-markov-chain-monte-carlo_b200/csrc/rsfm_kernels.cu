@@ -104,6 +104,8 @@ static int check_cfg(const rsfm_cfg *c)
         return set_err(RSFM_ERR_INVALID, "bad integ_mode%s", "");
     if (c->loading == RSFM_LOAD_VSTEP && !(c->vstep_period > 0.0))
         return set_err(RSFM_ERR_INVALID, "vstep_period must be positive%s", "");
+    if (c->loading == RSFM_LOAD_VSTEP && !(c->vstep_factor > 0.0))
+        return set_err(RSFM_ERR_INVALID, "vstep_factor must be positive%s", "");
     if (!(c->rtol > 0.0) || !(c->atol >= 0.0)) return set_err(RSFM_ERR_INVALID, "rtol must be positive and atol non-negative%s", "");
     if (!(c->a > 0.0) || !(c->V_ref > 0.0)) return set_err(RSFM_ERR_INVALID, "a and V_ref must be positive%s", "");
     if (c->adapt_interval < 2 || c->adapt_interval > 64) return set_err(RSFM_ERR_INVALID, "adapt_interval must be in [2, 64]%s", "");
@@ -119,7 +121,21 @@ static ModelK make_model(const rsfm_cfg *c)
     M.rtol = c->rtol; M.atol = c->atol; M.vstep_period = c->vstep_period; M.vstep_factor = c->vstep_factor;
     M.n_out = c->n_out; M.nmax = c->nmax; M.damping = c->radiation_damping; M.loading = c->loading;
     M.integ_mode = c->integ_mode;
+    M.vstep_lnf = (c->loading == RSFM_LOAD_VSTEP) ? log(c->vstep_factor) : 0.0;
+    M.vstep_rfac = (c->loading == RSFM_LOAD_VSTEP) ? 1.0 / c->vstep_factor : 1.0;
+    M.vstep_rper = (c->loading == RSFM_LOAD_VSTEP) ? 1.0 / c->vstep_period : 1.0;
     return M;
+}
+
+// Which instantiation of the solver runs: the kernels exist twice.  VS = false keeps the general
+// (state-by-state) interval path inline exactly as the non-stiff configurations were tuned with it; VS = true
+// calls the out-of-line rsf_interval_general, which re-bases the friction law on the current load level and
+// resumes the general-range step from the first stage that left the fast ranges -- the variant for
+// velocity-step loading (cfg 4), where nearly every interval is a general one.  RSFM_STIFF=0/1 overrides.
+static bool stiff_variant(const ModelK &M)
+{
+    if (const char *e = getenv("RSFM_STIFF")) return atoi(e) != 0;       // tuning / experiments only
+    return M.loading == RSFM_LOAD_VSTEP;
 }
 
 // chains per block: small batches are spread over more SMs (the kernel is latency
@@ -303,9 +319,9 @@ extern "C" int rsfm_trim(void)
 // ---------------------------------------------------------------------------
 // MB = resident blocks per SM the register budget is sized for: 3 (<= 168 registers) pays at saturating
 // batch sizes (+5 %), 1 (no cap) is 8 % faster when the batch is small and the kernel latency-bound.
-template <int MB>
-__global__ void __launch_bounds__(128, MB)
-rsf_forward_kernel(ModelK M, int C, double a0, double b0, const double *__restrict__ dc_in,
+template <int MB, bool VS>
+__global__ void __launch_bounds__(128, VS ? 1 : MB)
+rsf_forward_kernel(const __grid_constant__ ModelK M, int C, double a0, double b0, const double *__restrict__ dc_in,
                    const double *__restrict__ a_in, const double *__restrict__ b_in,
                    const double *__restrict__ data, double *__restrict__ acc_out,
                    double *__restrict__ t_out, double *__restrict__ sse_out, int32_t *__restrict__ status_out,
@@ -327,7 +343,7 @@ rsf_forward_kernel(ModelK M, int C, double a0, double b0, const double *__restri
     SeriesStage series;
     series.begin(s_tile, s_bar, data, M.n_out);
     series.start_solve();
-    SolveOut o = rsf_solve(M, a, b, dc, active, series, lscr, acc_out ? acc_out + cc : nullptr, nullptr, (size_t)C,
+    SolveOut o = rsf_solve<VS>(M, a, b, dc, active, series, lscr, acc_out ? acc_out + cc : nullptr, nullptr, (size_t)C,
                            1.0, nullptr, t_out ? t_out + cc : nullptr);
     if (active) {
         if (sse_out) sse_out[c] = o.sse;
@@ -356,14 +372,14 @@ extern "C" int rsfm_forward_batch(const rsfm_cfg *cfg, int32_t C, const double *
     const double *nom = nullptr;
     rc = get_nominal_table(M, (cudaStream_t)stream, &nom);
     if (rc) return rc;
-    if (C <= 148 * 4 * 32 * 2)
-        rsf_forward_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(
-            M, C, cfg->a, cfg->b, dc_dev, a_dev, b_dev, sse_out_dev ? data_dev : nullptr, acc_out_dev, t_out_dev,
-            sse_out_dev, status_dev, filled_dev, (unsigned long long *)nrhs_dev, (unsigned long long *)nstep_dev, nom);
-    else
-        rsf_forward_kernel<3><<<grid, block, 0, (cudaStream_t)stream>>>(
-            M, C, cfg->a, cfg->b, dc_dev, a_dev, b_dev, sse_out_dev ? data_dev : nullptr, acc_out_dev, t_out_dev,
-            sse_out_dev, status_dev, filled_dev, (unsigned long long *)nrhs_dev, (unsigned long long *)nstep_dev, nom);
+    const bool vs = stiff_variant(M);
+#define RSFM_FWD(MB, VS)                                                                                              \
+    rsf_forward_kernel<MB, VS><<<grid, block, 0, (cudaStream_t)stream>>>(                                            \
+        M, C, cfg->a, cfg->b, dc_dev, a_dev, b_dev, sse_out_dev ? data_dev : nullptr, acc_out_dev, t_out_dev,         \
+        sse_out_dev, status_dev, filled_dev, (unsigned long long *)nrhs_dev, (unsigned long long *)nstep_dev, nom)
+    if (C <= 148 * 4 * 32 * 2) { if (vs) RSFM_FWD(1, true); else RSFM_FWD(1, false); }
+    else { if (vs) RSFM_FWD(3, true); else RSFM_FWD(3, false); }
+#undef RSFM_FWD
     CUDA_TRY(cudaGetLastError());
     return RSFM_OK;
 }
@@ -474,9 +490,9 @@ extern "C" int64_t rsfm_iteration(const rsfm_sampler *s) { return s ? s->iterati
 // pass j = 1..d: solve at q0 with parameter j-1 scaled by (1 + 1e-6); accumulates
 //                the column products needed for X'X.  d = 1 keeps everything in
 //                one pass; d = 3 stores the three sensitivity columns.
-template <int D>
+template <int D, bool VS>
 __global__ void __launch_bounds__(128)
-rsf_init_kernel(ModelK M, int C, int pass, double a0, double b0, int n_prior_len, SamplerDev S,
+rsf_init_kernel(const __grid_constant__ ModelK M, int C, int pass, double a0, double b0, int n_prior_len, SamplerDev S,
                 double *__restrict__ scratch /* [(1+ (D>1?D:0))][n_out][C] */)
 {
     __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
@@ -510,7 +526,7 @@ rsf_init_kernel(ModelK M, int C, int pass, double a0, double b0, int n_prior_len
     //   pass j, d = 3   : trajectory -> scratch plane j (combined by rsf_init_finish_kernel)
     double *wr = (pass == 0) ? scratch + cc : (D == 1 ? nullptr : scratch + (size_t)pass * plane + cc);
     const double *rd = (pass > 0 && D == 1) ? scratch + cc : nullptr;
-    SolveOut o = rsf_solve(M, a, b, dc, active, series, lscr, wr, rd, (size_t)C, fd_den, &xtx);
+    SolveOut o = rsf_solve<VS>(M, a, b, dc, active, series, lscr, wr, rd, (size_t)C, fd_den, &xtx);
     if (active) {
         if (pass == 0) {
             S.sse[c] = o.sse;
@@ -611,10 +627,11 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     loading_table_kernel<<<1, 1024, 0, stream>>>(M, s->d.nom);
     CUDA_TRY(cudaGetLastError());
     for (int pass = 0; pass <= d; pass++) {
-        if (d == 1)
-            rsf_init_kernel<1><<<grid, block, 0, stream>>>(M, C, pass, s->cfg.a, s->cfg.b, s->cfg.n_prior_len, s->d, s->scratch);
-        else
-            rsf_init_kernel<3><<<grid, block, 0, stream>>>(M, C, pass, s->cfg.a, s->cfg.b, s->cfg.n_prior_len, s->d, s->scratch);
+#define RSFM_INIT(D, VS)                                                                                              \
+    rsf_init_kernel<D, VS><<<grid, block, 0, stream>>>(M, C, pass, s->cfg.a, s->cfg.b, s->cfg.n_prior_len, s->d, s->scratch)
+        if (d == 1) { if (stiff_variant(M)) RSFM_INIT(1, true); else RSFM_INIT(1, false); }
+        else { if (stiff_variant(M)) RSFM_INIT(3, true); else RSFM_INIT(3, false); }
+#undef RSFM_INIT
         CUDA_TRY(cudaGetLastError());
     }
     if (d == 3) {
@@ -662,9 +679,9 @@ struct RunArgs {
 };
 
 // (128, 3): three resident blocks per SM (<= 168 registers); measured +5 % at saturating sizes
-template <int D, bool DET>
-__global__ void __launch_bounds__(128, 3)
-rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
+template <int D, bool DET, bool VS>
+__global__ void __launch_bounds__(128, VS ? 1 : 3)
+rsf_mcmc_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunArgs A)
 {
     __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -771,7 +788,7 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
             }
             const double sse_limit = solve ? ss - 2.0 * s2 * lnu : INFINITY;
             series.start_solve();
-            SolveOut o = rsf_solve(M, solve ? qn[0] : q[0], solve ? qn[1] : q[1], solve ? qn[2] : q[2], solve, series, lscr,
+            SolveOut o = rsf_solve<VS>(M, solve ? qn[0] : q[0], solve ? qn[1] : q[1], solve ? qn[2] : q[2], solve, series, lscr,
                                    nullptr, nullptr, Cz, 1.0, nullptr, nullptr, sse_limit);
             bool acc = false;
             if (solve) {
@@ -841,7 +858,7 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
             const double pb = (D == 3) ? qn[1] : A.b0;
             const double pdc = solve ? qn[D - 1] : q[D - 1];
             series.start_solve();
-            SolveOut o = rsf_solve(M, solve ? pa : ((D == 3) ? q[0] : A.a0), solve ? pb : ((D == 3) ? q[1] : A.b0), pdc,
+            SolveOut o = rsf_solve<VS>(M, solve ? pa : ((D == 3) ? q[0] : A.a0), solve ? pb : ((D == 3) ? q[1] : A.b0), pdc,
                                    solve, series, lscr, nullptr, nullptr, Cz, 1.0, nullptr, nullptr, sse_limit);
             // ---- accept / reject (MCMC.py:327-331) ----
             bool acc = false;
@@ -957,9 +974,9 @@ rsf_mcmc_kernel(ModelK M, int C, SamplerDev S, RunArgs A)
 // COMPAT = true (d = 1, the reference's dict-prior adaptation): the proposal scale changes after every
 // adapt_interval-th sample, so a round never looks past that boundary; the writer lane keeps the
 // reference's sample ring and hands the new scale to its group when the boundary is reached.
-template <int D, bool COMPAT>
+template <int D, bool COMPAT, bool VS>
 __global__ void __launch_bounds__(128)
-rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
+rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunArgs A, int g)
 {
     __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -1050,7 +1067,7 @@ rsf_mcmc_spec_kernel(ModelK M, int C, SamplerDev S, RunArgs A, int g)
         const double pa = (D == 3) ? qn[0] : A.a0;
         const double pb = (D == 3) ? qn[1] : A.b0;
         series.start_solve();
-        SolveOut o = rsf_solve(M, solve ? pa : A.a0, solve ? pb : A.b0, solve ? qn[D - 1] : q[D - 1], solve, series, lscr,
+        SolveOut o = rsf_solve<VS>(M, solve ? pa : A.a0, solve ? pb : A.b0, solve ? qn[D - 1] : q[D - 1], solve, series, lscr,
                                nullptr, nullptr, Cz, 1.0, nullptr, nullptr, limit);
         // executed work of this lane (speculative or not) is accounted by the writer after a group sum
         unsigned int w_rhs = solve ? o.nrhs : 0u, w_step = solve ? o.nstep : 0u, w_exec = solve ? 1u : 0u;
@@ -1217,21 +1234,27 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
     A.adapt_mode = s->cfg.adapt_mode; A.adapt_interval = s->cfg.adapt_interval;
     const ModelK M = make_model(&s->cfg);
     const int g = pick_spec_depth(s, A);
+    const bool vs = stiff_variant(M);
     if (g >= 2) {
         const long long threads = (long long)C << g;
         const int sblock = threads <= 148 * 32 * 4 ? 32 : 128;
         const int sgrid = (int)((threads + sblock - 1) / sblock);
-        if (s->cfg.n_params == 1 && s->cfg.adapt_mode == RSFM_ADAPT_COMPAT)
-            rsf_mcmc_spec_kernel<1, true><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);
-        else if (s->cfg.n_params == 1) rsf_mcmc_spec_kernel<1, false><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);
-        else rsf_mcmc_spec_kernel<3, false><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);
+#define RSFM_SPEC(D, CO)                                                                                              \
+    { if (vs) rsf_mcmc_spec_kernel<D, CO, true><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);                      \
+      else rsf_mcmc_spec_kernel<D, CO, false><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g); }
+#define RSFM_SEQ(D, DET)                                                                                              \
+    { if (vs) rsf_mcmc_kernel<D, DET, true><<<grid, block, 0, stream>>>(M, C, s->d, A);                               \
+      else rsf_mcmc_kernel<D, DET, false><<<grid, block, 0, stream>>>(M, C, s->d, A); }
+        if (s->cfg.n_params == 1 && s->cfg.adapt_mode == RSFM_ADAPT_COMPAT) RSFM_SPEC(1, true)
+        else if (s->cfg.n_params == 1) RSFM_SPEC(1, false)
+        else RSFM_SPEC(3, false)
     } else if (s->cfg.n_params == 1) {
-        if (A.deterministic) rsf_mcmc_kernel<1, true><<<grid, block, 0, stream>>>(M, C, s->d, A);
-        else rsf_mcmc_kernel<1, false><<<grid, block, 0, stream>>>(M, C, s->d, A);
+        if (A.deterministic) RSFM_SEQ(1, true) else RSFM_SEQ(1, false)
     } else {
-        if (A.deterministic) rsf_mcmc_kernel<3, true><<<grid, block, 0, stream>>>(M, C, s->d, A);
-        else rsf_mcmc_kernel<3, false><<<grid, block, 0, stream>>>(M, C, s->d, A);
+        if (A.deterministic) RSFM_SEQ(3, true) else RSFM_SEQ(3, false)
     }
+#undef RSFM_SPEC
+#undef RSFM_SEQ
     CUDA_TRY(cudaGetLastError());
     s->iteration += A.n_iters;
     if (s->cfg.adapt_mode == RSFM_ADAPT_POOLED) s->suff_count += A.n_iters;
@@ -1533,3 +1556,13 @@ extern "C" int rsfm_measure_fp64_peak(double millis, double *flops_out)
     *flops_out = best;
     return RSFM_OK;
 }
+
+#ifdef RSFM_DEBUG_COUNT
+extern "C" int rsfm_debug_counters(unsigned long long *out16, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, rsfm::g_dbg, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(rsfm::g_dbg, z, sizeof(z)); }
+    return 0;
+}
+#endif
