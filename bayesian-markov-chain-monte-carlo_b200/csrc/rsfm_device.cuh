@@ -220,14 +220,14 @@ __device__ __noinline__ double loading_rel(int loading, double t_start, double p
 
 // Period index floor((t - t_start)/period) of the VSTEP load, as the correctly rounded division gives it.
 // The product with the host-computed reciprocal differs from the rounded quotient by a few ulp at most, so its
-// floor is the same unless the quotient lies within 1e-9 (relative) of an integer; only then is the division done
+// floor is the same unless the quotient lies within 1e-6 of an integer (indices stay far below 1e9); only then is the division done
 // (output times that are multiples of the period: one interval end per period).
 __device__ __forceinline__ double vstep_index(const ModelK &M, double t)
 {
     const double x = t - M.t_start;
     const double q = x * M.vstep_rper;
     const double n = rint(q);
-    if (fabs(q - n) <= 1e-9 * fmax(1.0, fabs(n))) return floor(x / M.vstep_period);
+    if (fabs(q - n) <= 1e-6) return floor(x / M.vstep_period);
     return floor(q);
 }
 
@@ -335,6 +335,28 @@ __device__ __forceinline__ void rsf_rhs(const ChainConst &c, double L, double mu
 }
 
 __device__ __forceinline__ double root8(double x) { return sqrt(sqrt(sqrt(x))); }
+
+// (q/den)^(-1/16) for positive, normal, finite q and den, to ~5e-12 relative: exponents by integer arithmetic,
+// log2 / exp2 of the mantissas on the SFU in single precision (z0, ~2^-21), then one Newton step in double,
+// z = z0 (1 + (1 - (q/den) z0^16)/16), whose small residual only needs the approximate reciprocal of den.
+// Replaces sqrt + division + three sqrt + two divisions (~1,000 dependent cycles) in the step-size controller
+// of the stiff variant by ~200.
+__device__ __forceinline__ double inv_root16(double q, double den)
+{
+    const int hq = __double2hiint(q), hd = __double2hiint(den);
+    const int eq = (hq >> 20) - 1023, ed = (hd >> 20) - 1023;
+    const float mq = (float)__hiloint2double((hq & 0x000fffff) | 0x3ff00000, __double2loint(q));
+    const float md = (float)__hiloint2double((hd & 0x000fffff) | 0x3ff00000, __double2loint(den));
+    const float l = (float)(eq - ed) + (__log2f(mq) - __log2f(md));
+    float z0f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(z0f) : "f"(-0.0625f * l));
+    const double z0 = (double)z0f;
+    const double z2 = z0 * z0, z4 = z2 * z2, z8 = z4 * z4, z16 = z8 * z8;
+    const double r = fma(-q, z16, den);
+    double rc;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
+    return fma(z0, (r * rc) * 0.0625, z0);
+}
 
 // One attempted DOP853 step (stages 2..12, 8th-order solution, error forms).  Lp points at the
 // eleven stage values of L (stride ls doubles, shared memory).
@@ -822,9 +844,14 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         double h0 = hmax;
         if (!h0max) h0 = tiny ? fmin(1.0e-6, hmax) : fmin(sqrt(Ny / Nf) * 0.01, hmax);
         // the probe point t + h0 is stage 12 of the step (t, hmax): speculate on that table
-        ensure_table(running, hmax);
-        double Lp = wtab[10];
-        if (running && !(t == tab_t && h0 == tab_h)) Lp = loading_of(M, t + h0);
+        double Lp;
+        if (M.loading == RSFM_LOAD_VSTEP) {
+            Lp = loading_of(M, t + h0);                   // piecewise constant: nothing to share
+        } else {
+            ensure_table(running, hmax);
+            Lp = wtab[10];
+            if (running && !(t == tab_t && h0 == tab_h)) Lp = loading_of(M, t + h0);
+        }
         double f1m, f1t, f1v, rprobe = rth;
         rsf_rhs_checked(cr, cc, lam, mu_ref_r, (Lp - Lc) * rl, mu + h0 * k1m, th + h0 * k1t, rprobe, f1m, f1t, f1v);
         if (running) out.nrhs++;
@@ -860,8 +887,10 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         }
         if (__ballot_sync(FULL_MASK, !done) == 0) break;
         const bool stepping = !done;
-        ensure_table(stepping, h);
-        const bool hit = (t == tab_t && h == tab_h);
+        const bool pwc = M.loading == RSFM_LOAD_VSTEP;      // piecewise-constant load: no table to share
+        if (!pwc) ensure_table(stepping, h);
+        const bool hit = !pwc && (t == tab_t && h == tab_h);
+        int lstride = hit ? 1 : nthr;
         if (stepping && !hit) {
             // private stage values (this lane is not on the warp's (t, h)).  A piecewise-constant load
             // that does not switch between t and t + h has one value for the whole step.
@@ -873,15 +902,14 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
                 La = ((long long)ia & 1) ? M.vstep_factor - 1.0 : 0.0;
             }
             if (flat) {
-#pragma unroll
-                for (int i = 0; i < 11; i++) ptab[i * nthr] = La;
+                ptab[0] = La;                                 // one value for every stage (stride 0)
+                lstride = 0;
             } else {
 #pragma unroll 1
                 for (int i = 0; i < 11; i++) ptab[i * nthr] = loading_of(M, __dadd_rn(t, __dmul_rn(TB.c[i], h)));
             }
         }
         const double *Lsrc = hit ? wtab : ptab;
-        const int lstride = hit ? 1 : nthr;
 
         StepIn in;
         in.h = h; in.mu = mu; in.th = th; in.V = V; in.k1m = k1m; in.k1t = k1t; in.k1v = k1v; in.rth = rth;
@@ -928,9 +956,18 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
                 const bool keeps_hmax = (hold == hmax) && !reject &&
                                         (hold * hold) * (so.errA * so.errA) <= 0.185302018885184 * so.den3;
                 if ((!last || !parity) && !keeps_hmax) {
-                    const double err = so.den3 > 0.0 ? fabs(hold) * so.errA / sqrt(so.den3) : 0.0;
-                    const double fac = fmax(facc2, fmin(facc1, root8(err) / safe));
-                    double hnew = hold / fac;
+                    // h_new = h g,  g = 1/fac = clamp(0.9 err^(-1/8), 0.3, 6),  err^2 = q/den3  (accepted: err <= 1)
+                    const double q = (hold * hold) * (so.errA * so.errA);
+                    double g;
+                    if (q <= 6.568408355712891e-14 * so.den3) {
+                        g = 6.0;                                   // err <= 0.15^8 (and den3 = 0): growth limit
+                    } else if (q > 1e-290 && so.den3 > 1e-290 && so.den3 < 1e290) {
+                        g = fmin(6.0, fmax(0.3, safe * inv_root16(q, so.den3)));
+                    } else {                                       // out of inv_root16's range: as written in dop853.f
+                        const double err = fabs(hold) * so.errA / sqrt(so.den3);
+                        g = 1.0 / fmax(facc2, fmin(facc1, root8(err) / safe));
+                    }
+                    double hnew = hold * g;
                     if (fabs(hnew) > hmax) hnew = hmax;
                     if (reject) hnew = fmin(fabs(hnew), fabs(hold));
                     h = hnew;

@@ -138,6 +138,12 @@ static bool stiff_variant(const ModelK &M)
     return M.loading == RSFM_LOAD_VSTEP;
 }
 
+// The stiff variant runs one-warp blocks: with a streamed series (cfg 4) the block barriers at tile boundaries
+// would otherwise make every warp of a block wait for the slowest lane of all of them.  (Measured and dropped,
+// profiles/microbench/forward_stiff_r1b.txt: spreading the chains over more, partly empty warps -- the kernel is
+// instruction-fetch bound, a second warp per sub-partition doubles the time -- and a rolled stage loop.)
+static const int STIFF_BLOCK = 32;
+
 // chains per block: small batches are spread over more SMs (the kernel is latency
 // bound there), large batches use 128-thread blocks.
 static int pick_block(int C)
@@ -330,8 +336,8 @@ rsf_forward_kernel(const __grid_constant__ ModelK M, int C, double a0, double b0
 {
     __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ double s_ltab[4 * LTAB_STRIDE];
-    __shared__ double s_lpriv[11 * 128];
+    __shared__ double s_ltab[(VS ? 1 : 4) * LTAB_STRIDE];       // VS kernels run one-warp blocks (STIFF_BLOCK)
+    __shared__ double s_lpriv[11 * (VS ? 32 : 128)];
     LoadScratch lscr;
     lscr.tab = s_ltab; lscr.priv = s_lpriv; lscr.nom = nom;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,12 +379,14 @@ extern "C" int rsfm_forward_batch(const rsfm_cfg *cfg, int32_t C, const double *
     rc = get_nominal_table(M, (cudaStream_t)stream, &nom);
     if (rc) return rc;
     const bool vs = stiff_variant(M);
+    const int vgrid = (C + STIFF_BLOCK - 1) / STIFF_BLOCK;
 #define RSFM_FWD(MB, VS)                                                                                              \
-    rsf_forward_kernel<MB, VS><<<grid, block, 0, (cudaStream_t)stream>>>(                                            \
+    rsf_forward_kernel<MB, VS><<<VS ? vgrid : grid, VS ? STIFF_BLOCK : block, 0, (cudaStream_t)stream>>>(            \
         M, C, cfg->a, cfg->b, dc_dev, a_dev, b_dev, sse_out_dev ? data_dev : nullptr, acc_out_dev, t_out_dev,         \
         sse_out_dev, status_dev, filled_dev, (unsigned long long *)nrhs_dev, (unsigned long long *)nstep_dev, nom)
-    if (C <= 148 * 4 * 32 * 2) { if (vs) RSFM_FWD(1, true); else RSFM_FWD(1, false); }
-    else { if (vs) RSFM_FWD(3, true); else RSFM_FWD(3, false); }
+    if (vs) RSFM_FWD(1, true);
+    else if (C <= 148 * 4 * 32 * 2) RSFM_FWD(1, false);
+    else RSFM_FWD(3, false);
 #undef RSFM_FWD
     CUDA_TRY(cudaGetLastError());
     return RSFM_OK;
@@ -497,8 +505,8 @@ rsf_init_kernel(const __grid_constant__ ModelK M, int C, int pass, double a0, do
 {
     __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ double s_ltab[4 * LTAB_STRIDE];
-    __shared__ double s_lpriv[11 * 128];
+    __shared__ double s_ltab[(VS ? 1 : 4) * LTAB_STRIDE];       // VS kernels run one-warp blocks (STIFF_BLOCK)
+    __shared__ double s_lpriv[11 * (VS ? 32 : 128)];
     LoadScratch lscr;
     lscr.tab = s_ltab; lscr.priv = s_lpriv; lscr.nom = S.nom;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -628,7 +636,8 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     CUDA_TRY(cudaGetLastError());
     for (int pass = 0; pass <= d; pass++) {
 #define RSFM_INIT(D, VS)                                                                                              \
-    rsf_init_kernel<D, VS><<<grid, block, 0, stream>>>(M, C, pass, s->cfg.a, s->cfg.b, s->cfg.n_prior_len, s->d, s->scratch)
+    rsf_init_kernel<D, VS><<<VS ? (C + STIFF_BLOCK - 1) / STIFF_BLOCK : grid, VS ? STIFF_BLOCK : block, 0, stream>>>( \
+        M, C, pass, s->cfg.a, s->cfg.b, s->cfg.n_prior_len, s->d, s->scratch)
         if (d == 1) { if (stiff_variant(M)) RSFM_INIT(1, true); else RSFM_INIT(1, false); }
         else { if (stiff_variant(M)) RSFM_INIT(3, true); else RSFM_INIT(3, false); }
 #undef RSFM_INIT
@@ -685,8 +694,8 @@ rsf_mcmc_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunArgs A
 {
     __shared__ __align__(128) double s_tile[2 * SERIES_TILE];
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ double s_ltab[4 * LTAB_STRIDE];
-    __shared__ double s_lpriv[11 * 128];
+    __shared__ double s_ltab[(VS ? 1 : 4) * LTAB_STRIDE];       // VS kernels run one-warp blocks (STIFF_BLOCK)
+    __shared__ double s_lpriv[11 * (VS ? 32 : 128)];
     LoadScratch lscr;
     lscr.tab = s_ltab; lscr.priv = s_lpriv; lscr.nom = S.nom;
     constexpr int T = D * (D + 1) / 2;
@@ -1243,7 +1252,7 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
     { if (vs) rsf_mcmc_spec_kernel<D, CO, true><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);                      \
       else rsf_mcmc_spec_kernel<D, CO, false><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g); }
 #define RSFM_SEQ(D, DET)                                                                                              \
-    { if (vs) rsf_mcmc_kernel<D, DET, true><<<grid, block, 0, stream>>>(M, C, s->d, A);                               \
+    { if (vs) rsf_mcmc_kernel<D, DET, true><<<(C + STIFF_BLOCK - 1) / STIFF_BLOCK, STIFF_BLOCK, 0, stream>>>(M, C, s->d, A); \
       else rsf_mcmc_kernel<D, DET, false><<<grid, block, 0, stream>>>(M, C, s->d, A); }
         if (s->cfg.n_params == 1 && s->cfg.adapt_mode == RSFM_ADAPT_COMPAT) RSFM_SPEC(1, true)
         else if (s->cfg.n_params == 1) RSFM_SPEC(1, false)
