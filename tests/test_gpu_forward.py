@@ -254,3 +254,39 @@ def test_long_series_is_causal_and_streamed_sse_is_consistent(cuda, pkg):
     assert lo["t"].cpu().numpy()[-1, 0] == t
     # the velocity steps are felt: acceleration spikes right after t = 1000 s
     assert np.max(np.abs(acc_l[10_000:10_020, 2])) > 100 * np.max(np.abs(acc_l[9_900:9_990, 2]))
+
+
+def test_stiff_variant_on_reference_loading_and_both_variants_on_vstep(cuda, pkg, orc, monkeypatch):
+    """The kernels exist in two variants (rsfm_kernels.cu: stiff_variant): the default one and the one used for
+    velocity-step loading, which re-bases the friction law on the current load level, resumes the general-range
+    step from the first stage that left the fast ranges and uses the SFU-seeded controller root.  Forced onto the
+    reference's own loading (RSFM_STIFF=1) it must stay inside the golden-trajectory gate; on a velocity-step
+    problem both variants must agree with the oracle and with each other."""
+    monkeypatch.setenv("RSFM_STIFF", "1")
+    for case in load_golden("forward_trajectories.json")["cases"]:
+        if "filled" in case or not case["RadiationDamping"]:
+            continue
+        m = pkg.RateStateModel(number_time_steps=case["N"], end_time=case.get("end_time", 50.0))
+        m.Dc = case["Dc"]
+        _, acc, _ = m.evaluate()
+        _check(acc, case["acc"], case["Dc"])
+    # velocity steps, stiff and non-stiff chains in one batch
+    n, t_end = 1200, 120.0
+    kw = dict(loading=orc.LOAD_VSTEP, vstep_period=30.0, vstep_factor=10.0)
+    dcs = np.array([0.05, 0.3, 2.0, 40.0, 400.0])
+    m = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
+    m.loading, m.vstep_period, m.vstep_factor = "vstep", 30.0, 10.0
+    _, acc_o, _ = orc.forward_batch(orc.make_model(number_time_steps=n, end_time=t_end, **kw), dcs, want_acc=True)
+    res = {}
+    for v in ("0", "1"):
+        monkeypatch.setenv("RSFM_STIFF", v)
+        o = m.evaluate_batch(dcs)
+        assert np.all(o["status"].cpu().numpy() == 0)
+        res[v] = (o["acc"].t().cpu().numpy(), o["nstep"].cpu().numpy())
+    for i in range(len(dcs)):
+        scale = np.max(np.abs(acc_o[i]))
+        for v in ("0", "1"):
+            assert np.max(np.abs(res[v][0][i] - acc_o[i])) <= 2e-5 * scale, (v, dcs[i])
+        assert np.max(np.abs(res["0"][0][i] - res["1"][0][i])) <= 2e-5 * scale
+    # same controller semantics: attempted-step counts of the two variants differ by well under 1 %
+    assert np.all(np.abs(res["0"][1].astype(float) - res["1"][1]) <= 0.01 * res["0"][1])
