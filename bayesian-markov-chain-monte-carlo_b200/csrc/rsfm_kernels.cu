@@ -1076,7 +1076,9 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
         const double pa = (D == 3) ? qn[0] : A.a0;
         const double pb = (D == 3) ? qn[1] : A.b0;
         series.start_solve();
-        SolveOut o = rsf_solve<VS>(M, solve ? pa : A.a0, solve ? pb : A.b0, solve ? qn[D - 1] : q[D - 1], solve, series, lscr,
+        // ISO: the general interval path out of line (255 registers available here; the 168-register kernels
+        // would spill in the fast interval around the call)
+        SolveOut o = rsf_solve<VS, true>(M, solve ? pa : A.a0, solve ? pb : A.b0, solve ? qn[D - 1] : q[D - 1], solve, series, lscr,
                                nullptr, nullptr, Cz, 1.0, nullptr, nullptr, limit);
         // executed work of this lane (speculative or not) is accounted by the writer after a group sum
         unsigned int w_rhs = solve ? o.nrhs : 0u, w_step = solve ? o.nstep : 0u, w_exec = solve ? 1u : 0u;
