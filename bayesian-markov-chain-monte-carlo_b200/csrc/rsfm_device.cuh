@@ -37,6 +37,7 @@ struct ModelK {
     double rtol, atol, vstep_period, vstep_factor;
     double vstep_lnf, vstep_rfac;      // log(vstep_factor), 1/vstep_factor: host-computed (re-basing, see rsf_interval_general)
     double vstep_rper;                 // 1/vstep_period (vstep_index)
+    int stiff_exact;                   // stiff variant: score every step that left the fast ranges (tuning / tests)
     int n_out, nmax, damping, loading, integ_mode;
 };
 
@@ -517,6 +518,9 @@ __device__ __forceinline__ bool rsf_stage_fast(const ChainConst &cc, double fs, 
     const double e0 = fma(-th1, rth, 1.0);
     double r = fma(rth, e0, rth);
     r = fma(r, fma(-th1, r, 1.0), r);
+    // stiff variant: a third Newton step (error e0^8) admits |e0| < 1e-2.  Near the stability limit theta moves
+    // by more than 6e-5 between stages in 40 % of the trial steps that leave the ranges, and in nothing else.
+    if (WANT_OK) r = fma(r, fma(-th1, r, 1.0), r);
     rth = r;
     const double sb = (cc.b * r) * o.kt;
     const double v0 = voa * (o.d0 - sb);
@@ -524,7 +528,7 @@ __device__ __forceinline__ bool rsf_stage_fast(const ChainConst &cc, double fs, 
     o.km = o.d0 - o.c;                                          // mu' with radiation damping
     o.kv = fma(-(voa * cc.k1e), v0, v0);                        // V'
     if (WANT_OK) {
-        const bool ok = fabs(fs) * cc.qscale < 0.001953125 && fabs(As) < 0.015625 && fabs(e0) < 6.0e-5;
+        const bool ok = fabs(fs) * cc.qscale < 0.001953125 && fabs(As) < 0.015625 && fabs(e0) < 1.0e-2;
         bad = bad || !ok;
         return ok;
     }
@@ -935,7 +939,14 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         else first_bad = 2;
         bad = first_bad != 0;
         if (first_bad < 6) first_bad = 2;
-        if (stepping && bad)
+        // A step that STARTS well inside the fast ranges and leaves them at an internal stage is the trial step the
+        // controller grew past the stability limit: it explodes and SciPy rejects it.  It is taken as rejected without
+        // scoring it with the general-range stages (a rejected step shrinks by exactly 0.3 whatever its error was).
+        // CPU-oracle count over eight stiff solves (profiles/microbench/forward_stiff_r1b.txt): of ~100,000 such steps
+        // none is accepted by the exact arithmetic; were one ever, the retry at 0.3 h only costs a step.
+        // M.stiff_exact (RSFM_STIFF_EXACT=1) scores them exactly instead.
+        const bool presumed_wild = bad && start_in && !M.stiff_exact;
+        if (stepping && bad && !presumed_wild)
             dop853_step_general(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, rl, first_bad, &sv, &so);
         RSFM_DBG(0, stepping) RSFM_DBG(1, stepping && try_fast) RSFM_DBG(2, stepping && bad)
         RSFM_DBGW(3, stepping) RSFM_DBGW(4, stepping && bad) RSFM_DBGW(5, stepping && try_fast)
@@ -943,7 +954,7 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         // err <= 1   <=>   h^2 errA^2 <= den3   (no sqrt, no division; NaN rejects; 0 <= 0 accepts).
         // errA < 1e140 keeps the squares finite: an unstable step whose error norm overflows must be
         // rejected (dop853.f gets inf * 0 = NaN there), not pass as inf <= inf.
-        const bool accept = so.errA < 1e140 && (h * h) * (so.errA * so.errA) <= so.den3;
+        const bool accept = !presumed_wild && so.errA < 1e140 && (h * h) * (so.errA * so.errA) <= so.den3;
 
         RSFM_DBG(6, stepping && accept) RSFM_DBG(10, stepping && !accept && bad)
         if (stepping) {

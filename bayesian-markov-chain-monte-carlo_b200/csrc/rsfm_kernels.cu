@@ -124,6 +124,7 @@ static ModelK make_model(const rsfm_cfg *c)
     M.vstep_lnf = (c->loading == RSFM_LOAD_VSTEP) ? log(c->vstep_factor) : 0.0;
     M.vstep_rfac = (c->loading == RSFM_LOAD_VSTEP) ? 1.0 / c->vstep_factor : 1.0;
     M.vstep_rper = (c->loading == RSFM_LOAD_VSTEP) ? 1.0 / c->vstep_period : 1.0;
+    if (const char *e = getenv("RSFM_STIFF_EXACT")) M.stiff_exact = atoi(e) != 0;
     return M;
 }
 

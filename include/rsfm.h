@@ -69,7 +69,7 @@ typedef struct rsfm_cfg {
     double  t_start, t_final;            /* :174-175 */
     double  delta_t;                     /* :177, computed by the host exactly as the reference */
     double  mu_t_zero;                   /* :180 */
-    double  vstep_period, vstep_factor;  /* RSFM_LOAD_VSTEP only */
+    double  vstep_period, vstep_factor;  /* RSFM_LOAD_VSTEP only; both must be positive (RSFM_ERR_INVALID otherwise) */
     double  rtol, atol;                  /* :374 */
     double  n0;                          /* MCMC.py:97 */
     double  lo[RSFM_MAX_PARAMS];         /* strict box prior, MCMC.py:98,318-320 */

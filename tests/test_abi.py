@@ -85,6 +85,7 @@ def test_cfg_validation_needs_no_device(built_lib, pkg):
         return rc, lib.rsfm_last_error().decode()
 
     for kw, word in (({"loading": pkg._lib.LOAD_VSTEP, "vstep_period": 0.0}, "vstep_period"),
+                     ({"loading": pkg._lib.LOAD_VSTEP, "vstep_factor": 0.0}, "vstep_factor"),
                      ({"rtol": 0.0}, "rtol"), ({"n_params": 2}, "n_params"), ({"loading": 7}, "loading"),
                      ({"adapt_interval": 1}, "adapt_interval"), ({"delta_t": 0.0}, "grid"), ({"a": -1.0}, "positive")):
         rc, msg = refused(**kw)

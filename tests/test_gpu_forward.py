@@ -277,16 +277,20 @@ def test_stiff_variant_on_reference_loading_and_both_variants_on_vstep(cuda, pkg
     m = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
     m.loading, m.vstep_period, m.vstep_factor = "vstep", 30.0, 10.0
     _, acc_o, _ = orc.forward_batch(orc.make_model(number_time_steps=n, end_time=t_end, **kw), dcs, want_acc=True)
+    # "1x": the stiff variant scoring every step that left the fast ranges with the general-range stages
+    # (RSFM_STIFF_EXACT) instead of taking the exploding trial steps as rejected
     res = {}
-    for v in ("0", "1"):
+    for v, exact in (("0", "0"), ("1", "0"), ("1", "1")):
         monkeypatch.setenv("RSFM_STIFF", v)
+        monkeypatch.setenv("RSFM_STIFF_EXACT", exact)
         o = m.evaluate_batch(dcs)
         assert np.all(o["status"].cpu().numpy() == 0)
-        res[v] = (o["acc"].t().cpu().numpy(), o["nstep"].cpu().numpy())
+        res[v + ("x" if exact == "1" else "")] = (o["acc"].t().cpu().numpy(), o["nstep"].cpu().numpy())
     for i in range(len(dcs)):
         scale = np.max(np.abs(acc_o[i]))
-        for v in ("0", "1"):
+        for v in res:
             assert np.max(np.abs(res[v][0][i] - acc_o[i])) <= 2e-5 * scale, (v, dcs[i])
         assert np.max(np.abs(res["0"][0][i] - res["1"][0][i])) <= 2e-5 * scale
-    # same controller semantics: attempted-step counts of the two variants differ by well under 1 %
-    assert np.all(np.abs(res["0"][1].astype(float) - res["1"][1]) <= 0.01 * res["0"][1])
+    # same controller semantics: attempted-step counts of the variants differ by well under 1 %
+    for v in ("1", "1x"):
+        assert np.all(np.abs(res["0"][1].astype(float) - res[v][1]) <= 0.01 * res["0"][1]), v
