@@ -7,4 +7,6 @@ python bench.py --no-cpu-baseline > gpurun_out/bench_plain.json 2>/dev/null && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 export STIFF_N=1000
 python profiles/microbench/forward_stiff_once.py > gpurun_out/stiff_once.txt 2>&1 && \
-ncu --section SourceCounters --section WarpStateStats --section SchedulerStats --section LaunchStats --section InstructionStats --section Occupancy --clock-control none --import-source on -k regex:rsf_forward -s 1 -c 1 -f -o gpurun_out/prof_stiff6 python profiles/microbench/forward_stiff_once.py > gpurun_out/ncu_stiff6.log 2>&1
+ncu --section SourceCounters --section WarpStateStats --section SchedulerStats --section LaunchStats --section InstructionStats --section Occupancy --clock-control none --import-source on -k regex:rsf_forward -s 1 -c 1 -f -o gpurun_out/prof_stiff7 python profiles/microbench/forward_stiff_once.py > gpurun_out/ncu_stiff7.log 2>&1
+python profiles/microbench/run_configs.py cfg4 2 > gpurun_out/cfg4.json 2> gpurun_out/cfg4.err
+python profiles/microbench/forward_stiff_ab.py > gpurun_out/stiff_ab.txt 2>&1
