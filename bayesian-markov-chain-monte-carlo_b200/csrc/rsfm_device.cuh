@@ -19,6 +19,13 @@
 //   * restarting k1 = f(t, y) at every interval is skipped: it is bit-identical to the FSAL evaluation that
 //     closed the previous interval.
 //   * sqrt- and division-free accept / hinit decisions; exact early rejection against an SSE bound.
+//
+// Layout of this file: TMA staging of the series; the RHS (rsf_rhs) and the two DOP853 step forms (dop853_step_impl:
+// general range, optionally resumed from a stage; dop853_step_fast: short dependency chain); the general interval
+// path in its two variants -- rsf_interval_plain (SciPy's controller as written; inline in the 168-register kernels,
+// out of line in the speculative one) and rsf_interval_general (stiff variant for velocity-step loading: re-based
+// friction law, exploding trial steps not scored, SFU-seeded controller root) -- and rsf_solve_mode, the output loop
+// with the fast interval.  Kernels pick the variant with the template flags VS / ISO (rsfm_kernels.cu).
 #pragma once
 
 #include <cstdint>
@@ -1011,9 +1018,9 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
 // whose hot part (fast interval, FSAL, output) then spans ~22 KB instead of ~58 KB of addresses (instruction-fetch
 // stalls at the loop head, profiles/README.md).  ISO kernels only (see rsf_solve_mode).
 template <bool PARITY>
-__device__ __noinline__ void rsf_interval_plain(const ModelK *Mp, const ChainConst *ccp, IvState *S, double *wtab,
-                                                double *ptab, int k, int running_i, int *was_bad_io,
-                                                unsigned int *stiff_steps_io)
+__device__ __forceinline__ void rsf_interval_plain_body(const ModelK *Mp, const ChainConst *ccp, IvState *S, double *wtab,
+                                                        double *ptab, int k, int running_i, int *was_bad_io,
+                                                        unsigned int *stiff_steps_io)
 {
     const ModelK &M = *Mp;
     const ChainConst &cc = *ccp;
@@ -1181,6 +1188,14 @@ __device__ __noinline__ void rsf_interval_plain(const ModelK *Mp, const ChainCon
     *was_bad_io = was_bad ? 1 : 0; *stiff_steps_io = stiff_steps;
 }
 
+template <bool PARITY>
+__device__ __noinline__ void rsf_interval_plain(const ModelK *Mp, const ChainConst *ccp, IvState *S, double *wtab,
+                                                double *ptab, int k, int running_i, int *was_bad_io,
+                                                unsigned int *stiff_steps_io)
+{
+    rsf_interval_plain_body<PARITY>(Mp, ccp, S, wtab, ptab, k, running_i, was_bad_io, stiff_steps_io);
+}
+
 // Integrate one chain over the whole output grid.  All 32 lanes of a warp must call this together
 // (it contains warp collectives) and all threads of a block must call it together when
 // `series.g != nullptr` (block barriers at tile boundaries).  `active` = this lane owns a chain.
@@ -1199,15 +1214,13 @@ __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, do
                                                     double *xtx_out, double *t_out, double sse_limit)
 {
     const int lane = threadIdx.x & 31;
-    const int nthr = blockDim.x;
     double *const wbase = ls.tab + (threadIdx.x >> 5) * LTAB_STRIDE;
     double *wtab = wbase;                  // current buffer (wbase or wbase + 16)
     double *ptab = ls.priv + threadIdx.x;
     const ChainConst cc = make_chain_const(M, a, b, dc);
     const bool have_data = series.g != nullptr;
     constexpr bool parity = PARITY;      // compile-time: keeps the fast interval one branch-free block
-    const double uround = 2.3e-16, safe = 0.9;
-    const double facc1 = 1.0 / 0.3, facc2 = 1.0 / 6.0;
+    const double uround = 2.3e-16;
 
     double t = M.t_start;
     double mu = M.mu_t_zero, th = dc / M.V_ref, V = M.V_ref;       // :367-370,377
@@ -1229,25 +1242,9 @@ __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, do
     double vprev = V;
     double h_carry = 0.0;
 
-    // Key (tab_t, tab_h) of the warp's shared table.  It is rebuilt when some lane misses and at
-    // least two lanes would share the new key (always, outside the stiff regime).
+    // Key (tab_t, tab_h) of the warp's shared table (rebuilt by the general interval path when lanes leave the
+    // nominal grid).
     double tab_t = 0.0, tab_h = -1.0;
-    auto ensure_table = [&](bool want, double hk) {
-        const bool miss = want && !(t == tab_t && hk == tab_h);
-        const unsigned mm = __ballot_sync(FULL_MASK, miss);
-        if (mm != 0) {
-            const int src = __ffs(mm) - 1;
-            const double nt = __shfl_sync(FULL_MASK, t, src), nh = __shfl_sync(FULL_MASK, hk, src);
-            const unsigned share = __ballot_sync(FULL_MASK, want && t == nt && hk == nh);
-            if (__popc(share) >= 2) {
-                tab_t = nt; tab_h = nh;
-                __syncwarp();                                      // readers of the old table are done
-                if (lane < 11) wtab[lane] = loading_of(M, __dadd_rn(nt, __dmul_rn(TB.c[lane], nh)));
-                __syncwarp();
-            }
-        }
-    };
-
     // Nominal table (global, built by loading_table_kernel): entry k is fetched one interval ahead with
     // cp.async into the other half of the warp's double buffer, so no load latency is ever exposed.
     // Its key (t_k, h_k) is the recurrence every lane can run itself: t_{k+1} = t_k + ((t_k + dt) - t_k).
@@ -1288,9 +1285,6 @@ __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, do
         const bool running = active && !failed;
         const double xend = t + M.delta_t;                         // :382
         const double hmax = fabs(xend - t);
-        int nstep_call = 0;
-        bool reject = false, last = false;
-        double h;
 
         // ---- fast interval: the whole warp is on the nominal grid ----
         // Outside the stiff regime every SciPy call of the reference does the same thing: hinit returns
@@ -1359,148 +1353,21 @@ __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, do
             h_carry = S.h_carry; tab_t = S.tab_t; tab_h = S.tab_h;
             out.status = S.status; out.nrhs = S.nrhs; out.nstep = S.nstep; failed = S.failed != 0;
         }
-        (void)nstep_call; (void)reject; (void)last; (void)h; (void)was_bad; (void)stiff_steps; (void)nthr; (void)safe; (void)facc1; (void)facc2;
-        (void)ensure_table;
-        } else if constexpr (ISO) {
+        (void)was_bad; (void)stiff_steps;
+        } else {
         if (!fast_done) {
             IvState S;
             S.t = t; S.mu = mu; S.th = th; S.V = V; S.rth = rth; S.k1m = k1m; S.k1t = k1t; S.k1v = k1v;
             S.h_carry = h_carry; S.tab_t = tab_t; S.tab_h = tab_h;
             S.status = out.status; S.nrhs = out.nrhs; S.nstep = out.nstep; S.failed = failed ? 1 : 0;
             int wb = was_bad ? 1 : 0;
-            rsf_interval_plain<PARITY>(&M, &cc, &S, wtab, ptab, k, running ? 1 : 0, &wb, &stiff_steps);
+            if constexpr (ISO) rsf_interval_plain<PARITY>(&M, &cc, &S, wtab, ptab, k, running ? 1 : 0, &wb, &stiff_steps);
+            else rsf_interval_plain_body<PARITY>(&M, &cc, &S, wtab, ptab, k, running ? 1 : 0, &wb, &stiff_steps);
             t = S.t; mu = S.mu; th = S.th; V = S.V; rth = S.rth; k1m = S.k1m; k1t = S.k1t; k1v = S.k1v;
             h_carry = S.h_carry; tab_t = S.tab_t; tab_h = S.tab_h;
             out.status = S.status; out.nrhs = S.nrhs; out.nstep = S.nstep; failed = S.failed != 0;
             was_bad = wb != 0;
         }
-        (void)nstep_call; (void)reject; (void)last; (void)h; (void)nthr; (void)safe; (void)facc1; (void)facc2;
-        (void)ensure_table;
-        } else {
-        if (!fast_done) {
-        if (parity || k == 1) {
-            // ---- HINIT (dop853.f, iord = 8).  The common outcome h0 = h = hmax is recognised by
-            // comparisons in the squared / 16th-power domain, without sqrt or division. ----
-            // Norms over the common denominator D = (sk0 sk1 sk2)^2:  ||f/sk||^2 = Nf/D etc.
-            const double k0 = M.atol + M.rtol * fabs(mu), k1 = M.atol + M.rtol * fabs(th), k2 = M.atol + M.rtol * fabs(V);
-            const double p0 = k1 * k2, p1 = k0 * k2, p2 = k0 * k1;
-            const double dd = k0 * p0, D = dd * dd;
-            const double Nf = (k1m * p0) * (k1m * p0) + (k1t * p1) * (k1t * p1) + (k1v * p2) * (k1v * p2);
-            const double Ny = (mu * p0) * (mu * p0) + (th * p1) * (th * p1) + (V * p2) * (V * p2);
-            // h0 = min(0.01 sqrt(dny/dnf), hmax)  (1e-6 when either norm^2 <= 1e-10)
-            const bool tiny = (Nf <= 1e-10 * D) || (Ny <= 1e-10 * D);
-            const bool h0max = !tiny && (Ny >= Nf * (1.0e4 * hmax * hmax));
-            double h0 = hmax;
-            if (!h0max) h0 = tiny ? fmin(1.0e-6, hmax) : fmin(sqrt(Ny / Nf) * 0.01, hmax);
-            // the probe point t + h0 is stage 12 of the step (t, hmax): speculate on that table
-            ensure_table(running, hmax);
-            double Lp = wtab[10];
-            if (running && !(t == tab_t && h0 == tab_h)) Lp = loading_of(M, t + h0);
-            double f1m, f1t, f1v, rprobe = rth;
-            rsf_rhs_checked(cc, Lp, mu + h0 * k1m, th + h0 * k1t, rprobe, f1m, f1t, f1v);
-            if (running) out.nrhs++;
-            const double e0 = (f1m - k1m) * p0, e1 = (f1t - k1t) * p1, e2 = (f1v - k1v) * p2;
-            const double Ne = e0 * e0 + e1 * e1 + e2 * e2;                      // ||(f1-f0)/sk||^2 = Ne/D
-            // h = min(100 h0, (0.01/der12)^(1/8), hmax) with der12^2 = max(Ne/(D h0^2), Nf/D).
-            // (0.01/der12)^(1/8) >= hmax  <=>  der12^2 hmax^16 <= 1e-4: decided without sqrt / division
-            const double hm2 = hmax * hmax, hm4 = hm2 * hm2, hm8 = hm4 * hm4, hm16 = hm8 * hm8;
-            const double lim = 1.0e-4 * D;
-            if (h0max && Ne * hm16 <= lim * hm2 && Nf * hm16 <= lim && fmax(Ne, Nf * hm2) > 1e-30 * D * hm2) {
-                h = hmax;
-            } else {
-                const double d12sq = fmax(Ne / (D * h0 * h0), Nf / D);
-                double h1;
-                if (d12sq <= 1e-30) h1 = fmax(1.0e-6, fabs(h0) * 1.0e-3);
-                else h1 = root8(0.01 / sqrt(d12sq));
-                h = fmin(fmin(100.0 * fabs(h0), h1), hmax);
-            }
-        } else {
-            h = fmin(h_carry, hmax);
-        }
-
-        // ---- dp86co step loop: every iteration is one attempted step of all unfinished lanes ----
-        bool done = !running;
-        for (;;) {
-            if (!done) {
-                if (nstep_call > M.nmax) { failed = true; done = true; out.status = RSFM_CHAIN_NMAX; }
-                else if (0.1 * fabs(h) <= fabs(t) * uround) { failed = true; done = true; out.status = RSFM_CHAIN_HSMALL; }
-                else {
-                    if ((t + 1.01 * h - xend) > 0.0) { h = xend - t; last = true; }
-                    nstep_call++;
-                }
-            }
-            if (__ballot_sync(FULL_MASK, !done) == 0) break;
-            const bool stepping = !done;
-            ensure_table(stepping, h);
-            const bool hit = (t == tab_t && h == tab_h);
-            if (stepping && !hit) {
-                // private stage values (this lane is not on the warp's (t, h)).  A piecewise-constant load
-                // that does not switch between t and t + h has one value for the whole step.
-                const double La = loading_of(M, t), Lb = loading_of(M, t + h);
-                if (M.loading == RSFM_LOAD_VSTEP && La == Lb &&
-                    floor((t - M.t_start) / M.vstep_period) == floor((t + h - M.t_start) / M.vstep_period)) {
-#pragma unroll
-                    for (int i = 0; i < 11; i++) ptab[i * nthr] = La;
-                } else {
-#pragma unroll 1
-                    for (int i = 0; i < 11; i++) ptab[i * nthr] = loading_of(M, __dadd_rn(t, __dmul_rn(TB.c[i], h)));
-                }
-            }
-            const double *Lsrc = hit ? wtab : ptab;
-            const int lstride = hit ? 1 : nthr;
-
-            StepIn in;
-            in.h = h; in.mu = mu; in.th = th; in.V = V; in.k1m = k1m; in.k1t = k1t; in.k1v = k1v; in.rth = rth;
-            in.atol = M.atol; in.rtol = M.rtol;
-            StepOut so;
-            bool bad = false;
-            // A warp whose stepping lanes all left the fast ranges on their previous step (stiff regime)
-            // goes straight to the general step; the fast one is retried every 64 steps.
-            const bool try_fast = !__all_sync(FULL_MASK, !stepping || was_bad) || (++stiff_steps & 63u) == 0u;
-            if (try_fast) dop853_step_fast(cc, in, Lsrc, lstride, so, bad);
-            else bad = true;
-            if (stepping && bad) dop853_step_general(&cc, &in, Lsrc, lstride, &so);
-            if (stepping) was_bad = bad;
-            // err <= 1   <=>   h^2 errA^2 <= den3   (no sqrt, no division; NaN rejects; 0 <= 0 accepts).
-            // errA < 1e140 keeps the squares finite: an unstable step whose error norm overflows must be
-            // rejected (dop853.f gets inf * 0 = NaN there), not pass as inf <= inf.
-            const bool accept = so.errA < 1e140 && (h * h) * (so.errA * so.errA) <= so.den3;
-
-            if (stepping) {
-                out.nstep++;
-                out.nrhs += 11;
-                if (accept) {
-                    // FSAL: f(x + h, y_new) is k1 of the next step and of the next interval's restart
-                    rth = so.rth;
-                    rsf_rhs_checked(cc, so.L12, so.muN, so.thN, rth, k1m, k1t, k1v);
-                    out.nrhs++;
-                    const double hold = h;
-                    mu = so.muN; th = so.thN; V = so.VN; t = t + h;
-                    // the controller's h_new is only consumed when the step does not end the
-                    // interval, or when the step size is carried across output points
-                    // (h_new = h / max(1/6, min(1/0.3, err^(1/8)/0.9)) >= h when err <= 0.9^8; with h = hmax it is
-                    //  clamped back to hmax, so the 8th root is skipped)
-                    const bool keeps_hmax = (hold == hmax) && !reject &&
-                                            (hold * hold) * (so.errA * so.errA) <= 0.185302018885184 * so.den3;
-                    if ((!last || !parity) && !keeps_hmax) {
-                        const double err = so.den3 > 0.0 ? fabs(hold) * so.errA / sqrt(so.den3) : 0.0;
-                        const double fac = fmax(facc2, fmin(facc1, root8(err) / safe));
-                        double hnew = hold / fac;
-                        if (fabs(hnew) > hmax) hnew = hmax;
-                        if (reject) hnew = fmin(fabs(hnew), fabs(hold));
-                        h = hnew;
-                    }
-                    reject = false;
-                    if (last) { done = true; h_carry = h; }
-                } else {
-                    // rejected (also NaN).  SciPy 1.18.1's dop853 shrinks by exactly 1/facc1 here.
-                    h = h / facc1;
-                    reject = true;
-                    last = false;
-                }
-            }
-        }
-        }   // !fast_done
         }
 
         // ---- output point k: RateStateModel.py:384-388, MCMC.py:387 ----
