@@ -677,7 +677,7 @@ __device__ __forceinline__ int dop853_step_fast_rb(const ChainConst *cc, double 
     bool bad = false;
     int first_bad = 0;
     dop853_step_fast<true>(cr, *I, Lp, ls, cc->kV, Lc, *O, bad, first_bad, sv);
-    return first_bad ? __ffs(first_bad) + 1 : 0;          // stage mask -> first offending stage
+    return first_bad;                                     // mask of the stages outside the ranges (bit s - 2)
 }
 
 __device__ __noinline__ void rsf_rhs_general(const ChainConst *c, double lam, double mu_ref_r, double L, double mu,
@@ -842,9 +842,20 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
     };
 
     double Lc = 0.0, rl = 1.0, lam = 1.0, mu_ref_r = cc.mu_ref;
-    if (vstep && loading_of(M, t) == M.vstep_factor - 1.0) {
-        Lc = M.vstep_factor - 1.0; rl = M.vstep_rfac; lam = M.vstep_factor;
-        mu_ref_r = fma(1.0 / cc.inv_a - cc.b, M.vstep_lnf, cc.mu_ref);     // (a - b) ln lam: a, b not kept live
+    // [pw_lo, pw_hi]: times at which the piecewise-constant load certainly has the value pw_L (the period of t,
+    // shrunk by a guard far above the rounding of the index computation); a step inside it needs no index
+    // arithmetic at all, any other one takes the exact per-stage route.
+    double pw_lo = 1.0, pw_hi = 0.0, pw_L = 0.0;
+    if (M.loading == RSFM_LOAD_VSTEP) {
+        const double ia = vstep_index(M, t);
+        const double guard = 1e-6 * M.vstep_period;
+        pw_lo = fma(ia, M.vstep_period, M.t_start) + guard;
+        pw_hi = fma(ia + 1.0, M.vstep_period, M.t_start) - guard;
+        pw_L = ((long long)ia & 1) ? M.vstep_factor - 1.0 : 0.0;
+        if (vstep && pw_L != 0.0) {
+            Lc = pw_L; rl = M.vstep_rfac; lam = M.vstep_factor;
+            mu_ref_r = fma(1.0 / cc.inv_a - cc.b, M.vstep_lnf, cc.mu_ref);     // (a - b) ln lam: a, b not kept live
+        }
     }
     const ChainConst cr = rebase_const(cc, lam, mu_ref_r);
     if (parity || k == 1) {
@@ -912,9 +923,9 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         if (stepping && !hit) {
             // private stage values (this lane is not on the warp's (t, h)).  A piecewise-constant load
             // that does not switch between t and t + h has one value for the whole step.
-            bool flat = false;
-            double La = 0.0;
-            if (M.loading == RSFM_LOAD_VSTEP) {
+            bool flat = t >= pw_lo && t + h <= pw_hi;
+            double La = pw_L;
+            if (!flat && M.loading == RSFM_LOAD_VSTEP) {
                 const double ia = vstep_index(M, t), ib = vstep_index(M, t + h);
                 flat = ia == ib;
                 La = ((long long)ia & 1) ? M.vstep_factor - 1.0 : 0.0;
@@ -940,12 +951,11 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         const double f0s = fma(cr.w, th, -1.0), A0s = (mu - cr.mu_ref) * cr.inv_a;
         const bool start_in = fabs(f0s) * cr.qscale < 0.5 * 0.001953125 && fabs(A0s) < 0.5 * 0.015625;
         const bool try_fast = __any_sync(FULL_MASK, stepping && start_in);
-        int first_bad = 0;
+        int bad_mask = 0;                 // bit s - 2: stage s left the fast ranges
         StepSave sv;
-        if (try_fast) first_bad = dop853_step_fast_rb(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, &so, &sv);
-        else first_bad = 2;
-        bad = first_bad != 0;
-        if (first_bad < 6) first_bad = 2;
+        if (try_fast) bad_mask = dop853_step_fast_rb(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, &so, &sv);
+        else bad_mask = 1;
+        bad = bad_mask != 0;
         // A step that STARTS well inside the fast ranges and leaves them at an internal stage is the trial step the
         // controller grew past the stability limit: it explodes and SciPy rejects it.  It is taken as rejected without
         // scoring it with the general-range stages (a rejected step shrinks by exactly 0.3 whatever its error was).
@@ -954,10 +964,13 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         // M.stiff_exact (RSFM_STIFF_EXACT=1) scores them exactly instead.
         const bool presumed_wild = bad && start_in && !M.stiff_exact;
         if (stepping && bad && !presumed_wild)
-            dop853_step_general(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, rl, first_bad, &sv, &so);
+        {
+            const int first = __ffs(bad_mask) + 1;                  // first offending stage; < 6: nothing is reused
+            dop853_step_general(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, rl, first < 6 ? 2 : first, &sv, &so);
+        }
         RSFM_DBG(0, stepping) RSFM_DBG(1, stepping && try_fast) RSFM_DBG(2, stepping && bad)
         RSFM_DBGW(3, stepping) RSFM_DBGW(4, stepping && bad) RSFM_DBGW(5, stepping && try_fast)
-        RSFM_DBG(8, stepping && lam != 1.0) RSFM_DBG(9, stepping && bad && first_bad > 2)
+        RSFM_DBG(8, stepping && lam != 1.0) RSFM_DBG(9, stepping && bad && (__ffs(bad_mask) + 1) > 5)
         // err <= 1   <=>   h^2 errA^2 <= den3   (no sqrt, no division; NaN rejects; 0 <= 0 accepts).
         // errA < 1e140 keeps the squares finite: an unstable step whose error norm overflows must be
         // rejected (dop853.f gets inf * 0 = NaN there), not pass as inf <= inf.
