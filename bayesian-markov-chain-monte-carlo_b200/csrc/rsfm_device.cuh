@@ -379,81 +379,64 @@ struct StepIn { double h, mu, th, V, k1m, k1t, k1v, rth, atol, rtol; };
 // err = |h| ||e5||^2 / sqrt(3 (||e5||^2 + 0.01 ||e3||^2)) = |h| errA / sqrt(den3)   (dop853.f, n = 3)
 struct StepOut { double muN, thN, VN, errA, den3, L12, rth; };
 
-// What a fast step hands to the general step when one of its stages left the fast ranges: the stage
-// derivatives that are still exact (every stage before the first offending one).  Stages 2, 3 feed no later
-// stage than 5, so only k4..k11 (mu', theta') and the V' of stages 6..11 are kept.
-struct StepSave { double km[8], kt[8], kv[6]; };
-
-// General-range step: the reference's formulas (libdevice log / exp, true division) at every stage from
-// `first` on; the stages before it are taken from the fast step that found stage `first` outside its
-// ranges (sv).  first <= 5 (in particular 2): nothing is reused.  In the stiff regime the trial step that the
-// controller grows past the stability limit leaves the ranges at stage 9, 11 or 12 in 80 % of the cases
-// (CPU oracle statistics, profiles/microbench/stiff_paths.md), so only its last stages are evaluated twice.
-// Lc, rl: the stage values of L are re-based on the fly, L' = (L - Lc) rl (see rsf_solve_mode; 0, 1 = none).
+// General-range step: the reference's formulas (libdevice log / exp, true division) at every stage.
+// Lc, rl: the stage values of L are re-based on the fly, L' = (L - Lc) rl (see rsf_interval_general; 0, 1 = none).
 __device__ __forceinline__ void dop853_step_impl(const ChainConst &cc, const StepIn &I, const double *Lp, int ls,
-                                                 double Lc, double rl, int first, const StepSave &sv, StepOut &O)
+                                                 double Lc, double rl, StepOut &O)
 {
+    bool bad = false;
     const double h = I.h, mu = I.mu, th = I.th, k1m = I.k1m, k1t = I.k1t, k1v = I.k1v;
     double rth = I.rth;
-    bool bad = false;
-    double k2m = 0.0, k2t = 0.0, k3m = 0.0, k3t = 0.0, k4m, k4t, k5m, k5t, k6m, k6t, k7m, k7t, k8m, k8t, k9m, k9t, k10m, k10t;
+    double k2m, k2t, k3m, k3t, k4m, k4t, k5m, k5t, k6m, k6t, k7m, k7t, k8m, k8t, k9m, k9t, k10m, k10t;
     double kv, k9v, k12v, bV, eV;
-    const bool all = first < 6;
-#define RSFM_GSTAGE(S, YM, YT, KM, KT, KV, SM, ST, SV)                                                         \
-    if (all || first <= (S)) rsf_rhs<false>(cc, (Lp[((S) - 2) * ls] - Lc) * rl, YM, YT, rth, KM, KT, KV, bad); \
-    else { KM = (SM); KT = (ST); KV = (SV); }
     // stages 2..5: their V-derivatives carry zero weight everywhere
-    if (all) {
-        rsf_rhs<false>(cc, (Lp[0 * ls] - Lc) * rl, mu + h * (TB.a21 * k1m), th + h * (TB.a21 * k1t), rth, k2m, k2t, kv, bad);
-        rsf_rhs<false>(cc, (Lp[1 * ls] - Lc) * rl, mu + h * (TB.a31 * k1m + TB.a32 * k2m),
-                       th + h * (TB.a31 * k1t + TB.a32 * k2t), rth, k3m, k3t, kv, bad);
-        rsf_rhs<false>(cc, (Lp[2 * ls] - Lc) * rl, mu + h * (TB.a41 * k1m + TB.a43 * k3m),
-                       th + h * (TB.a41 * k1t + TB.a43 * k3t), rth, k4m, k4t, kv, bad);
-        rsf_rhs<false>(cc, (Lp[3 * ls] - Lc) * rl, mu + h * (TB.a51 * k1m + TB.a53 * k3m + TB.a54 * k4m),
-                       th + h * (TB.a51 * k1t + TB.a53 * k3t + TB.a54 * k4t), rth, k5m, k5t, kv, bad);
-    } else {
-        k4m = sv.km[0]; k4t = sv.kt[0]; k5m = sv.km[1]; k5t = sv.kt[1];
-    }
-    RSFM_GSTAGE(6, mu + h * (TB.a61 * k1m + TB.a64 * k4m + TB.a65 * k5m),
-                th + h * (TB.a61 * k1t + TB.a64 * k4t + TB.a65 * k5t), k6m, k6t, kv, sv.km[2], sv.kt[2], sv.kv[0]);
+    rsf_rhs<false>(cc, (Lp[0 * ls] - Lc) * rl, mu + h * (TB.a21 * k1m), th + h * (TB.a21 * k1t), rth, k2m, k2t, kv, bad);
+    rsf_rhs<false>(cc, (Lp[1 * ls] - Lc) * rl, mu + h * (TB.a31 * k1m + TB.a32 * k2m), th + h * (TB.a31 * k1t + TB.a32 * k2t),
+                  rth, k3m, k3t, kv, bad);
+    rsf_rhs<false>(cc, (Lp[2 * ls] - Lc) * rl, mu + h * (TB.a41 * k1m + TB.a43 * k3m), th + h * (TB.a41 * k1t + TB.a43 * k3t),
+                  rth, k4m, k4t, kv, bad);
+    rsf_rhs<false>(cc, (Lp[3 * ls] - Lc) * rl, mu + h * (TB.a51 * k1m + TB.a53 * k3m + TB.a54 * k4m),
+                  th + h * (TB.a51 * k1t + TB.a53 * k3t + TB.a54 * k4t), rth, k5m, k5t, kv, bad);
+    rsf_rhs<false>(cc, (Lp[4 * ls] - Lc) * rl, mu + h * (TB.a61 * k1m + TB.a64 * k4m + TB.a65 * k5m),
+                  th + h * (TB.a61 * k1t + TB.a64 * k4t + TB.a65 * k5t), rth, k6m, k6t, kv, bad);
     bV = TB.b1 * k1v + TB.b6 * kv;
     eV = TB.e1 * k1v + TB.e6 * kv;
-    RSFM_GSTAGE(7, mu + h * (TB.a71 * k1m + TB.a74 * k4m + TB.a75 * k5m + TB.a76 * k6m),
-                th + h * (TB.a71 * k1t + TB.a74 * k4t + TB.a75 * k5t + TB.a76 * k6t), k7m, k7t, kv, sv.km[3], sv.kt[3],
-                sv.kv[1]);
+    rsf_rhs<false>(cc, (Lp[5 * ls] - Lc) * rl, mu + h * (TB.a71 * k1m + TB.a74 * k4m + TB.a75 * k5m + TB.a76 * k6m),
+                  th + h * (TB.a71 * k1t + TB.a74 * k4t + TB.a75 * k5t + TB.a76 * k6t), rth, k7m, k7t, kv, bad);
     bV += TB.b7 * kv; eV += TB.e7 * kv;
-    RSFM_GSTAGE(8, mu + h * (TB.a81 * k1m + TB.a84 * k4m + TB.a85 * k5m + TB.a86 * k6m + TB.a87 * k7m),
-                th + h * (TB.a81 * k1t + TB.a84 * k4t + TB.a85 * k5t + TB.a86 * k6t + TB.a87 * k7t), k8m, k8t, kv,
-                sv.km[4], sv.kt[4], sv.kv[2]);
+    rsf_rhs<false>(cc, (Lp[6 * ls] - Lc) * rl,
+                  mu + h * (TB.a81 * k1m + TB.a84 * k4m + TB.a85 * k5m + TB.a86 * k6m + TB.a87 * k7m),
+                  th + h * (TB.a81 * k1t + TB.a84 * k4t + TB.a85 * k5t + TB.a86 * k6t + TB.a87 * k7t), rth,
+                  k8m, k8t, kv, bad);
     bV += TB.b8 * kv; eV += TB.e8 * kv;
-    RSFM_GSTAGE(9, mu + h * (TB.a91 * k1m + TB.a94 * k4m + TB.a95 * k5m + TB.a96 * k6m + TB.a97 * k7m + TB.a98 * k8m),
-                th + h * (TB.a91 * k1t + TB.a94 * k4t + TB.a95 * k5t + TB.a96 * k6t + TB.a97 * k7t + TB.a98 * k8t), k9m, k9t,
-                k9v, sv.km[5], sv.kt[5], sv.kv[3]);
+    rsf_rhs<false>(cc, (Lp[7 * ls] - Lc) * rl,
+                  mu + h * (TB.a91 * k1m + TB.a94 * k4m + TB.a95 * k5m + TB.a96 * k6m + TB.a97 * k7m + TB.a98 * k8m),
+                  th + h * (TB.a91 * k1t + TB.a94 * k4t + TB.a95 * k5t + TB.a96 * k6t + TB.a97 * k7t + TB.a98 * k8t),
+                  rth, k9m, k9t, k9v, bad);
     bV += TB.b9 * k9v; eV += TB.e9 * k9v;
-    RSFM_GSTAGE(10,
-                mu + h * (TB.a101 * k1m + TB.a104 * k4m + TB.a105 * k5m + TB.a106 * k6m + TB.a107 * k7m + TB.a108 * k8m +
-                          TB.a109 * k9m),
-                th + h * (TB.a101 * k1t + TB.a104 * k4t + TB.a105 * k5t + TB.a106 * k6t + TB.a107 * k7t + TB.a108 * k8t +
-                          TB.a109 * k9t),
-                k10m, k10t, kv, sv.km[6], sv.kt[6], sv.kv[4]);
+    rsf_rhs<false>(cc, (Lp[8 * ls] - Lc) * rl,
+                  mu + h * (TB.a101 * k1m + TB.a104 * k4m + TB.a105 * k5m + TB.a106 * k6m + TB.a107 * k7m +
+                            TB.a108 * k8m + TB.a109 * k9m),
+                  th + h * (TB.a101 * k1t + TB.a104 * k4t + TB.a105 * k5t + TB.a106 * k6t + TB.a107 * k7t +
+                            TB.a108 * k8t + TB.a109 * k9t),
+                  rth, k10m, k10t, kv, bad);
     bV += TB.b10 * kv; eV += TB.e10 * kv;
     // stage 11 -> k2 slot
-    RSFM_GSTAGE(11,
-                mu + h * (TB.a111 * k1m + TB.a114 * k4m + TB.a115 * k5m + TB.a116 * k6m + TB.a117 * k7m + TB.a118 * k8m +
-                          TB.a119 * k9m + TB.a1110 * k10m),
-                th + h * (TB.a111 * k1t + TB.a114 * k4t + TB.a115 * k5t + TB.a116 * k6t + TB.a117 * k7t + TB.a118 * k8t +
-                          TB.a119 * k9t + TB.a1110 * k10t),
-                k2m, k2t, kv, sv.km[7], sv.kt[7], sv.kv[5]);
+    rsf_rhs<false>(cc, (Lp[9 * ls] - Lc) * rl,
+                  mu + h * (TB.a111 * k1m + TB.a114 * k4m + TB.a115 * k5m + TB.a116 * k6m + TB.a117 * k7m +
+                            TB.a118 * k8m + TB.a119 * k9m + TB.a1110 * k10m),
+                  th + h * (TB.a111 * k1t + TB.a114 * k4t + TB.a115 * k5t + TB.a116 * k6t + TB.a117 * k7t +
+                            TB.a118 * k8t + TB.a119 * k9t + TB.a1110 * k10t),
+                  rth, k2m, k2t, kv, bad);
     bV += TB.b11 * kv; eV += TB.e11 * kv;
-#undef RSFM_GSTAGE
-    // stage 12 -> k3 slot, at x + h (always evaluated here: first <= 12)
+    // stage 12 -> k3 slot, at x + h
     const double L12 = Lp[10 * ls];                 // returned as stored (the caller re-bases it for the FSAL evaluation)
     rsf_rhs<false>(cc, (L12 - Lc) * rl,
-                   mu + h * (TB.a121 * k1m + TB.a124 * k4m + TB.a125 * k5m + TB.a126 * k6m + TB.a127 * k7m +
-                             TB.a128 * k8m + TB.a129 * k9m + TB.a1210 * k10m + TB.a1211 * k2m),
-                   th + h * (TB.a121 * k1t + TB.a124 * k4t + TB.a125 * k5t + TB.a126 * k6t + TB.a127 * k7t +
-                             TB.a128 * k8t + TB.a129 * k9t + TB.a1210 * k10t + TB.a1211 * k2t),
-                   rth, k3m, k3t, k12v, bad);
+                  mu + h * (TB.a121 * k1m + TB.a124 * k4m + TB.a125 * k5m + TB.a126 * k6m + TB.a127 * k7m +
+                            TB.a128 * k8m + TB.a129 * k9m + TB.a1210 * k10m + TB.a1211 * k2m),
+                  th + h * (TB.a121 * k1t + TB.a124 * k4t + TB.a125 * k5t + TB.a126 * k6t + TB.a127 * k7t +
+                            TB.a128 * k8t + TB.a129 * k9t + TB.a1210 * k10t + TB.a1211 * k2t),
+                  rth, k3m, k3t, k12v, bad);
     bV += TB.b12 * k12v; eV += TB.e12 * k12v;
     // 8th-order solution, 5th/3rd-order error forms
     const double bM = TB.b1 * k1m + TB.b6 * k6m + TB.b7 * k7m + TB.b8 * k8m + TB.b9 * k9m + TB.b10 * k10m +
@@ -499,10 +482,10 @@ __device__ __forceinline__ void dop853_step_impl(const ChainConst &cc, const Ste
 // Values agree with the textbook order to rounding; both are the same function of (mu_s, theta_s).
 struct StageOut { double km, kt, kv, d0, c; };
 
-// (WANT_OK = false keeps the range test in the one-expression form the fast interval was tuned with: ptxas
-//  schedules the whole 1,000-instruction block ~25 % longer when the flag is also materialised.)
-template <bool WANT_OK>
-__device__ __forceinline__ bool rsf_stage_fast(const ChainConst &cc, double fs, double As, double dl, double th1,
+// STIFF: the stiff variant's form (third Newton step for 1/theta).  The range test stays one expression OR-ed into
+// `bad`: ptxas schedules the 1,000-instruction fast-interval block ~25 % longer when a per-stage flag is materialised.
+template <bool STIFF>
+__device__ __forceinline__ void rsf_stage_fast(const ChainConst &cc, double fs, double As, double dl, double th1,
                                                double kVL, double &rth, StageOut &o, bool &bad)
 {
     double p = fma(cc.cq[5], fs, cc.cq[4]);
@@ -527,28 +510,21 @@ __device__ __forceinline__ bool rsf_stage_fast(const ChainConst &cc, double fs, 
     r = fma(r, fma(-th1, r, 1.0), r);
     // stiff variant: a third Newton step (error e0^8) admits |e0| < 1e-2.  Near the stability limit theta moves
     // by more than 6e-5 between stages in 40 % of the trial steps that leave the ranges, and in nothing else.
-    if (WANT_OK) r = fma(r, fma(-th1, r, 1.0), r);
+    if (STIFF) r = fma(r, fma(-th1, r, 1.0), r);
     rth = r;
     const double sb = (cc.b * r) * o.kt;
     const double v0 = voa * (o.d0 - sb);
     o.c = cc.k1e * v0;
     o.km = o.d0 - o.c;                                          // mu' with radiation damping
     o.kv = fma(-(voa * cc.k1e), v0, v0);                        // V'
-    if (WANT_OK) {
-        const bool ok = fabs(fs) * cc.qscale < 0.001953125 && fabs(As) < 0.015625 && fabs(e0) < 1.0e-2;
-        bad = bad || !ok;
-        return ok;
-    }
-    bad = bad || !(fabs(fs) * cc.qscale < 0.001953125 && fabs(As) < 0.015625 && fabs(e0) < 6.0e-5);
-    return true;
+    bad = bad || !(fabs(fs) * cc.qscale < 0.001953125 && fabs(As) < 0.015625 && fabs(e0) < (STIFF ? 1.0e-2 : 6.0e-5));
 }
 
 // RB = true: re-based frame (see Rebase): cc holds the re-based constants and the stage values of L are taken
 // relative to the base level, k'V_ref' L' = kVb (L - Lc) with kVb the chain's own k'V_ref.
 template <bool RB>
 __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const StepIn &I, const double *Lp, int ls,
-                                                 double kVb, double Lc, StepOut &O, bool &bad, int &first_bad,
-                                                 StepSave *sv)
+                                                 double kVb, double Lc, StepOut &O, bool &bad)
 {
     const double h = I.h, mu = I.mu, th = I.th, k1m = I.k1m, k1t = I.k1t, k1v = I.k1v;
     double rth = I.rth;
@@ -565,9 +541,8 @@ __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const Ste
         const double th__ = fma(h * (ANEW), so.kt, fma(h, pt__, th));                                      \
         const double As__ = fma(ih * (ANEW), so.d0, fma(ih, pm__, A0));                                    \
         const double dl__ = -(ih * (ANEW)) * so.c;                                                         \
-        const bool ok__ = rsf_stage_fast<RB>(cc, fs__, As__, dl__, th__,                                       \
-                       RB ? kVb * (Lp[(IDX) * ls] - Lc) : cc.kV * Lp[(IDX) * ls], rth, so, bad);           \
-        if (RB) first_bad |= (ok__ ? 0 : 1) << (IDX);      /* bit IDX: stage IDX + 2 outside the ranges */    \
+        rsf_stage_fast<RB>(cc, fs__, As__, dl__, th__,                                                     \
+                           RB ? kVb * (Lp[(IDX) * ls] - Lc) : cc.kV * Lp[(IDX) * ls], rth, so, bad);       \
     }
     // stage 2: the "stage in flight" is k1 itself (complete: no damping split)
     so.kt = k1t; so.d0 = k1m; so.c = 0.0;
@@ -577,34 +552,27 @@ __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const Ste
     k3m = so.km; k3t = so.kt;
     RSFM_STAGE(2, TB.a41 * k1t, TB.a41 * k1m, TB.a43);
     k4m = so.km; k4t = so.kt;
-    if (RB) { sv->km[0] = k4m; sv->kt[0] = k4t; }
     RSFM_STAGE(3, TB.a51 * k1t + TB.a53 * k3t, TB.a51 * k1m + TB.a53 * k3m, TB.a54);
     k5m = so.km; k5t = so.kt;
-    if (RB) { sv->km[1] = k5m; sv->kt[1] = k5t; }
     RSFM_STAGE(4, TB.a61 * k1t + TB.a64 * k4t, TB.a61 * k1m + TB.a64 * k4m, TB.a65);
     k6m = so.km; k6t = so.kt;
     bV = TB.b1 * k1v + TB.b6 * so.kv;
     eV = TB.e1 * k1v + TB.e6 * so.kv;
-    if (RB) { sv->km[2] = k6m; sv->kt[2] = k6t; sv->kv[0] = so.kv; }
     RSFM_STAGE(5, TB.a71 * k1t + TB.a74 * k4t + TB.a75 * k5t, TB.a71 * k1m + TB.a74 * k4m + TB.a75 * k5m, TB.a76);
     k7m = so.km; k7t = so.kt;
     bV += TB.b7 * so.kv; eV += TB.e7 * so.kv;
-    if (RB) { sv->km[3] = k7m; sv->kt[3] = k7t; sv->kv[1] = so.kv; }
     RSFM_STAGE(6, TB.a81 * k1t + TB.a84 * k4t + TB.a85 * k5t + TB.a86 * k6t,
                TB.a81 * k1m + TB.a84 * k4m + TB.a85 * k5m + TB.a86 * k6m, TB.a87);
     k8m = so.km; k8t = so.kt;
     bV += TB.b8 * so.kv; eV += TB.e8 * so.kv;
-    if (RB) { sv->km[4] = k8m; sv->kt[4] = k8t; sv->kv[2] = so.kv; }
     RSFM_STAGE(7, TB.a91 * k1t + TB.a94 * k4t + TB.a95 * k5t + TB.a96 * k6t + TB.a97 * k7t,
                TB.a91 * k1m + TB.a94 * k4m + TB.a95 * k5m + TB.a96 * k6m + TB.a97 * k7m, TB.a98);
     k9m = so.km; k9t = so.kt; k9v = so.kv;
     bV += TB.b9 * k9v; eV += TB.e9 * k9v;
-    if (RB) { sv->km[5] = k9m; sv->kt[5] = k9t; sv->kv[3] = k9v; }
     RSFM_STAGE(8, TB.a101 * k1t + TB.a104 * k4t + TB.a105 * k5t + TB.a106 * k6t + TB.a107 * k7t + TB.a108 * k8t,
                TB.a101 * k1m + TB.a104 * k4m + TB.a105 * k5m + TB.a106 * k6m + TB.a107 * k7m + TB.a108 * k8m, TB.a109);
     k10m = so.km; k10t = so.kt;
     bV += TB.b10 * so.kv; eV += TB.e10 * so.kv;
-    if (RB) { sv->km[6] = k10m; sv->kt[6] = k10t; sv->kv[4] = so.kv; }
     // stage 11 -> k2 slot
     RSFM_STAGE(9,
                TB.a111 * k1t + TB.a114 * k4t + TB.a115 * k5t + TB.a116 * k6t + TB.a117 * k7t + TB.a118 * k8t + TB.a119 * k9t,
@@ -612,7 +580,6 @@ __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const Ste
                TB.a1110);
     k2m = so.km; k2t = so.kt;
     bV += TB.b11 * so.kv; eV += TB.e11 * so.kv;
-    if (RB) { sv->km[7] = k2m; sv->kt[7] = k2t; sv->kv[5] = so.kv; }
     // stage 12 -> k3 slot, at x + h
     const double L12 = Lp[10 * ls];
     RSFM_STAGE(10,
@@ -660,24 +627,20 @@ __device__ __forceinline__ ChainConst rebase_const(const ChainConst &c, double l
 // out-of-line general-range step (one copy; taken only when a fast range condition failed).  The base
 // constants are passed by address and re-based inside, so that the caller keeps no second copy in memory.
 __device__ __noinline__ void dop853_step_general(const ChainConst *cc, double lam, double mu_ref_r, const StepIn *I,
-                                                 const double *Lp, int ls, double Lc, double rl, int first,
-                                                 const StepSave *sv, StepOut *O)
+                                                 const double *Lp, int ls, double Lc, double rl, StepOut *O)
 {
     const ChainConst cr = rebase_const(*cc, lam, mu_ref_r);
-    dop853_step_impl(cr, *I, Lp, ls, Lc, rl, first, *sv, *O);
+    dop853_step_impl(cr, *I, Lp, ls, Lc, rl, *O);
 }
 
-// out-of-line fast step in a re-based frame, for the step loop (one copy, so that the only inlined fast step
-// is the one of the fast interval and the hot path keeps its register budget).  Returns the first stage
-// whose arguments left the fast ranges, 0 if none did (then *O is the step).
-__device__ __forceinline__ int dop853_step_fast_rb(const ChainConst *cc, double lam, double mu_ref_r, const StepIn *I,
-                                                const double *Lp, int ls, double Lc, StepOut *O, StepSave *sv)
+// fast step in a re-based frame (rsf_interval_general); returns whether a stage left the fast ranges
+__device__ __forceinline__ bool dop853_step_fast_rb(const ChainConst *cc, double lam, double mu_ref_r, const StepIn *I,
+                                                    const double *Lp, int ls, double Lc, StepOut *O)
 {
     const ChainConst cr = rebase_const(*cc, lam, mu_ref_r);
     bool bad = false;
-    int first_bad = 0;
-    dop853_step_fast<true>(cr, *I, Lp, ls, cc->kV, Lc, *O, bad, first_bad, sv);
-    return first_bad;                                     // mask of the stages outside the ranges (bit s - 2)
+    dop853_step_fast<true>(cr, *I, Lp, ls, cc->kV, Lc, *O, bad);
+    return bad;
 }
 
 __device__ __noinline__ void rsf_rhs_general(const ChainConst *c, double lam, double mu_ref_r, double L, double mu,
@@ -709,8 +672,7 @@ __device__ __forceinline__ void rsf_rhs_checked(const ChainConst &c, const Chain
 __device__ __noinline__ void dop853_step_general(const ChainConst *cc, const StepIn *I, const double *Lp, int ls,
                                                  StepOut *O)
 {
-    StepSave none;
-    dop853_step_impl(*cc, *I, Lp, ls, 0.0, 1.0, 2, none, *O);
+    dop853_step_impl(*cc, *I, Lp, ls, 0.0, 1.0, *O);
 }
 
 __device__ __noinline__ void rsf_rhs_general(const ChainConst *c, double L, double mu, double th, double *res)
@@ -736,8 +698,7 @@ __device__ __forceinline__ void rsf_rhs_checked(const ChainConst &c, double L, d
 __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const StepIn &I, const double *Lp, int ls,
                                                  StepOut &O, bool &bad)
 {
-    int fb_unused = 0;
-    dop853_step_fast<false>(cc, I, Lp, ls, cc.kV, 0.0, O, bad, fb_unused, nullptr);
+    dop853_step_fast<false>(cc, I, Lp, ls, cc.kV, 0.0, O, bad);
 }
 
 #ifdef RSFM_DEBUG_COUNT
@@ -951,26 +912,19 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         const double f0s = fma(cr.w, th, -1.0), A0s = (mu - cr.mu_ref) * cr.inv_a;
         const bool start_in = fabs(f0s) * cr.qscale < 0.5 * 0.001953125 && fabs(A0s) < 0.5 * 0.015625;
         const bool try_fast = __any_sync(FULL_MASK, stepping && start_in);
-        int bad_mask = 0;                 // bit s - 2: stage s left the fast ranges
-        StepSave sv;
-        if (try_fast) bad_mask = dop853_step_fast_rb(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, &so, &sv);
-        else bad_mask = 1;
-        bad = bad_mask != 0;
+        if (try_fast) bad = dop853_step_fast_rb(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, &so);
+        else bad = true;
         // A step that STARTS well inside the fast ranges and leaves them at an internal stage is the trial step the
         // controller grew past the stability limit: it explodes and SciPy rejects it.  It is taken as rejected without
         // scoring it with the general-range stages (a rejected step shrinks by exactly 0.3 whatever its error was).
         // CPU-oracle count over eight stiff solves (profiles/microbench/forward_stiff_r1b.txt): of ~100,000 such steps
         // none is accepted by the exact arithmetic; were one ever, the retry at 0.3 h only costs a step.
-        // M.stiff_exact (RSFM_STIFF_EXACT=1) scores them exactly instead.
+        // M.stiff_exact (RSFM_STIFF_EXACT=1) scores them with the general-range step instead.
         const bool presumed_wild = bad && start_in && !M.stiff_exact;
-        if (stepping && bad && !presumed_wild)
-        {
-            const int first = __ffs(bad_mask) + 1;                  // first offending stage; < 6: nothing is reused
-            dop853_step_general(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, rl, first < 6 ? 2 : first, &sv, &so);
-        }
+        if (stepping && bad && !presumed_wild) dop853_step_general(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, rl, &so);
         RSFM_DBG(0, stepping) RSFM_DBG(1, stepping && try_fast) RSFM_DBG(2, stepping && bad)
         RSFM_DBGW(3, stepping) RSFM_DBGW(4, stepping && bad) RSFM_DBGW(5, stepping && try_fast)
-        RSFM_DBG(8, stepping && lam != 1.0) RSFM_DBG(9, stepping && bad && (__ffs(bad_mask) + 1) > 5)
+        RSFM_DBG(8, stepping && lam != 1.0) RSFM_DBG(9, stepping && bad && start_in)
         // err <= 1   <=>   h^2 errA^2 <= den3   (no sqrt, no division; NaN rejects; 0 <= 0 accepts).
         // errA < 1e140 keeps the squares finite: an unstable step whose error norm overflows must be
         // rejected (dop853.f gets inf * 0 = NaN there), not pass as inf <= inf.

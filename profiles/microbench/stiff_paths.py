@@ -10,7 +10,7 @@ n = 4000
 m = pkg.RateStateModel(number_time_steps=n, end_time=n * 0.1)
 m.loading, m.vstep_period, m.vstep_factor = "vstep", 100.0, 10.0
 names = ["lane-steps", "lane-steps fast tried", "lane-steps general", "warp-steps", "warp-steps general", "warp-steps fast tried",
-         "lane-steps accepted", "warp fast intervals", "lane-steps raised level", "lane-steps raised+general", "lane rejected+general"]
+         "lane-steps accepted", "warp fast intervals", "lane-steps raised level", "lane-steps out of range from an in-range start", "lane rejected + out of range"]
 for label, dc_h in (("all 0.05", np.full(2048, 0.05)), ("U(0.03,0.08)", np.random.default_rng(0).uniform(0.03, 0.08, 2048))):
     buf = (ctypes.c_ulonglong * 16)()
     lib.rsfm_debug_counters(buf, 1)
