@@ -917,7 +917,7 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         // A step that STARTS well inside the fast ranges and leaves them at an internal stage is the trial step the
         // controller grew past the stability limit: it explodes and SciPy rejects it.  It is taken as rejected without
         // scoring it with the general-range stages (a rejected step shrinks by exactly 0.3 whatever its error was).
-        // CPU-oracle count over eight stiff solves (profiles/microbench/forward_stiff_r1b.txt): of ~100,000 such steps
+        // CPU-oracle count over seven stiff solves (profiles/microbench/forward_stiff_r1b.txt): of ~49,000 such steps
         // none is accepted by the exact arithmetic; were one ever, the retry at 0.3 h only costs a step.
         // M.stiff_exact (RSFM_STIFF_EXACT=1) scores them with the general-range step instead.
         const bool presumed_wild = bad && start_in && !M.stiff_exact;
