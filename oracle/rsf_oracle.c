@@ -15,6 +15,23 @@
 #include <stdatomic.h>
 
 /* RateStateModel.py:5-11,167-184 and the solver settings of :374 */
+/* Optional step instrumentation (tests/test_stiff_rule.py; single-threaded use only).  After every attempted
+ * DOP853 step the hook receives the step, its error estimate and, relative to the limits of the CUDA fast step
+ * (|f'| (1 + b/a) < 2^-9, |A'| < 2^-6 in the frame re-based on the load level at the start of the step), the excess
+ * of the series arguments at the start of the step and the largest excess at any of its stages. */
+static orc_step_hook_t g_hook = 0;
+static double g_hook_lam = 1.0, g_hook_max = 0.0;
+void orc_set_step_hook(orc_step_hook_t hook) { g_hook = hook; }
+
+static double hook_ratio(const orc_model *m, const double y[3])
+{
+    const double fp = g_hook_lam * m->V_ref * y[1] / m->Dc - 1.0;
+    const double Ap = (y[0] - (m->mu_ref + (m->a - m->b) * log(g_hook_lam))) / m->a;
+    const double r1 = fabs(fp) * (1.0 + m->b / m->a) / 0.001953125, r2 = fabs(Ap) / 0.015625;
+    const double r = r1 > r2 ? r1 : r2;
+    return r == r ? r : HUGE_VAL;
+}
+
 void orc_model_defaults(orc_model *m)
 {
     m->a = 0.011; m->b = 0.014; m->mu_ref = 0.6; m->V_ref = 1.0; m->k1 = 1.0e-7;
@@ -47,6 +64,7 @@ void orc_rhs(const orc_model *m, double t, const double y[3], double dydt[3])
     const double V_ref = m->V_ref, a = m->a, b = m->b, dc = m->Dc;
     const double kprime = 1e-2 * 10 / dc;                       /* :324 */
     const double V_l = loading_velocity(m, t);                  /* :329 */
+    if (g_hook) { const double r = hook_ratio(m, y); if (r > g_hook_max) g_hook_max = r; }
     const double temp = 1 / a * (y[0] - m->mu_ref - b * log(V_ref * y[1] / dc));  /* :336 */
     const double v = V_ref * exp(temp);                         /* :337 */
     dydt[1] = 1. - v * y[1] / dc;                               /* :340 */
@@ -121,6 +139,8 @@ int orc_dop853_call(const orc_model *m, double *t, double y[3], double xend,
         if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = 1; }
         nstep++;
         st->nstep++;
+        double hook_start = 0.0;
+        if (g_hook) { g_hook_lam = loading_velocity(m, x) / m->V_ref; hook_start = hook_ratio(m, y); g_hook_max = 0.0; }
         for (int i = 0; i < n; i++) y1[i] = y[i] + h * DP_A2_1 * k1[i];
         orc_rhs(m, x + DP_C2 * h, y1, k2);
         for (int i = 0; i < n; i++) y1[i] = y[i] + h * (DP_A3_1 * k1[i] + DP_A3_2 * k2[i]);
@@ -178,6 +198,7 @@ int orc_dop853_call(const orc_model *m, double *t, double y[3], double xend,
         double deno = err + 0.01 * err2;
         if (deno <= 0.0) deno = 1.0;
         err = fabs(h) * err * sqrt(1.0 / (n * deno));
+        if (g_hook) g_hook(x, h, err, hook_start, g_hook_max);
         /* step-size controller */
         double fac11 = pow(err, expo1);
         double fac = fac11 / pow(facold, beta);
