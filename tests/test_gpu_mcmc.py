@@ -411,3 +411,50 @@ def test_out_of_bounds_walk_with_idle_warps_and_pooled_sums(cuda, pkg):
                       adapt_start=1000, adapt_interval=3, **kw)
     out_p = pooled.sample(False)
     assert np.array_equal(out_p, out)                          # no adaptation before adapt_start: same chains
+
+
+@pytest.mark.parametrize("spec_depth", ["", "0"])
+def test_stiff_velocity_step_chains_replay_through_oracle(cuda, pkg, orc, monkeypatch, spec_depth):
+    """cfg-4 style at reduced size (velocity steps x10, Dc ~ 0.05: stability-limited DOP853): the stiff kernel
+    variant inside the sampler -- speculative kernel and, with RSFM_SPEC_DEPTH=0, the sequential one.  The draws the
+    kernel used are replayed on the CPU oracle: same accept / reject decision at every step."""
+    import ctypes as C
+    torch = cuda
+    if spec_depth:
+        monkeypatch.setenv("RSFM_SPEC_DEPTH", spec_depth)
+    n, t_end, period, factor = 400, 40.0, 10.0, 10.0
+    om = orc.make_model(Dc=0.05, number_time_steps=n, end_time=t_end, loading=orc.LOAD_VSTEP, vstep_period=period,
+                        vstep_factor=factor)
+    _, acc_true, _ = orc.forward(om)
+    rng = np.random.default_rng(11)
+    data = acc_true + 0.2 * np.abs(acc_true) * rng.standard_normal(acc_true.size)
+    lib = pkg._lib.load()
+    model = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
+    model.loading, model.vstep_period, model.vstep_factor = "vstep", period, factor
+    cfg = model.to_cfg()
+    cfg.n_params, cfg.n_prior_len = 1, 3
+    cfg.lo[0], cfg.hi[0] = 0.03, 0.09
+    c, ns = 32, 12
+    dev = torch.device("cuda", 0)
+    q0 = torch.full((1, c), 0.06, dtype=torch.float64, device=dev)
+    data_t = torch.from_numpy(data).to(dev)
+    h = lib.rsfm_create(C.byref(cfg), c, 77, 0)
+    assert h
+    try:
+        pkg._lib.check(lib.rsfm_init(h, q0.data_ptr(), data_t.data_ptr(), None))
+        samples = torch.empty((ns, 1, c), dtype=torch.float64, device=dev)
+        s2 = torch.empty((ns, c), dtype=torch.float64, device=dev)
+        acc = torch.empty((ns, c), dtype=torch.uint8, device=dev)
+        draws = torch.empty((ns, 3, c), dtype=torch.float64, device=dev)
+        pkg._lib.check(lib.rsfm_run(h, ns, samples.data_ptr(), s2.data_ptr(), acc.data_ptr(), draws.data_ptr(), None))
+        torch.cuda.synchronize()
+    finally:
+        lib.rsfm_destroy(h)
+    samples, s2, acc, draws = (x.cpu().numpy() for x in (samples, s2, acc, draws))
+    assert 0 < acc.mean() < 1
+    for ch in (0, 5, 31):
+        prop, u, gam = draws[:, 0, ch], draws[:, 1, ch], draws[:, 2, ch]
+        chain_o, s2_o, acc_o, _, _ = orc.chain_replay(om, data, 0.06, 0.03, 0.09, 3, ns, prop, np.nan_to_num(u, nan=0.5), gam)
+        assert np.array_equal(acc[:, ch], acc_o)
+        assert np.array_equal(samples[:, 0, ch], chain_o[1:])
+        assert np.allclose(s2[:, ch], s2_o[1:], rtol=1e-4, atol=0)          # SSE to ~1e-6 in the stiff regime
