@@ -294,3 +294,23 @@ def test_stiff_variant_on_reference_loading_and_both_variants_on_vstep(cuda, pkg
     # same controller semantics: attempted-step counts of the variants differ by well under 1 %
     for v in ("1", "1x"):
         assert np.all(np.abs(res["0"][1].astype(float) - res[v][1]) <= 0.01 * res["0"][1]), v
+
+
+def test_stiff_variant_per_chain_a_b(cuda, pkg, orc):
+    """Velocity-step loading with per-chain (a, b, Dc) -- the forward solves of a joint-posterior sampler in the stiff
+    regime: the re-based reference friction mu_ref + (a - b) ln(lambda) differs from chain to chain."""
+    rng = np.random.default_rng(5)
+    c, n, t_end = 12, 600, 60.0
+    a = rng.uniform(0.008, 0.013, c)
+    b = rng.uniform(0.012, 0.018, c)
+    dc = np.concatenate([rng.uniform(0.04, 0.3, c // 2), rng.uniform(1.0, 300.0, c - c // 2)])
+    m = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
+    m.loading, m.vstep_period, m.vstep_factor = "vstep", 15.0, 10.0
+    out = m.evaluate_batch(dc, a=a, b=b)
+    assert np.all(out["status"].cpu().numpy() == 0)
+    acc_g = out["acc"].t().cpu().numpy()
+    for i in range(c):
+        _, acc_o, _ = orc.forward(orc.make_model(Dc=dc[i], a=a[i], b=b[i], number_time_steps=n, end_time=t_end,
+                                                 loading=orc.LOAD_VSTEP, vstep_period=15.0, vstep_factor=10.0))
+        scale = np.max(np.abs(acc_o))
+        assert np.max(np.abs(acc_g[i] - acc_o)) <= 2e-5 * scale, (i, dc[i])
