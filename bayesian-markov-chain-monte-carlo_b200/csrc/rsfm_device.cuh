@@ -21,7 +21,7 @@
 //   * sqrt- and division-free accept / hinit decisions; exact early rejection against an SSE bound.
 //
 // Layout of this file: TMA staging of the series; the RHS (rsf_rhs) and the two DOP853 step forms (dop853_step_impl:
-// general range, optionally resumed from a stage; dop853_step_fast: short dependency chain); the general interval
+// general range; dop853_step_fast: short dependency chain); the general interval
 // path in its two variants -- rsf_interval_plain (SciPy's controller as written; inline in the 168-register kernels,
 // out of line in the speculative one) and rsf_interval_general (stiff variant for velocity-step loading: re-based
 // friction law, exploding trial steps not scored, SFU-seeded controller root) -- and rsf_solve_mode, the output loop

@@ -129,10 +129,11 @@ static ModelK make_model(const rsfm_cfg *c)
 }
 
 // Which instantiation of the solver runs: the kernels exist twice.  VS = false keeps the general
-// (state-by-state) interval path inline exactly as the non-stiff configurations were tuned with it; VS = true
-// calls the out-of-line rsf_interval_general, which re-bases the friction law on the current load level and
-// resumes the general-range step from the first stage that left the fast ranges -- the variant for
-// velocity-step loading (cfg 4), where nearly every interval is a general one.  RSFM_STIFF=0/1 overrides.
+// (state-by-state) interval path exactly as the non-stiff configurations were tuned with it (rsf_interval_plain);
+// VS = true uses rsf_interval_general, which re-bases the friction law on the current load level, does not score
+// the exploding trial steps of the stability-limited regime and has a cheaper step-size controller -- the variant
+// for velocity-step loading (cfg 4), where nearly every interval is a general one.
+// RSFM_STIFF=0/1 overrides (tests, tuning).
 static bool stiff_variant(const ModelK &M)
 {
     if (const char *e = getenv("RSFM_STIFF")) return atoi(e) != 0;       // tuning / experiments only
