@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("RSFM_LIB") or os.path.join(_PKG_DIR, "librsfm.so")   # RSFM_LIB: tuning builds only
+LIB_PATH = os.path.join(_PKG_DIR, "librsfm.so")
 
 RSFM_MAX_PARAMS = 3
 
@@ -16,6 +16,10 @@ LOAD_SINE_DECAY, LOAD_VSTEP = 0, 1
 INTEG_PARITY, INTEG_CARRY = 0, 1
 ADAPT_NONE, ADAPT_COMPAT, ADAPT_POOLED = 0, 1, 2
 CHAIN_OK, CHAIN_NMAX, CHAIN_HSMALL, CHAIN_NONFINITE = 0, 2, 3, 4
+OBS_ACC, OBS_MU = 0, 1
+VARIANT_AUTO, VARIANT_DEFAULT, VARIANT_STIFF = 0, 1, 2
+POOL_GROUP, POOL_ROWS = 1024, 16
+ABI_VERSION = 2
 
 # every symbol include/rsfm.h declares (tests check the library exports them all)
 EXPORTED_SYMBOLS = (
@@ -24,6 +28,8 @@ EXPORTED_SYMBOLS = (
     "rsfm_run_deterministic", "rsfm_spec_depth", "rsfm_get_state", "rsfm_set_state", "rsfm_iteration",
     "rsfm_get_totals", "rsfm_get_suffstats", "rsfm_set_proposal_chol", "rsfm_chain_diagnostics",
     "rsfm_kde_grid", "rsfm_measure_fp64_peak", "rsfm_trim",
+    "rsfm_pooled_groups", "rsfm_pooled_partials", "rsfm_pooled_update",
+    "rsfm_philox_raw", "rsfm_philox_draws", "rsfm_rhs_eval", "rsfm_get_ring", "rsfm_set_ring",
 )
 
 
@@ -41,6 +47,8 @@ class RsfmCfg(C.Structure):
         ("loading", C.c_int32), ("integ_mode", C.c_int32), ("n_params", C.c_int32),
         ("n_prior_len", C.c_int32), ("adapt_interval", C.c_int32), ("adapt_mode", C.c_int32),
         ("spec_depth", C.c_int32),
+        ("observable", C.c_int32), ("solver_variant", C.c_int32), ("stiff_exact", C.c_int32),
+        ("block_threads", C.c_int32),
     ]
 
 
@@ -102,8 +110,24 @@ def load():
     lib.rsfm_measure_fp64_peak.restype = C.c_int
     lib.rsfm_trim.argtypes = []
     lib.rsfm_trim.restype = C.c_int
-    if lib.rsfm_abi_version() != 1:
-        raise RsfmError(f"librsfm ABI version {lib.rsfm_abi_version()} != 1")
+    lib.rsfm_get_ring.argtypes = [vp, vp, vp]
+    lib.rsfm_get_ring.restype = C.c_int
+    lib.rsfm_set_ring.argtypes = [vp, vp, vp]
+    lib.rsfm_set_ring.restype = C.c_int
+    lib.rsfm_pooled_groups.argtypes = [vp]
+    lib.rsfm_pooled_groups.restype = C.c_int
+    lib.rsfm_pooled_partials.argtypes = [vp, vp, i32, vp]
+    lib.rsfm_pooled_partials.restype = C.c_int
+    lib.rsfm_pooled_update.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp]
+    lib.rsfm_pooled_update.restype = C.c_int
+    lib.rsfm_philox_raw.argtypes = [vp, vp, i32, vp]
+    lib.rsfm_philox_raw.restype = C.c_int
+    lib.rsfm_philox_draws.argtypes = [u64, u64, i32, C.c_uint32, i32, dbl, vp, vp]
+    lib.rsfm_philox_draws.restype = C.c_int
+    lib.rsfm_rhs_eval.argtypes = [cfgp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.rsfm_rhs_eval.restype = C.c_int
+    if lib.rsfm_abi_version() != ABI_VERSION:
+        raise RsfmError(f"librsfm ABI version {lib.rsfm_abi_version()} != {ABI_VERSION}: rebuild the library")
     _lib = lib
     return lib
 

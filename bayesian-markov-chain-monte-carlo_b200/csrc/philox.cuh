@@ -69,7 +69,9 @@ __device__ __forceinline__ void philox_normal2(PhiloxKey key, unsigned long long
 
 // Unit-scale Gamma(shape), shape > 1: Marsaglia & Tsang (2000), the algorithm
 // behind NumPy's legacy standard_gamma that scipy.stats.gamma.rvs draws from.
-__device__ __forceinline__ double philox_gamma(PhiloxKey key, unsigned long long chain, uint32_t iter, double shape)
+// `tries` (optional, test hook): number of attempts consumed.
+__device__ __forceinline__ double philox_gamma(PhiloxKey key, unsigned long long chain, uint32_t iter, double shape,
+                                               uint32_t *tries = nullptr)
 {
     const double d = shape - 1.0 / 3.0;
     const double c = 1.0 / sqrt(9.0 * d);
@@ -77,6 +79,7 @@ __device__ __forceinline__ double philox_gamma(PhiloxKey key, unsigned long long
         double x, unused;
         philox_normal2(key, chain, iter, 4u + 2u * j, x, unused);
         double v = 1.0 + c * x;
+        if (tries) *tries = j + 1u;
         if (v <= 0.0) continue;
         v = v * v * v;
         const double u = philox_uniform(key, chain, iter, 5u + 2u * j);

@@ -45,6 +45,7 @@ struct ModelK {
     double vstep_lnf, vstep_rfac;      // log(vstep_factor), 1/vstep_factor: host-computed (re-basing, see rsf_interval_general)
     double vstep_rper;                 // 1/vstep_period (vstep_index)
     int stiff_exact;                   // stiff variant: score every step that left the fast ranges (tuning / tests)
+    int observable;                    // RSFM_OBS_ACC (reference) / RSFM_OBS_MU
     int n_out, nmax, damping, loading, integ_mode;
 };
 
@@ -155,6 +156,15 @@ struct SeriesStage {
             if (n > SERIES_TILE) issue(1);
         }
         __syncthreads();                               // odd-tail plain stores visible
+        if (resident) {
+            // A resident series (n <= 1024: one or two tiles, fetched once per kernel) is waited for here, by every
+            // thread, before the first pass: a warp may leave the output loop of any pass early (all its lanes
+            // rejected / inactive), so no later point of the loop is reached by every warp of the block.  Each
+            // barrier completes exactly one phase in the kernel's lifetime.
+            while (!mbar_try_wait(&bar[0], 0u)) { }
+            if (n > SERIES_TILE) { while (!mbar_try_wait(&bar[1], 0u)) { } }
+            loaded = true;
+        }
     }
 
     // value data[k]; in streaming mode entering a tile recycles the buffer two tiles back
@@ -164,8 +174,8 @@ struct SeriesStage {
         return at_staging(k);
     }
 
-    // first pass over a resident series / streamed series: out of line, so that the output loop of the solver
-    // stays compact (every thread of the block calls it with the same k: it contains block barriers)
+    // streamed series (n > 1024): out of line, so that the output loop of the solver stays compact (every thread
+    // of the block calls it with the same k: it contains block barriers)
     __device__ __noinline__ double at_staging(int k)
     {
         const int tile = k / SERIES_TILE;
@@ -181,7 +191,6 @@ struct SeriesStage {
             }
             if (tile & 1) { while (!mbar_try_wait(&bar[1], par1)) { } par1 ^= 1u; }
             else          { while (!mbar_try_wait(&bar[0], par0)) { } par0 ^= 1u; }
-            if (resident && (tile + 1) * SERIES_TILE >= n) loaded = true;
         }
         return buf[(tile & 1) * SERIES_TILE + off];
     }
@@ -1198,10 +1207,13 @@ __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, do
     out.filled = M.n_out;
     out.nrhs = 0; out.nstep = 0;
     double sse = 0.0, xtx = 0.0;
-    if (have_data) { const double d0 = series.at(0); sse = d0 * d0; }   // acc[0] = 0  (:371)
-    if (acc_out && active) acc_out[0] = 0.0;
+    // observable: acc (reference, acc[0] = 0, :371) or the friction series mu (mu[0] = mu_ref, :367)
+    const bool obs_mu = M.observable == RSFM_OBS_MU;
+    const double obs0 = obs_mu ? M.mu_ref : 0.0;
+    if (have_data) { const double d0 = obs0 - series.at(0); sse = d0 * d0; }
+    if (acc_out && active) acc_out[0] = obs0;
     if (t_out && active) t_out[0] = t;
-    if (acc_ref && active) { const double x0 = (0.0 - acc_ref[0]) / fd_den; xtx = x0 * x0; }
+    if (acc_ref && active) { const double x0 = (obs0 - acc_ref[0]) / fd_den; xtx = x0 * x0; }
 
     rsf_rhs_checked(cc, loading_of(M, t), mu, th, rth, k1m, k1t, k1v);
     out.nrhs++;
@@ -1344,6 +1356,7 @@ __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, do
             const double qd = dv * inv_dt;                        // (V_k - V_{k-1}) / delta_t  (:388):
             accv = fma(fma(-qd, M.delta_t, dv), inv_dt, qd);      // reciprocal + one correction = correctly rounded
             vprev = V;
+            if (obs_mu) accv = mu;                                // mu[k] = r.y[0]  (:385)
             if (failed && out.filled == M.n_out) out.filled = k + 1;
         }
         acc_pending = accv; dk_pending = dk; have_pending = have_data;

@@ -108,7 +108,20 @@ static int check_cfg(const rsfm_cfg *c)
         return set_err(RSFM_ERR_INVALID, "vstep_factor must be positive%s", "");
     if (!(c->rtol > 0.0) || !(c->atol >= 0.0)) return set_err(RSFM_ERR_INVALID, "rtol must be positive and atol non-negative%s", "");
     if (!(c->a > 0.0) || !(c->V_ref > 0.0)) return set_err(RSFM_ERR_INVALID, "a and V_ref must be positive%s", "");
-    if (c->adapt_interval < 2 || c->adapt_interval > 64) return set_err(RSFM_ERR_INVALID, "adapt_interval must be in [2, 64]%s", "");
+    // the per-chain sample ring of the reference's windowed update is the only user of adapt_interval in here
+    // (the reference accepts any value and, with list priors, never uses it: MCMC.py:58, 523-527)
+    if (c->adapt_mode == RSFM_ADAPT_COMPAT && (c->adapt_interval < 2 || c->adapt_interval > 64))
+        return set_err(RSFM_ERR_INVALID, "adapt_interval must be in [2, 64] with RSFM_ADAPT_COMPAT%s", "");
+    if (c->adapt_mode != RSFM_ADAPT_NONE && c->adapt_mode != RSFM_ADAPT_COMPAT && c->adapt_mode != RSFM_ADAPT_POOLED)
+        return set_err(RSFM_ERR_INVALID, "bad adapt_mode%s", "");
+    if (c->observable != RSFM_OBS_ACC && c->observable != RSFM_OBS_MU)
+        return set_err(RSFM_ERR_INVALID, "bad observable selector%s", "");
+    if (c->solver_variant < RSFM_VARIANT_AUTO || c->solver_variant > RSFM_VARIANT_STIFF)
+        return set_err(RSFM_ERR_INVALID, "bad solver_variant%s", "");
+    if (c->block_threads != 0 && c->block_threads != 32 && c->block_threads != 64 && c->block_threads != 96 &&
+        c->block_threads != 128)
+        return set_err(RSFM_ERR_INVALID, "block_threads must be 0, 32, 64, 96 or 128%s", "");
+    if (c->spec_depth < 0 || c->spec_depth > 5) return set_err(RSFM_ERR_INVALID, "spec_depth must be in [0, 5]%s", "");
     return RSFM_OK;
 }
 
@@ -124,7 +137,8 @@ static ModelK make_model(const rsfm_cfg *c)
     M.vstep_lnf = (c->loading == RSFM_LOAD_VSTEP) ? log(c->vstep_factor) : 0.0;
     M.vstep_rfac = (c->loading == RSFM_LOAD_VSTEP) ? 1.0 / c->vstep_factor : 1.0;
     M.vstep_rper = (c->loading == RSFM_LOAD_VSTEP) ? 1.0 / c->vstep_period : 1.0;
-    if (const char *e = getenv("RSFM_STIFF_EXACT")) M.stiff_exact = atoi(e) != 0;
+    M.stiff_exact = c->stiff_exact != 0;
+    M.observable = c->observable;
     return M;
 }
 
@@ -133,11 +147,12 @@ static ModelK make_model(const rsfm_cfg *c)
 // VS = true uses rsf_interval_general, which re-bases the friction law on the current load level, does not score
 // the exploding trial steps of the stability-limited regime and has a cheaper step-size controller -- the variant
 // for velocity-step loading (cfg 4), where nearly every interval is a general one.
-// RSFM_STIFF=0/1 overrides (tests, tuning).
-static bool stiff_variant(const ModelK &M)
+// cfg->solver_variant overrides the choice (tests, tuning).
+static bool stiff_variant(const rsfm_cfg *c)
 {
-    if (const char *e = getenv("RSFM_STIFF")) return atoi(e) != 0;       // tuning / experiments only
-    return M.loading == RSFM_LOAD_VSTEP;
+    if (c->solver_variant == RSFM_VARIANT_DEFAULT) return false;
+    if (c->solver_variant == RSFM_VARIANT_STIFF) return true;
+    return c->loading == RSFM_LOAD_VSTEP;
 }
 
 // The stiff variant runs one-warp blocks: with a streamed series (cfg 4) the block barriers at tile boundaries
@@ -148,12 +163,9 @@ static const int STIFF_BLOCK = 32;
 
 // chains per block: small batches are spread over more SMs (the kernel is latency
 // bound there), large batches use 128-thread blocks.
-static int pick_block(int C)
+static int pick_block(int C, const rsfm_cfg *c)
 {
-    if (const char *e = getenv("RSFM_BLOCK")) {          // tuning / experiments only
-        const int b = atoi(e);
-        if (b == 32 || b == 64 || b == 96 || b == 128) return b;
-    }
+    if (c->block_threads) return c->block_threads;       // tuning / experiments only
     if (C <= 148 * 32) return 32;
     if (C <= 148 * 64 * 2) return 64;
     return 128;
@@ -374,13 +386,13 @@ extern "C" int rsfm_forward_batch(const rsfm_cfg *cfg, int32_t C, const double *
     if (data_dev && ((uintptr_t)data_dev & 15)) return set_err(RSFM_ERR_INVALID, "forward_batch: data_dev must be 16-byte aligned%s", "");
     rc = require_device();
     if (rc) return rc;
-    const int block = pick_block(C);
+    const int block = pick_block(C, cfg);
     const int grid = (C + block - 1) / block;
     const ModelK M = make_model(cfg);
     const double *nom = nullptr;
     rc = get_nominal_table(M, (cudaStream_t)stream, &nom);
     if (rc) return rc;
-    const bool vs = stiff_variant(M);
+    const bool vs = stiff_variant(cfg);
     const int vgrid = (C + STIFF_BLOCK - 1) / STIFF_BLOCK;
 #define RSFM_FWD(MB, VS)                                                                                              \
     rsf_forward_kernel<MB, VS><<<VS ? vgrid : grid, VS ? STIFF_BLOCK : block, 0, (cudaStream_t)stream>>>(            \
@@ -452,7 +464,7 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_q = take(sizeof(double) * d * Cz), o_sse = take(sizeof(double) * Cz), o_s2 = take(sizeof(double) * Cz);
-    const size_t o_chol = take(sizeof(double) * tri(d) * Cz), o_ring = take(sizeof(double) * cfg->adapt_interval * Cz);
+    const size_t o_chol = take(sizeof(double) * tri(d) * Cz), o_ring = take(sizeof(double) * (cfg->adapt_mode == RSFM_ADAPT_COMPAT ? cfg->adapt_interval : 1) * Cz);
     const size_t o_suff = take(sizeof(double) * (d + tri(d)) * Cz), o_data = take(sizeof(double) * ((size_t)cfg->n_out + 2));
     const size_t o_nom = take(sizeof(double) * NOM_STRIDE * (size_t)cfg->n_out);
     const size_t o_acc = take(sizeof(unsigned int) * Cz), o_status = take(sizeof(int) * Cz);
@@ -632,7 +644,7 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     CUDA_TRY(cudaMemsetAsync(s->d.urhs, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.ustep, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * (d + tri(d)) * (size_t)C, stream));
-    const int block = pick_block(C), grid = (C + block - 1) / block;
+    const int block = pick_block(C, &s->cfg), grid = (C + block - 1) / block;
     const ModelK M = make_model(&s->cfg);
     loading_table_kernel<<<1, 1024, 0, stream>>>(M, s->d.nom);
     CUDA_TRY(cudaGetLastError());
@@ -640,8 +652,8 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
 #define RSFM_INIT(D, VS)                                                                                              \
     rsf_init_kernel<D, VS><<<VS ? (C + STIFF_BLOCK - 1) / STIFF_BLOCK : grid, VS ? STIFF_BLOCK : block, 0, stream>>>( \
         M, C, pass, s->cfg.a, s->cfg.b, s->cfg.n_prior_len, s->d, s->scratch)
-        if (d == 1) { if (stiff_variant(M)) RSFM_INIT(1, true); else RSFM_INIT(1, false); }
-        else { if (stiff_variant(M)) RSFM_INIT(3, true); else RSFM_INIT(3, false); }
+        if (d == 1) { if (stiff_variant(&s->cfg)) RSFM_INIT(1, true); else RSFM_INIT(1, false); }
+        else { if (stiff_variant(&s->cfg)) RSFM_INIT(3, true); else RSFM_INIT(3, false); }
 #undef RSFM_INIT
         CUDA_TRY(cudaGetLastError());
     }
@@ -1213,8 +1225,7 @@ static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
     if (A.deterministic) return 0;
     if (s->cfg.adapt_mode == RSFM_ADAPT_COMPAT && s->cfg.n_params != 1) return 0;
     if (s->cfg.n_out > 2 * SERIES_TILE) return 0;          // streamed series: block barriers, no speculation
-    int want = s->cfg.spec_depth;
-    if (const char *e = getenv("RSFM_SPEC_DEPTH")) want = atoi(e);
+    const int want = s->cfg.spec_depth;
     if (want == 1) return 0;
     if (want >= 2 && want <= 5) return want;
     int sms = 148;
@@ -1240,14 +1251,14 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
 {
     if (!s->initialised) return set_err(RSFM_ERR_STATE, "sampler used before rsfm_init%s", "");
     if (A.n_iters < 1) return set_err(RSFM_ERR_INVALID, "n_iters < 1%s", "");
-    const int C = s->C, block = pick_block(C), grid = (C + block - 1) / block;
+    const int C = s->C, block = pick_block(C, &s->cfg), grid = (C + block - 1) / block;
     A.iter0 = s->iteration; A.seed = s->seed; A.chain_id0 = s->chain_id0;
     A.a0 = s->cfg.a; A.b0 = s->cfg.b; A.n0 = s->cfg.n0;
     for (int i = 0; i < RSFM_MAX_PARAMS; i++) { A.lo[i] = s->cfg.lo[i]; A.hi[i] = s->cfg.hi[i]; }
     A.adapt_mode = s->cfg.adapt_mode; A.adapt_interval = s->cfg.adapt_interval;
     const ModelK M = make_model(&s->cfg);
     const int g = pick_spec_depth(s, A);
-    const bool vs = stiff_variant(M);
+    const bool vs = stiff_variant(&s->cfg);
     if (g >= 2) {
         const long long threads = (long long)C << g;
         const int sblock = threads <= 148 * 32 * 4 ? 32 : 128;
@@ -1336,6 +1347,25 @@ extern "C" int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double
     return RSFM_OK;
 }
 
+static int ring_copy(rsfm_sampler *s, double *dst, const double *src, cudaStream_t st, const char *who)
+{
+    if (!s || !dst || !src) return set_err(RSFM_ERR_INVALID, "%s: NULL argument", who);
+    if (s->cfg.adapt_mode != RSFM_ADAPT_COMPAT) return set_err(RSFM_ERR_INVALID, "%s: the sampler keeps a ring only with RSFM_ADAPT_COMPAT", who);
+    CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)s->cfg.adapt_interval * (size_t)s->C, cudaMemcpyDeviceToDevice, st));
+    return RSFM_OK;
+}
+
+extern "C" int rsfm_get_ring(rsfm_sampler *s, double *ring_dev, void *stream)
+{
+    return ring_copy(s, ring_dev, s ? s->d.ring : nullptr, (cudaStream_t)stream, "rsfm_get_ring");
+}
+
+extern "C" int rsfm_set_ring(rsfm_sampler *s, const double *ring_dev, void *stream)
+{
+    if (s && !s->initialised) return set_err(RSFM_ERR_STATE, "rsfm_set_ring before rsfm_init%s", "");
+    return ring_copy(s, s ? s->d.ring : nullptr, ring_dev, (cudaStream_t)stream, "rsfm_set_ring");
+}
+
 // ---------------------------------------------------------------------------
 // work totals (forward solves, RHS evaluations, steps, accepted moves, failed chains)
 // ---------------------------------------------------------------------------
@@ -1369,10 +1399,12 @@ extern "C" int rsfm_get_totals(rsfm_sampler *s, uint64_t *out_host, void *stream
 // ---------------------------------------------------------------------------
 // pooled sufficient statistics: sum over chains with warp shuffles
 // ---------------------------------------------------------------------------
-__global__ void suffstats_kernel(int C, int rows, const double *__restrict__ suff, double *__restrict__ out)
+__global__ void suffstats_kernel(int C, int rows, double n, const double *__restrict__ suff, double *__restrict__ out)
 {
-    // one block per row; grid-stride not needed: blockDim = 1024
+    // one block per row; grid-stride not needed: blockDim = 1024.  out[0] = n, out[1 + r] = sum of row r
     const int r = blockIdx.x;
+    if (r == 0 && threadIdx.x == 0) out[0] = n;
+    out += 1;
     double acc = 0.0;
     for (int c = threadIdx.x; c < C; c += blockDim.x) acc += suff[(size_t)r * C + c];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL_MASK, acc, o);
@@ -1392,11 +1424,9 @@ extern "C" int rsfm_get_suffstats(rsfm_sampler *s, double *out_dev, int32_t rese
     if (!s || !out_dev) return set_err(RSFM_ERR_INVALID, "rsfm_get_suffstats: NULL argument%s", "");
     cudaStream_t st = (cudaStream_t)stream_;
     const int d = s->cfg.n_params, rows = d + tri(d);
-    suffstats_kernel<<<rows, 1024, 0, st>>>(s->C, rows, s->d.suff, out_dev + 1);
-    CUDA_TRY(cudaGetLastError());
     const double n = (double)s->suff_count * (double)s->C;
-    CUDA_TRY(cudaMemcpyAsync(out_dev, &n, sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));      // `n` lives on this stack frame
+    suffstats_kernel<<<rows, 1024, 0, st>>>(s->C, rows, n, s->d.suff, out_dev);
+    CUDA_TRY(cudaGetLastError());
     if (reset) {
         CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * rows * (size_t)s->C, st));
         s->suff_count = 0;
@@ -1419,6 +1449,223 @@ extern "C" int rsfm_set_proposal_chol(rsfm_sampler *s, const double *chol_host, 
     CUDA_TRY(cudaMemcpyAsync(s->reduce_out, chol_host, sizeof(double) * T, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     broadcast_chol_kernel<<<(s->C + 255) / 256, 256, 0, st>>>(s->C, T, s->reduce_out, s->d.chol);
+    CUDA_TRY(cudaGetLastError());
+    return RSFM_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// pooled adaptation on the device: sharding-invariant partial sums, moments, Cholesky, install
+// ---------------------------------------------------------------------------
+// One block per group of RSFM_POOL_GROUP chains aligned on the GLOBAL chain id; every reduction runs in a fixed
+// order (shuffle tree inside a warp, then the 32 warp sums through the same tree), so a group's row is the same
+// bits on whichever rank, block or launch it is computed.
+__global__ void __launch_bounds__(RSFM_POOL_GROUP)
+pooled_partials_kernel(int C, int rows, unsigned long long id0, double iters, const double *__restrict__ suff,
+                       double *__restrict__ out)
+{
+    const unsigned long long gfirst = (id0 / RSFM_POOL_GROUP + blockIdx.x) * (unsigned long long)RSFM_POOL_GROUP;
+    const long long c = (long long)(gfirst + threadIdx.x) - (long long)id0;
+    const bool in = c >= 0 && c < (long long)C;
+    __shared__ double ws[32];
+    double *o = out + (size_t)blockIdx.x * RSFM_POOL_ROWS;
+    for (int r = -1; r < rows; r++) {
+        double v = in ? (r < 0 ? iters : suff[(size_t)r * C + c]) : 0.0;       // r = -1: the sample count
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(FULL_MASK, v, off);
+        if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double w = ws[threadIdx.x];
+            for (int off = 16; off > 0; off >>= 1) w += __shfl_down_sync(FULL_MASK, w, off);
+            if (threadIdx.x == 0) o[r + 1] = w;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x > rows && threadIdx.x < RSFM_POOL_ROWS) o[threadIdx.x] = 0.0;
+}
+
+extern "C" int rsfm_pooled_groups(const rsfm_sampler *s)
+{
+    if (!s) return -1;
+    const unsigned long long first = s->chain_id0 / RSFM_POOL_GROUP, last = (s->chain_id0 + (unsigned long long)s->C - 1) / RSFM_POOL_GROUP;
+    return (int)(last - first + 1);
+}
+
+extern "C" int rsfm_pooled_partials(rsfm_sampler *s, double *out_dev, int32_t reset, void *stream_)
+{
+    if (!s || !out_dev) return set_err(RSFM_ERR_INVALID, "rsfm_pooled_partials: NULL argument%s", "");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int d = s->cfg.n_params, rows = d + tri(d);
+    pooled_partials_kernel<<<rsfm_pooled_groups(s), RSFM_POOL_GROUP, 0, st>>>(s->C, rows, s->chain_id0, (double)s->suff_count,
+                                                                              s->d.suff, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    if (reset) {
+        CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * rows * (size_t)s->C, st));
+        s->suff_count = 0;
+    }
+    return RSFM_OK;
+}
+
+// moments += sum of the gathered rows (sequential over parts: the order is the global chain order), then the
+// Haario proposal (2.38^2/d) cov and its closed-form Cholesky factor (d <= 3).  fac[0] = 1 when a factor was
+// formed (finite, positive definite), fac[1..] = the factor (d = 1: the variance).
+__global__ void pooled_update_kernel(int d, int n_parts, const double *__restrict__ parts, double *__restrict__ moments,
+                                     int accumulate, int install, double *__restrict__ fac)
+{
+    const int T = d * (d + 1) / 2, rows = 1 + d + T;
+    const int r = threadIdx.x;
+    if (accumulate && parts != nullptr && r < rows) {
+        double a = moments[r];
+        for (int p = 0; p < n_parts; p++) a += parts[(size_t)p * RSFM_POOL_ROWS + r];
+        moments[r] = a;
+    }
+    __syncthreads();
+    if (r != 0) return;
+    fac[0] = 0.0;
+    if (!install) return;
+    const double n = moments[0];
+    if (!(n > (double)(d + 1))) return;
+    const double sc = 2.38 * 2.38 / (double)d;
+    double mean[3], v[6];
+    for (int i = 0; i < d; i++) mean[i] = moments[1 + i] / n;
+    bool ok = true;
+    int t = 0;
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j <= i; j++, t++) {
+            double c = (moments[1 + d + t] - n * (mean[i] * mean[j])) / (n - 1.0);
+            c *= sc;
+            if (i == j) { ok = ok && (c > 0.0); c = c + 1e-10 * c; }
+            ok = ok && isfinite(c);
+            v[t] = c;
+        }
+    if (!ok) return;
+    if (d == 1) { fac[1] = v[0]; fac[0] = 1.0; return; }
+    // d = 3: v = (v00, v10, v11, v20, v21, v22)
+    const double l00 = sqrt(v[0]), l10 = v[1] / l00, l20 = v[3] / l00;
+    const double a11 = v[2] - l10 * l10;
+    if (!(a11 > 0.0)) return;
+    const double l11 = sqrt(a11), l21 = (v[4] - l20 * l10) / l11;
+    const double a22 = v[5] - l20 * l20 - l21 * l21;
+    if (!(a22 > 0.0)) return;
+    const double l22 = sqrt(a22);
+    if (!(isfinite(l10) && isfinite(l20) && isfinite(l21) && isfinite(l22))) return;
+    fac[1] = l00; fac[2] = l10; fac[3] = l11; fac[4] = l20; fac[5] = l21; fac[6] = l22;
+    fac[0] = 1.0;
+}
+
+__global__ void install_chol_kernel(int C, int T, const double *__restrict__ fac, double *__restrict__ chol)
+{
+    if (fac[0] == 0.0) return;                      // no valid factor: the proposal stays (cf. quirk q4)
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    for (int j = 0; j < T; j++) chol[(size_t)j * C + c] = fac[1 + j];
+}
+
+extern "C" int rsfm_pooled_update(rsfm_sampler *s, const double *parts_dev, int32_t n_parts, double *moments_dev,
+                                  int32_t accumulate, int32_t install, double *factor_out_dev, void *stream_)
+{
+    if (!s || !moments_dev) return set_err(RSFM_ERR_INVALID, "rsfm_pooled_update: NULL argument%s", "");
+    if (parts_dev && n_parts < 0) return set_err(RSFM_ERR_INVALID, "rsfm_pooled_update: n_parts < 0%s", "");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int d = s->cfg.n_params, T = tri(d);
+    pooled_update_kernel<<<1, 32, 0, st>>>(d, n_parts, parts_dev, moments_dev, accumulate, install, s->reduce_out);
+    CUDA_TRY(cudaGetLastError());
+    if (install) {
+        install_chol_kernel<<<(s->C + 255) / 256, 256, 0, st>>>(s->C, T, s->reduce_out, s->d.chol);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (factor_out_dev)
+        CUDA_TRY(cudaMemcpyAsync(factor_out_dev, s->reduce_out, sizeof(double) * (1 + T), cudaMemcpyDeviceToDevice, st));
+    return RSFM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// test hooks: the device's own Philox / samplers / RHS, element by element (tests compare them with the CPU oracle)
+// ---------------------------------------------------------------------------
+__global__ void philox_raw_kernel(int n, const uint32_t *__restrict__ in, uint32_t *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PhiloxKey k; k.k0 = in[6 * i + 4]; k.k1 = in[6 * i + 5];
+    const uint4 r = philox4x32_10(make_uint4(in[6 * i], in[6 * i + 1], in[6 * i + 2], in[6 * i + 3]), k);
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+extern "C" int rsfm_philox_raw(const uint32_t *in_dev, uint32_t *out_dev, int32_t n, void *stream)
+{
+    if (!in_dev || !out_dev || n < 1) return set_err(RSFM_ERR_INVALID, "rsfm_philox_raw: bad argument%s", "");
+    int rc = require_device();
+    if (rc) return rc;
+    philox_raw_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, in_dev, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return RSFM_OK;
+}
+
+__global__ void philox_draws_kernel(unsigned long long seed, unsigned long long id0, int C, unsigned int iter0,
+                                    int n_iters, double shape, double *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const PhiloxKey key = philox_key(seed);
+    const unsigned long long gid = id0 + (unsigned long long)c;
+    for (int i = 0; i < n_iters; i++) {
+        const unsigned int it = iter0 + (unsigned int)i;
+        double z0, z1, z2, zz;
+        philox_normal2(key, gid, it, 0u, z0, z1);
+        philox_normal2(key, gid, it, 1u, z2, zz);
+        const double u = philox_uniform(key, gid, it, 2u);
+        uint32_t tries = 0;
+        const double g = philox_gamma(key, gid, it, shape, &tries);
+        double *o = out + (size_t)i * 6 * C + c;
+        o[0] = z0; o[(size_t)C] = z1; o[2 * (size_t)C] = z2; o[3 * (size_t)C] = u; o[4 * (size_t)C] = g;
+        o[5 * (size_t)C] = (double)tries;
+    }
+}
+
+extern "C" int rsfm_philox_draws(uint64_t seed, uint64_t chain_id0, int32_t C, uint32_t iter0, int32_t n_iters,
+                                 double gamma_shape, double *out_dev, void *stream)
+{
+    if (!out_dev || C < 1 || n_iters < 1 || !(gamma_shape > 1.0))
+        return set_err(RSFM_ERR_INVALID, "rsfm_philox_draws: bad argument%s", "");
+    int rc = require_device();
+    if (rc) return rc;
+    philox_draws_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, chain_id0, C, iter0, n_iters, gamma_shape, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return RSFM_OK;
+}
+
+__global__ void rhs_eval_kernel(const __grid_constant__ ModelK M, int n, double a0, double b0, const double *__restrict__ t,
+                                const double *__restrict__ mu, const double *__restrict__ th,
+                                const double *__restrict__ dc, const double *__restrict__ a, const double *__restrict__ b,
+                                int general, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ChainConst cc = make_chain_const(M, a ? a[i] : a0, b ? b[i] : b0, dc[i]);
+    const double L = loading_of(M, t[i]);
+    double rth = 1.0 / th[i], dmu, dth, dV;
+    if (general) {
+        bool unused = false;
+        rsf_rhs<false>(cc, L, mu[i], th[i], rth, dmu, dth, dV, unused);
+    } else {
+        rsf_rhs_checked(cc, L, mu[i], th[i], rth, dmu, dth, dV);
+    }
+    out[i] = dmu; out[(size_t)n + i] = dth; out[2 * (size_t)n + i] = dV;
+}
+
+extern "C" int rsfm_rhs_eval(const rsfm_cfg *cfg, int32_t n, const double *t_dev, const double *mu_dev,
+                             const double *theta_dev, const double *dc_dev, const double *a_dev, const double *b_dev,
+                             int32_t general, double *out_dev, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (n < 1 || !t_dev || !mu_dev || !theta_dev || !dc_dev || !out_dev)
+        return set_err(RSFM_ERR_INVALID, "rsfm_rhs_eval: bad argument%s", "");
+    rc = require_device();
+    if (rc) return rc;
+    const ModelK M = make_model(cfg);
+    rhs_eval_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(M, n, cfg->a, cfg->b, t_dev, mu_dev, theta_dev, dc_dev,
+                                                                        a_dev, b_dev, general, out_dev);
     CUDA_TRY(cudaGetLastError());
     return RSFM_OK;
 }

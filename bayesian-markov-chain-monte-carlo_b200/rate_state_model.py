@@ -7,7 +7,11 @@ arrays of length ``num_steps``.  The ODE solve itself runs in librsfm's
 integrates on the CPU.
 
 Extensions (absent from the reference): ``evaluate_batch`` for many parameter
-sets at once, ``loading`` / ``integ_mode`` selectors.
+sets at once, ``loading`` / ``integ_mode`` selectors, and
+``observable``: ``"acc"`` (reference: the backward-difference
+acceleration, :388) or ``"mu"`` (the friction series the reference integrates and
+stores, :385, but never compares with data) -- what ``evaluate()[1]``, ``evaluate_batch``
+and the sampler's sum of squares are computed on.
 """
 import ctypes as C
 
@@ -26,6 +30,8 @@ END_TIME = 50.0
 
 _LOADING = {"sine_decay": _lib.LOAD_SINE_DECAY, "vstep": _lib.LOAD_VSTEP}
 _INTEG = {"parity": _lib.INTEG_PARITY, "carry": _lib.INTEG_CARRY}
+_OBSERVABLE = {"acc": _lib.OBS_ACC, "mu": _lib.OBS_MU}
+_VARIANT = {"auto": _lib.VARIANT_AUTO, "default": _lib.VARIANT_DEFAULT, "stiff": _lib.VARIANT_STIFF}
 
 
 class RateStateModel:
@@ -54,6 +60,10 @@ class RateStateModel:
         self.vstep_period = 1000.0
         self.vstep_factor = 10.0
         self.integ_mode = "parity"
+        self.observable = "acc"
+        self.solver_variant = "auto"   # "default" / "stiff": force a kernel variant (tests, tuning)
+        self.stiff_exact = False       # stiff variant: score every step that left the fast ranges
+        self.block_threads = 0         # threads per block of the one-thread-per-chain kernels (0 = auto)
         self.rtol = 1e-6            # RateStateModel.py:374
         self.atol = 1e-10
         self.nmax = 500             # scipy dop853 nsteps default
@@ -77,6 +87,10 @@ class RateStateModel:
         cfg.radiation_damping = 1 if self.RadiationDamping else 0
         cfg.loading = _LOADING[self.loading]
         cfg.integ_mode = _INTEG[self.integ_mode]
+        cfg.observable = _OBSERVABLE[self.observable]
+        cfg.solver_variant = _VARIANT[self.solver_variant]
+        cfg.stiff_exact = 1 if self.stiff_exact else 0
+        cfg.block_threads = int(self.block_threads)
         return cfg
 
     def _device(self, torch):
@@ -87,7 +101,8 @@ class RateStateModel:
         """Solve for many parameter sets in one launch.
 
         dc, a, b: 1-D array-likes / CUDA tensors of equal length C (a, b optional).
-        Returns a dict of CUDA tensors: ``acc`` [n_out, C] (time-major), ``t``,
+        Returns a dict of CUDA tensors: ``acc`` [n_out, C] (time-major; the observable: acceleration, or
+        mu when ``self.observable == "mu"``), ``t``,
         ``sse`` [C] (when ``data`` is given), ``status``, ``filled``, ``nrhs``, ``nstep``.
         """
         torch = _lib.require_cuda()
@@ -147,5 +162,7 @@ class RateStateModel:
             import warnings
             msg = {_lib.CHAIN_NMAX: "larger nsteps is needed", _lib.CHAIN_HSMALL: "step size becomes too small"}
             warnings.warn(f"dop853: {msg.get(status, 'integration failed')}", UserWarning, stacklevel=2)
-        acc_noise = acc + 1.0 * np.abs(acc) * np.random.randn(acc.shape[0])
+        # :392 -- for the reference observable acc[0] = 0, so |acc - acc[0]| is |acc| bit for bit; for
+        # observable = "mu" the noise scales with the excursion from mu[0] = mu_ref in the same way
+        acc_noise = acc + 1.0 * np.abs(acc - acc[0]) * np.random.randn(acc.shape[0])
         return t, acc, acc_noise

@@ -27,24 +27,51 @@ import time
 import numpy as np
 
 from . import _lib
-from .sharding import ChainShard, all_reduce_sum_
+from .sharding import ChainShard, all_gather_rows, max_pool_groups, rank_and_world
+
+# result arrays larger than this are copied to the host in chunks while the chains are still running
+_OVERLAP_BYTES = 128 << 20
+_CHUNK_BYTES = 96 << 20
 
 
-def _to_host(torch, dev, *tensors):
-    """Device -> host copy of the result arrays through page-locked staging buffers (torch's caching
-    host allocator recycles them between calls); one synchronisation for all of them.  Pageable
-    destinations cost ~8 ms per call for the 18 MB of cfg 2 against < 1 ms pinned."""
-    outs = []
-    for t in tensors:
-        t = t.contiguous()
-        try:
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        except RuntimeError:                     # locked-memory limit reached: plain pageable copy
-            h = torch.empty(t.shape, dtype=t.dtype)
-        h.copy_(t, non_blocking=True)
-        outs.append(h)
-    torch.cuda.synchronize(dev)
-    return [h.numpy() for h in outs]
+class _ResultPipe:
+    """Device -> host transfer of the result arrays, overlapped with the iterations.
+
+    The device arrays are time-major (``[rows, ...]``); rows become final as iterations complete, so
+    finished row ranges are copied on a side stream into page-locked host buffers of the same layout
+    while the next launch runs (torch's caching host allocator recycles the buffers between calls;
+    pageable destinations cost ~8 ms per call for the 18 MB of cfg 2 against < 1 ms pinned).  The
+    reference-shaped ``[C, d, n]`` outputs are transposed VIEWS of those buffers: no second copy."""
+
+    def __init__(self, torch, dev, arrays):
+        self.torch, self.dev = torch, dev
+        self.stream = torch.cuda.Stream(dev)
+        self.items = []                               # (device tensor, first row wanted, host tensor)
+        for t, first in arrays:
+            shape = (t.shape[0] - first,) + tuple(t.shape[1:])
+            try:
+                h = torch.empty(shape, dtype=t.dtype, pin_memory=True)
+            except RuntimeError:                      # locked-memory limit reached: plain pageable copy
+                h = torch.empty(shape, dtype=t.dtype)
+            self.items.append((t, first, h, [first]))
+
+    def push(self, upto_rows):
+        """Rows below ``upto_rows[i]`` of array i are final once the work queued so far on the current
+        stream is done: copy what has not been copied yet."""
+        torch = self.torch
+        ev = torch.cuda.current_stream(self.dev).record_event()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            for (t, first, h, done), upto in zip(self.items, upto_rows):
+                lo, hi = done[0], min(int(upto), t.shape[0])
+                if hi > lo:
+                    h[lo - first:hi - first].copy_(t[lo:hi], non_blocking=True)
+                    done[0] = hi
+
+    def finish(self):
+        self.push([t.shape[0] for t, _, _, _ in self.items])
+        self.stream.synchronize()
+        return [h.numpy() for _, _, h, _ in self.items]
 
 
 class MCMC:
@@ -174,6 +201,7 @@ class MCMC:
             s = np.random.randint(0, 2 ** 31 - 1, size=2)
             seed = (int(s[0]) << 31) | int(s[1])
         self.seed_used = int(seed)
+        self._pooled_stats, self._pooled_state = {}, None
 
         t_begin = time.perf_counter()
         with torch.cuda.device(dev):
@@ -192,6 +220,7 @@ class MCMC:
                 if self.resume is not None:
                     q0, s2_0 = self._apply_checkpoint(torch, lib, handle, dev, d, cl, stream)
                 ns = int(self.nsamples)
+                nb = self.nburn
                 chain = torch.empty((ns + 1, d, cl), dtype=torch.float64, device=dev)
                 std2 = torch.empty((ns + 1, cl), dtype=torch.float64, device=dev)
                 accept = torch.empty((ns, cl), dtype=torch.uint8, device=dev)
@@ -199,41 +228,67 @@ class MCMC:
                 draws = torch.empty((ns, d + 2, cl), dtype=torch.float64, device=dev) if want_draws else None
                 chain[0] = q0
                 std2[0] = s2_0
+                pipe = _ResultPipe(torch, dev, [(chain, nb), (std2, nb), (accept, 0)])
+                out_bytes = (ns + 1 - nb) * (d + 1) * cl * 8 + ns * cl
+
+                def run_iters(k, done):
+                    _lib.check(lib.rsfm_run(handle, k, _lib.ptr(chain[1 + done:]), _lib.ptr(std2[1 + done:]),
+                                            _lib.ptr(accept[done:]), _lib.ptr(draws[done:]) if draws is not None else None,
+                                            stream), "rsfm_run")
+
                 if self.deterministic_inputs is not None:
                     self._run_deterministic(torch, lib, handle, dev, d, cl, ns, chain, std2, accept, stream)
                 elif cfg.adapt_mode == _lib.ADAPT_POOLED:
-                    self._run_pooled(torch, lib, handle, dev, d, cl, ns, chain, std2, accept, stream)
+                    self._run_pooled(torch, lib, handle, dev, d, cl, ns, run_iters, pipe, stream)
+                elif out_bytes <= _OVERLAP_BYTES or ns < 2:
+                    run_iters(ns, 0)
                 else:
-                    _lib.check(lib.rsfm_run(handle, ns, _lib.ptr(chain[1:]), _lib.ptr(std2[1:]), _lib.ptr(accept),
-                                            _lib.ptr(draws), stream), "rsfm_run")
+                    # large outputs (cfg 5: 0.5 GB per GPU): burn-in in one launch, then launches of a few dozen
+                    # iterations whose results go to the host while the next launch runs.  The chains do not
+                    # depend on the launch partition (draws are keyed by chain and iteration).
+                    per_iter = (d + 1) * cl * 8 + cl
+                    step = max(20, _CHUNK_BYTES // per_iter)
+                    done = 0
+                    if nb > step:
+                        run_iters(nb - 1, 0)
+                        done = nb - 1
+                        pipe.push([1 + done, 1 + done, done])
+                    while done < ns:
+                        k = min(step, ns - done)
+                        run_iters(k, done)
+                        done += k
+                        pipe.push([1 + done, 1 + done, done])
                 acc_cnt = torch.empty(cl, dtype=torch.int32, device=dev)
                 status = torch.empty(cl, dtype=torch.int32, device=dev)
                 nrhs = torch.empty(cl, dtype=torch.int64, device=dev)
                 nstep = torch.empty(cl, dtype=torch.int64, device=dev)
                 _lib.check(lib.rsfm_get_state(handle, None, None, None, None, _lib.ptr(acc_cnt), _lib.ptr(status),
                                               _lib.ptr(nrhs), _lib.ptr(nstep), stream), "rsfm_get_state")
-                tot = (C.c_uint64 * 9)()
-                _lib.check(lib.rsfm_get_totals(handle, tot, stream), "rsfm_get_totals")
                 st_q = torch.empty((d, cl), dtype=torch.float64, device=dev)
                 st_sse = torch.empty(cl, dtype=torch.float64, device=dev)
                 st_s2 = torch.empty(cl, dtype=torch.float64, device=dev)
                 st_chol = torch.empty((d * (d + 1) // 2, cl), dtype=torch.float64, device=dev)
                 _lib.check(lib.rsfm_get_state(handle, _lib.ptr(st_q), _lib.ptr(st_sse), _lib.ptr(st_s2),
                                               _lib.ptr(st_chol), None, None, None, None, stream), "rsfm_get_state")
-                self._final_state = (st_q, st_sse, st_s2, st_chol, int(lib.rsfm_iteration(handle)))
+                st_ring = None
+                if cfg.adapt_mode == _lib.ADAPT_COMPAT:
+                    st_ring = torch.empty((int(self.adapt_interval), cl), dtype=torch.float64, device=dev)
+                    _lib.check(lib.rsfm_get_ring(handle, _lib.ptr(st_ring), stream), "rsfm_get_ring")
+                self._final_state = (st_q, st_sse, st_s2, st_chol, int(lib.rsfm_iteration(handle)), st_ring)
+                # ---- reference-shaped host outputs: the last rows go to the host, everything is awaited ----
+                chain_t, std2_t, accept_t = pipe.finish()                  # [n, d, C], [n, C], [ns, C]
+                tot = (C.c_uint64 * 9)()
+                _lib.check(lib.rsfm_get_totals(handle, tot, stream), "rsfm_get_totals")
                 torch.cuda.synchronize(dev)
             finally:
                 lib.rsfm_destroy(handle)
         elapsed = time.perf_counter() - t_begin
 
-        nb = self.nburn
         self.samples_device = chain                       # [nsamples+1, d, C_local], start value included
         self.std2_device = std2
         self.accept_device = accept
         in_bounds = None
-        # ---- reference-shaped host outputs (device -> host copy of the results) ----
-        chain_h, std2_h, accept_h = _to_host(torch, dev, chain[nb:].permute(2, 1, 0),      # [C, d, n]
-                                             std2[nb:].t(), accept.t())                    # [C, n], [C, ns]
+        chain_h, std2_h, accept_h = chain_t.transpose(2, 1, 0), std2_t.T, accept_t.T   # [C, d, n], [C, n], [C, ns]
         self.Vstart = self._vstart_host(chol0, d)
         self.status = status.cpu().numpy()
         n_acc = acc_cnt.cpu().numpy().astype(np.int64)
@@ -242,25 +297,29 @@ class MCMC:
             "elapsed_s": elapsed, "n_chains_local": cl, "chain_id0": id0,
             "nsolves": int(tot[0]), "nrhs": int(tot[1]), "nstep": int(tot[2]),
             "nsolves_stopped_early": int(tot[5]), "nsolves_executed": int(tot[6]),
+            "nrhs_deciding": int(tot[7]), "nstep_deciding": int(tot[8]),
             "failed_chains": int((status != 0).sum().item()),
         }
+        self.stats.update(getattr(self, "_pooled_stats", {}))
         if cl == 1:
+            last = None
             if draws is not None:
                 dr = draws[:, :, 0].cpu().numpy()
                 in_bounds = ~np.isnan(dr[:, d])
                 evaluated = dr[in_bounds, :d]
-                # the reference leaves model.Dc at the last evaluated proposal, a 1-element array (q6)
-                last = evaluated[-1, d - 1] if evaluated.shape[0] else float(np.ravel(self.qstart)[0])
-                self.model.Dc = np.array([last])
+                if evaluated.shape[0]:
+                    last = evaluated[-1, d - 1]
                 if self.verbose:
                     for i in range(self.nsamples):               # MCMC.py:503-504
                         print(i, bool(accept_h[0, i]))
                         print("Generated Sample ---- ", dr[i, d - 1] if d == 1 else dr[i, :d])
+                # the reference leaves model.Dc at the last evaluated proposal, a 1-element array (q6)
+                self.model.Dc = np.array([last if last is not None else float(np.ravel(self.qstart)[-1])])
             if self.verbose:
                 print("acceptance ratio:", self.acceptance_ratio[0])      # MCMC.py:530
-            self.std2 = std2_h[0]                                          # MCMC.py:533
-            self.accepts = accept_h[0]
-            return chain_h[0]                                              # (d, nsamples+1-nburn), MCMC.py:544
+            self.std2 = np.ascontiguousarray(std2_h[0])                    # MCMC.py:533
+            self.accepts = np.ascontiguousarray(accept_h[0])
+            return np.ascontiguousarray(chain_h[0])                        # (d, nsamples+1-nburn), MCMC.py:544
         if self.verbose:
             print("acceptance ratio:", float(self.acceptance_ratio.mean()))
         self.std2 = std2_h
@@ -294,50 +353,122 @@ class MCMC:
                                               _lib.ptr(accept), stream), "rsfm_run_deterministic")
         torch.cuda.synchronize(dev)
 
-    def _run_pooled(self, torch, lib, handle, dev, d, cl, ns, chain, std2, accept, stream):
-        """Haario-style adaptive Metropolis with the covariance pooled over all chains of all ranks.
+    def _run_pooled(self, torch, lib, handle, dev, d, cl, ns, run_iters, pipe, stream):
+        """Haario-style adaptive Metropolis with the covariance pooled over all chains of all ranks
+        (generalises MCMC.py:162-204, 523-527), every step of it on the device.
 
-        Every ``adapt_interval`` iterations (after ``adapt_start``): local sufficient statistics
-        (n, sum q, sum qq^T) -> one small all-reduce -> every rank forms the same
-        (2.38^2/d) * cov and installs its Cholesky factor.
-        """
-        from .adaptation import proposal_from_suffstats
+        Per interval j of ``adapt_interval`` iterations, without any host synchronisation:
+          main stream   [update(j-2)]  run(j)  partials(j)                    (rsfm_pooled_update / rsfm_run /
+          side stream                          all-gather(j) ............      rsfm_pooled_partials)
+        ``partials`` are sums over fixed groups of 1,024 chains aligned on the global chain id; the
+        all-gather (NCCL; a device copy for one rank) puts every rank's rows in global chain order, and
+        ``update`` adds them to the running moments in that order, forms (2.38^2/d) cov and its Cholesky
+        factor in closed form and installs it for every chain -- the same bits on every rank and for any
+        number of ranks.  The all-gather of interval j overlaps run(j+1); its factor is used from
+        interval j+2 on (adaptation lags one interval, as SURVEY 8e allows)."""
         tri = d * (d + 1) // 2
-        suff = torch.zeros(1 + d + tri, dtype=torch.float64, device=dev)
-        total = torch.zeros_like(suff)
-        done = 0
-        w = int(self.adapt_interval)
-        self.adapt_history = []
-        while done < ns:
-            k = min(w, ns - done)
-            _lib.check(lib.rsfm_run(handle, k, _lib.ptr(chain[1 + done:]), _lib.ptr(std2[1 + done:]),
-                                    _lib.ptr(accept[done:]), None, stream), "rsfm_run")
+        w = max(1, int(self.adapt_interval))
+        rank, world = rank_and_world() if self.shard else (0, 1)
+        g, rows = _lib.POOL_GROUP, _lib.POOL_ROWS
+        ng_local = int(lib.rsfm_pooled_groups(handle))
+        ng = max_pool_groups(self.n_chains, world, g) if world > 1 else ng_local
+        loc = [torch.zeros((ng, rows), dtype=torch.float64, device=dev) for _ in range(2)]
+        parts = [torch.zeros((world * ng, rows), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else loc
+        moments = torch.zeros(1 + d + tri, dtype=torch.float64, device=dev)
+        done = int(lib.rsfm_iteration(handle))            # > 0 after a resume
+        first = done
+        if self.resume is not None and "pooled_moments" in self.resume:
+            if done % w:
+                raise ValueError("a pooled-adaptation checkpoint continues exactly only from an adaptation "
+                                 f"boundary (iteration {done} is not a multiple of adapt_interval = {w})")
+            moments.copy_(torch.as_tensor(np.asarray(self.resume["pooled_moments"], dtype=np.float64)))
+            pend = np.asarray(self.resume["pooled_pending"], dtype=np.float64).reshape(-1, rows)
+            if pend.shape[0] != parts[0].shape[0]:
+                raise ValueError("checkpoint was written with a different number of ranks / chains")
+        n_int = (first + ns + w - 1) // w - first // w
+        hist = torch.zeros((n_int + 2, 1 + tri), dtype=torch.float64, device=dev)
+        side = torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+        gathered, ends, tev = {}, {}, []
+        half = self.adapt_start // 2
+
+        def update(j, install_ok=True):
+            """moments += rows(j) and, past adapt_start, install the factor they give (on the main stream)."""
+            main.wait_event(gathered[j])
+            acc = 1 if ends[j] > half else 0
+            inst = 1 if (install_ok and ends[j] >= self.adapt_start) else 0
+            _lib.check(lib.rsfm_pooled_update(handle, _lib.ptr(parts[j % 2]), int(parts[j % 2].shape[0]), _lib.ptr(moments),
+                                              acc, inst, _lib.ptr(hist[j + 1]), stream), "rsfm_pooled_update")
+
+        j = 0
+        if self.resume is not None and "pooled_moments" in self.resume:
+            # the interval that ended at the checkpoint was gathered but not yet applied (see below)
+            parts[1].copy_(torch.as_tensor(pend))
+            gathered[-1], ends[-1] = main.record_event(), done
+        pos = 0
+        while pos < ns:
+            k = min(w - (done % w), ns - pos)
+            if (j - 2) in gathered:
+                update(j - 2)
+            elif j == 1 and -1 in gathered:
+                update(-1)
+            run_iters(k, pos)
+            pos += k
             done += k
-            _lib.check(lib.rsfm_get_suffstats(handle, _lib.ptr(suff), 1, stream), "rsfm_get_suffstats")
-            all_reduce_sum_(suff)
-            if done > self.adapt_start // 2:          # discard the earliest draws from the pooled moments
-                total += suff
-            if done >= self.adapt_start and done < ns and total[0].item() > d + 1:
-                fac = proposal_from_suffstats(total.cpu().numpy(), d)
-                if fac is not None:
-                    arr = (C.c_double * tri)(*fac)
-                    _lib.check(lib.rsfm_set_proposal_chol(handle, arr, stream), "rsfm_set_proposal_chol")
-                    self.adapt_history.append((done, fac.copy()))
+            ends[j] = done
+            _lib.check(lib.rsfm_pooled_partials(handle, _lib.ptr(loc[j % 2]), 1, stream), "rsfm_pooled_partials")
+            ready = main.record_event()
+            if world > 1:
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    t0 = torch.cuda.Event(enable_timing=True)
+                    t1 = torch.cuda.Event(enable_timing=True)
+                    t0.record(side)
+                    all_gather_rows(parts[j % 2], loc[j % 2])
+                    t1.record(side)
+                    tev.append((t0, t1))
+                    gathered[j] = side.record_event()
+            else:
+                gathered[j] = ready
+            pipe.push([1 + pos, 1 + pos, pos])
+            j += 1
+        # drain: what an uninterrupted run would have applied before its next interval; the last interval's
+        # rows stay pending (they would be applied one interval later) and go into the checkpoint
+        if j >= 2:
+            update(j - 2)
+        elif j == 1 and -1 in gathered:
+            update(-1)
+        main.wait_event(gathered[j - 1])
+        self._pooled_state = (moments, parts[(j - 1) % 2].clone())
+        torch.cuda.synchronize(dev)
+        h = hist.cpu().numpy()
+        keys = sorted(k_ for k_ in ends if k_ + 1 < h.shape[0] and k_ + 1 >= 0)
+        self.adapt_history = [(ends[k_], h[k_ + 1, 1:].copy()) for k_ in keys if h[k_ + 1, 0] == 1.0]
+        coll_ms = sum(a.elapsed_time(b) for a, b in tev)
+        self._pooled_stats = {"n_adaptations": len(self.adapt_history), "n_intervals": j,
+                              "collective_ms_on_side_stream": coll_ms, "pool_rows_gathered": int(parts[0].shape[0])}
 
     # ------------------------------------------------------------------
     # ------------------------------------------------------------------
     def checkpoint(self, filename=None):
         """State needed to continue the chains exactly where they stopped (the reference has no
-        checkpoint): current q, SSE, sigma^2, proposal factor, iteration count, seed.
-        With counter-based Philox draws, ``MCMC(..., resume=ckpt).sample()`` continues the very same
-        chains.  Returned as a dict of NumPy arrays and, if ``filename`` is given, written in the
-        reference's JSON ndarray format.  (Compat adaptation keeps a 10-sample ring that is not saved.)"""
+        checkpoint): current q, SSE, sigma^2, proposal factor, iteration count, seed,
+        and the adaptation state -- the per-chain sample ring of the reference's windowed update
+        (compat mode), or the pooled moments plus the gathered rows of the last interval (pooled mode;
+        exact from an adaptation boundary).  With counter-based Philox draws,
+        ``MCMC(..., resume=ckpt).sample()`` continues the very same chains.  Returned as a dict of NumPy
+        arrays and, if ``filename`` is given, written in the reference's JSON ndarray format."""
         if getattr(self, "_final_state", None) is None:
             raise RuntimeError("call sample() first")
-        q, sse, s2, chol, iteration = self._final_state
+        q, sse, s2, chol, iteration, ring = self._final_state
         ck = {"q": q.cpu().numpy(), "sse": sse.cpu().numpy(), "sigma2": s2.cpu().numpy(), "chol": chol.cpu().numpy(),
               "iteration": int(iteration), "seed": int(self.seed_used), "chain_id0": int(self.stats["chain_id0"]),
               "param_names": list(self.param_names), "n_chains_local": int(q.shape[1])}
+        if ring is not None:
+            ck["ring"] = ring.cpu().numpy()
+        if self.adapt == "pooled" and getattr(self, "_pooled_state", None) is not None:
+            ck["pooled_moments"] = self._pooled_state[0].cpu().numpy()
+            ck["pooled_pending"] = self._pooled_state[1].cpu().numpy()
         if filename is not None:
             from .ndarray_json import save_object
             save_object(ck, filename)
@@ -353,6 +484,11 @@ class MCMC:
         chol = dev_t(ck["chol"], (d * (d + 1) // 2, cl))
         _lib.check(lib.rsfm_set_state(handle, _lib.ptr(q), _lib.ptr(sse), _lib.ptr(s2), _lib.ptr(chol),
                                       int(ck["iteration"]), stream), "rsfm_set_state")
+        if self.compat_adapt:
+            if "ring" not in ck:
+                raise ValueError("checkpoint holds no sample ring: it was not written by a compat-adaptation run")
+            ring = dev_t(ck["ring"], (int(self.adapt_interval), cl))
+            _lib.check(lib.rsfm_set_ring(handle, _lib.ptr(ring), stream), "rsfm_set_ring")
         return q, s2
 
     def diagnostics(self, max_lag=None):

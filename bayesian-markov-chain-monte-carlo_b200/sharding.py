@@ -49,6 +49,28 @@ def rank_and_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def pool_groups(start: int, count: int, group: int) -> int:
+    """Number of `group`-aligned blocks of global chain ids that [start, start + count) touches
+    (= rsfm_pooled_groups of a sampler holding that range)."""
+    return (start + count - 1) // group - start // group + 1
+
+
+def max_pool_groups(total: int, world: int, group: int) -> int:
+    """Largest per-rank group count of the balanced partition: the padded row count of the all-gather."""
+    return max(pool_groups(s.start, s.count, group) for s in (ChainShard.for_rank(total, r, world) for r in range(world)))
+
+
+def all_gather_rows(out, rows):
+    """Gather every rank's `rows` [R, W] into `out` [world * R, W] in rank order (= global chain order for the
+    contiguous partition).  One small collective on the current stream; a plain copy for a single process."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_gather_into_tensor(out, rows)
+    else:
+        out.copy_(rows)
+    return out
+
+
 def all_reduce_sum_(tensor):
     """In-place SUM all-reduce over the default process group; a no-op for a single process."""
     import torch.distributed as dist

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RSFM_ABI_VERSION 1
+#define RSFM_ABI_VERSION 2
 #define RSFM_MAX_PARAMS 3
 
 typedef enum {
@@ -53,7 +53,18 @@ enum { RSFM_INTEG_PARITY = 0,      /* fresh dop853 call + hinit per output inter
 /* proposal-covariance adaptation */
 enum { RSFM_ADAPT_NONE = 0,        /* list-typed priors: update silently dead (quirk q2) */
        RSFM_ADAPT_COMPAT = 1,      /* dict-typed priors: MCMC.py:200-204 as written (quirk q3) */
-       RSFM_ADAPT_POOLED = 2 };    /* host-driven: rsfm_get_suffstats + rsfm_set_proposal_chol */
+       RSFM_ADAPT_POOLED = 2 };    /* covariance pooled over all chains (and ranks): rsfm_pooled_partials +
+                                      rsfm_pooled_update, every step on the device */
+
+/* observable scored by the sum of squares */
+enum { RSFM_OBS_ACC = 0,           /* backward-difference acceleration, RateStateModel.py:388 (reference) */
+       RSFM_OBS_MU = 1 };          /* friction coefficient mu_k = y[0], RateStateModel.py:385 (extension:
+                                      the series the reference integrates and stores but never compares) */
+
+/* which instantiation of the solver kernels runs */
+enum { RSFM_VARIANT_AUTO = 0,      /* stiff variant for RSFM_LOAD_VSTEP, default one otherwise */
+       RSFM_VARIANT_DEFAULT = 1,
+       RSFM_VARIANT_STIFF = 2 };
 
 /* per-chain solver status word ("flag, not hang") */
 enum { RSFM_CHAIN_OK = 0,
@@ -85,6 +96,12 @@ typedef struct rsfm_cfg {
     int32_t adapt_mode;                  /* RSFM_ADAPT_* */
     int32_t spec_depth;                  /* speculation tree depth of rsfm_run: 0 auto (by chain count),
                                             1 off, 2..5 forced; results never depend on it */
+    int32_t observable;                  /* RSFM_OBS_* */
+    int32_t solver_variant;              /* RSFM_VARIANT_* (tests / tuning; results agree within the parity gates) */
+    int32_t stiff_exact;                 /* stiff variant: score every step that left the fast ranges with the
+                                            general-range stages instead of taking exploding trial steps as rejected */
+    int32_t block_threads;               /* threads per block of the one-thread-per-chain kernels: 0 auto, or
+                                            32 / 64 / 96 / 128 (tuning; results never depend on it) */
 } rsfm_cfg;
 
 typedef struct rsfm_sampler rsfm_sampler;   /* opaque; owns per-chain device state */
@@ -104,7 +121,8 @@ int          rsfm_trim(void);
 /* Batched RateStateModel.evaluate() (RateStateModel.py:188-395) + optional SSE
  * (MCMC.py:387).  dc_dev [C] is required; a_dev, b_dev [C] may be NULL (cfg->a,
  * cfg->b are used).  Outputs, each optional (NULL to skip):
- *   acc_out_dev [n_out][C]  backward-difference acceleration (:388)
+ *   acc_out_dev [n_out][C]  the observable: backward-difference acceleration (:388), or mu_k (:385, entry 0 =
+ *                           mu_ref, :367) with cfg->observable = RSFM_OBS_MU
  *   t_out_dev   [n_out][C]  output times as accumulated by the solver (:384)
  *   sse_out_dev [C]         sum_k (acc_k - data_k)^2, needs data_dev [n_out]
  *   status_dev  [C]         RSFM_CHAIN_*
@@ -167,6 +185,11 @@ int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double *sse_dev,
                    const double *sigma2_dev, const double *chol_dev, int64_t iteration,
                    void *stream);
 int64_t rsfm_iteration(const rsfm_sampler *s);
+/* RSFM_ADAPT_COMPAT only: the per-chain ring of the last adapt_interval samples, [adapt_interval][C], slot
+ * (iteration % adapt_interval) = the sample of that iteration (MCMC.py:200: qparams[:, -adapt_interval:]).
+ * Part of the state a checkpoint needs to continue a chain in the middle of an adaptation window. */
+int rsfm_get_ring(rsfm_sampler *s, double *ring_dev, void *stream);
+int rsfm_set_ring(rsfm_sampler *s, const double *ring_dev, void *stream);
 
 /* Work totals since rsfm_init, summed over chains on the device and copied to
  * out_host[9] = (forward solves of the chains = in-bounds proposals decided, RHS
@@ -176,12 +199,35 @@ int64_t rsfm_iteration(const rsfm_sampler *s);
  * solves only).  Synchronises the stream. */
 int rsfm_get_totals(rsfm_sampler *s, uint64_t *out_host, void *stream);
 
-/* Pooled adaptation (extension): local sufficient
- * statistics out_dev[1 + d + d(d+1)/2] = (n, sum q, sum q q^T lower) accumulated
- * over all chains and iterations since the last reset; the caller all-reduces
- * them over ranks (NCCL) and installs one common factor for every chain. */
+/* Pooled adaptation (extension; generalises MCMC.py:162-204, 523-527).
+ * Local sufficient statistics out_dev[1 + d + d(d+1)/2] = (n, sum q, sum qq^T lower) accumulated
+ * over all chains and iterations since the last reset.  Stream-ordered, no synchronisation. */
 int rsfm_get_suffstats(rsfm_sampler *s, double *out_dev, int32_t reset, void *stream);
+/* Install one common proposal factor for every chain from HOST memory (synchronises the stream). */
 int rsfm_set_proposal_chol(rsfm_sampler *s, const double *chol_host /* [d(d+1)/2] */, void *stream);
+
+/* The same statistics as partial sums over fixed groups of RSFM_POOL_GROUP chains, aligned on the GLOBAL
+ * chain id and reduced in a fixed order: out_dev [rsfm_pooled_groups(s)][RSFM_POOL_ROWS] with row layout
+ * (n, sum q (d), sum qq^T (lower, row-major), zero padding).  Ranks all-gather these rows (NCCL) in rank order
+ * = global chain order; every rank then holds the same array whatever the number of ranks, so the pooled
+ * moments -- and with them the chains -- do not depend on the sharding (when shard boundaries are multiples of
+ * RSFM_POOL_GROUP; otherwise they agree up to FP64 summation order).  reset != 0 clears the per-chain sums.
+ * Stream-ordered, no synchronisation. */
+#define RSFM_POOL_GROUP 1024
+#define RSFM_POOL_ROWS 16
+int rsfm_pooled_groups(const rsfm_sampler *s);
+int rsfm_pooled_partials(rsfm_sampler *s, double *out_dev, int32_t reset, void *stream);
+
+/* Device-side proposal update from gathered partials (no host round trip):
+ *   moments_dev [1 + d + d(d+1)/2] += sum over parts_dev[n_parts][RSFM_POOL_ROWS] (sequential, fixed order)
+ *       when accumulate != 0 (parts_dev may be NULL: nothing is added);
+ *   when install != 0: V = (2.38^2/d) cov(moments) (ddof 1) (1 + 1e-10 on the diagonal), closed-form Cholesky
+ *       (d <= 3); if V is finite and positive definite the common factor replaces every chain's proposal
+ *       factor (d = 1: the proposal VARIANCE, as the reference stores it), otherwise the proposal stays (q4).
+ *   factor_out_dev (optional) [1 + d(d+1)/2] receives (installed ? 1 : 0, factor).
+ * Stream-ordered, no synchronisation; every rank computes the same factor from the same moments. */
+int rsfm_pooled_update(rsfm_sampler *s, const double *parts_dev, int32_t n_parts, double *moments_dev,
+                       int32_t accumulate, int32_t install, double *factor_out_dev, void *stream);
 
 /* Diagnostics over a samples buffer [n][d][C] (device): per-chain mean, variance
  * (ddof 1) and autocovariance-based effective sample size (Geyer initial positive
@@ -195,6 +241,21 @@ int rsfm_chain_diagnostics(const double *samples_dev, int32_t n, int32_t d, int3
  * as used by RSF.plot_dist (RSF.py:734-737); the Scott bandwidth is chosen by the caller. */
 int rsfm_kde_grid(const double *samples_dev, int64_t n, const double *grid_dev, int32_t G, double bandwidth,
                   double *pdf_out_dev, void *stream);
+
+/* Test hooks: what the device computes, element by element, for the parity tests against the CPU oracle.
+ * rsfm_philox_raw: n Philox4x32-10 blocks, in_dev [n][6] = (counter[4], key[2]) -> out_dev [n][4] (the
+ *   Random123 known-answer vectors go through the device function the kernels use).
+ * rsfm_philox_draws: the draws iteration `iter0 + i` of chain `chain_id0 + c` consumes (csrc/philox.cuh stream
+ *   layout): out_dev [n_iters][6][C] = (z0, z1, z2, U, unit Gamma(gamma_shape), number of gamma attempts).
+ * rsfm_rhs_eval: friction(t, y) (RateStateModel.py:277-355) for n states, general == 0: the fast (series) form
+ *   with its fallback, exactly as the solver evaluates a single RHS; general != 0: the reference's formulas.
+ *   t/mu/theta/dc/a/b [n] -> out_dev [3][n] = (mu', theta', V'). */
+int rsfm_philox_raw(const uint32_t *in_dev, uint32_t *out_dev, int32_t n, void *stream);
+int rsfm_philox_draws(uint64_t seed, uint64_t chain_id0, int32_t C, uint32_t iter0, int32_t n_iters,
+                      double gamma_shape, double *out_dev, void *stream);
+int rsfm_rhs_eval(const rsfm_cfg *cfg, int32_t n, const double *t_dev, const double *mu_dev,
+                  const double *theta_dev, const double *dc_dev, const double *a_dev, const double *b_dev,
+                  int32_t general, double *out_dev, void *stream);
 
 /* FP64 roofline denominator: runs a dependent-free DFMA kernel for about
  * `millis` ms on the current device and returns the sustained FP64 FMA rate in

@@ -9,7 +9,7 @@ _, acc, _ = m.evaluate()
 rng = np.random.default_rng(0)
 MODES = os.environ.get("MODES", "parity").split(",")
 for blk in (os.environ.get("BLOCKS", "32,64,128").split(",")):
-    os.environ["RSFM_BLOCK"] = blk
+    m.block_threads = int(blk)
     for mode in MODES:
       m.integ_mode = mode
       for c in (32, 64, 128, 256, 512, 1024, 2048, 4096, 4736, 9472, 18944, 37888, 65536, 131072, 262144):

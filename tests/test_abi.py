@@ -24,7 +24,7 @@ def test_header_symbols_all_exported(built_lib, pkg):
 
 
 def test_abi_version_and_defaults(built_lib, pkg):
-    assert built_lib.rsfm_abi_version() == 1
+    assert built_lib.rsfm_abi_version() == 2
     cfg = pkg._lib.default_cfg()
     # RateStateModel.py:5-11 / :374 / MCMC.py:97
     assert (cfg.a, cfg.b, cfg.mu_ref, cfg.V_ref, cfg.k1) == (0.011, 0.014, 0.6, 1.0, 1e-7)
@@ -87,8 +87,15 @@ def test_cfg_validation_needs_no_device(built_lib, pkg):
     for kw, word in (({"loading": pkg._lib.LOAD_VSTEP, "vstep_period": 0.0}, "vstep_period"),
                      ({"loading": pkg._lib.LOAD_VSTEP, "vstep_factor": 0.0}, "vstep_factor"),
                      ({"rtol": 0.0}, "rtol"), ({"n_params": 2}, "n_params"), ({"loading": 7}, "loading"),
-                     ({"adapt_interval": 1}, "adapt_interval"), ({"delta_t": 0.0}, "grid"), ({"a": -1.0}, "positive")):
+                     ({"adapt_interval": 1, "adapt_mode": pkg._lib.ADAPT_COMPAT}, "adapt_interval"),
+                     ({"observable": 5}, "observable"), ({"solver_variant": 9}, "solver_variant"),
+                     ({"block_threads": 48}, "block_threads"), ({"spec_depth": 6}, "spec_depth"),
+                     ({"delta_t": 0.0}, "grid"), ({"a": -1.0}, "positive")):
         rc, msg = refused(**kw)
         assert rc < 0 and word in msg, (kw, rc, msg)
+    # the reference accepts any adapt_interval and never uses it with list priors (MCMC.py:58, q2)
+    for kw in ({"adapt_interval": 1}, {"adapt_interval": 100, "adapt_mode": pkg._lib.ADAPT_POOLED}):
+        rc, msg = refused(**kw)
+        assert rc < 0 and "dc_dev" in msg, (kw, msg)
     rc, msg = refused()                        # valid cfg, NULL parameter pointer
     assert rc < 0 and "dc_dev" in msg

@@ -256,17 +256,17 @@ def test_long_series_is_causal_and_streamed_sse_is_consistent(cuda, pkg):
     assert np.max(np.abs(acc_l[10_000:10_020, 2])) > 100 * np.max(np.abs(acc_l[9_900:9_990, 2]))
 
 
-def test_stiff_variant_on_reference_loading_and_both_variants_on_vstep(cuda, pkg, orc, monkeypatch):
+def test_stiff_variant_on_reference_loading_and_both_variants_on_vstep(cuda, pkg, orc):
     """The kernels exist in two variants (rsfm_kernels.cu: stiff_variant): the default one and the one used for
     velocity-step loading, which re-bases the friction law on the current load level, resumes the general-range
     step from the first stage that left the fast ranges and uses the SFU-seeded controller root.  Forced onto the
-    reference's own loading (RSFM_STIFF=1) it must stay inside the golden-trajectory gate; on a velocity-step
+    reference's own loading (cfg.solver_variant = RSFM_VARIANT_STIFF) it must stay inside the golden-trajectory gate; on a velocity-step
     problem both variants must agree with the oracle and with each other."""
-    monkeypatch.setenv("RSFM_STIFF", "1")
     for case in load_golden("forward_trajectories.json")["cases"]:
         if "filled" in case or not case["RadiationDamping"]:
             continue
         m = pkg.RateStateModel(number_time_steps=case["N"], end_time=case.get("end_time", 50.0))
+        m.solver_variant = "stiff"
         m.Dc = case["Dc"]
         _, acc, _ = m.evaluate()
         _check(acc, case["acc"], case["Dc"])
@@ -278,11 +278,11 @@ def test_stiff_variant_on_reference_loading_and_both_variants_on_vstep(cuda, pkg
     m.loading, m.vstep_period, m.vstep_factor = "vstep", 30.0, 10.0
     _, acc_o, _ = orc.forward_batch(orc.make_model(number_time_steps=n, end_time=t_end, **kw), dcs, want_acc=True)
     # "1x": the stiff variant scoring every step that left the fast ranges with the general-range stages
-    # (RSFM_STIFF_EXACT) instead of taking the exploding trial steps as rejected
+    # (cfg.stiff_exact) instead of taking the exploding trial steps as rejected
     res = {}
     for v, exact in (("0", "0"), ("1", "0"), ("1", "1")):
-        monkeypatch.setenv("RSFM_STIFF", v)
-        monkeypatch.setenv("RSFM_STIFF_EXACT", exact)
+        m.solver_variant = "stiff" if v == "1" else "default"
+        m.stiff_exact = exact == "1"
         o = m.evaluate_batch(dcs)
         assert np.all(o["status"].cpu().numpy() == 0)
         res[v + ("x" if exact == "1" else "")] = (o["acc"].t().cpu().numpy(), o["nstep"].cpu().numpy())

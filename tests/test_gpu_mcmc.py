@@ -413,15 +413,13 @@ def test_out_of_bounds_walk_with_idle_warps_and_pooled_sums(cuda, pkg):
     assert np.array_equal(out_p, out)                          # no adaptation before adapt_start: same chains
 
 
-@pytest.mark.parametrize("spec_depth", ["", "0"])
-def test_stiff_velocity_step_chains_replay_through_oracle(cuda, pkg, orc, monkeypatch, spec_depth):
+@pytest.mark.parametrize("spec_depth", [0, 1])
+def test_stiff_velocity_step_chains_replay_through_oracle(cuda, pkg, orc, spec_depth):
     """cfg-4 style at reduced size (velocity steps x10, Dc ~ 0.05: stability-limited DOP853): the stiff kernel
-    variant inside the sampler -- speculative kernel and, with RSFM_SPEC_DEPTH=0, the sequential one.  The draws the
+    variant inside the sampler -- speculative kernel and, with cfg.spec_depth = 1, the sequential one.  The draws the
     kernel used are replayed on the CPU oracle: same accept / reject decision at every step."""
     import ctypes as C
     torch = cuda
-    if spec_depth:
-        monkeypatch.setenv("RSFM_SPEC_DEPTH", spec_depth)
     n, t_end, period, factor = 400, 40.0, 10.0, 10.0
     om = orc.make_model(Dc=0.05, number_time_steps=n, end_time=t_end, loading=orc.LOAD_VSTEP, vstep_period=period,
                         vstep_factor=factor)
@@ -432,7 +430,7 @@ def test_stiff_velocity_step_chains_replay_through_oracle(cuda, pkg, orc, monkey
     model = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
     model.loading, model.vstep_period, model.vstep_factor = "vstep", period, factor
     cfg = model.to_cfg()
-    cfg.n_params, cfg.n_prior_len = 1, 3
+    cfg.n_params, cfg.n_prior_len, cfg.spec_depth = 1, 3, spec_depth
     cfg.lo[0], cfg.hi[0] = 0.03, 0.09
     c, ns = 32, 12
     dev = torch.device("cuda", 0)
