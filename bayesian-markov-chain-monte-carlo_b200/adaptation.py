@@ -9,7 +9,108 @@ covariance of ALL chains' draws, pooled over ranks by one all-reduce of
 """
 import numpy as np
 
+from . import _lib
+from .sharding import all_gather_rows, max_pool_groups
+
 EPS_REL = 1e-10
+
+
+class PooledAdaptation:
+    """Device-side pooled adaptive Metropolis around a ``rsfm_sampler`` (generalises
+    MCMC.py:162-204, 523-527).  Per interval j of ``adapt_interval`` iterations, with no host synchronisation:
+
+        main stream   [update(j-2)]  rsfm_run(j)  rsfm_pooled_partials(j)
+        side stream                               all-gather(j) ............
+
+    ``partials`` are sums over fixed groups of 1,024 chains aligned on the global chain id; the all-gather
+    (NCCL over NVLink; nothing for one rank) puts every rank's rows in global chain order and
+    ``rsfm_pooled_update`` adds them to the running moments in that order, forms (2.38^2/d) cov and its
+    Cholesky factor in closed form and installs it for every chain -- the same bits on every rank and for any
+    number of ranks.  The all-gather of interval j overlaps the kernel of interval j+1; its factor is used from
+    interval j+2 on (adaptation lags one interval, as SURVEY 8e allows).
+
+    Use: ``before_interval()`` -> launch the interval's iterations on the current stream ->
+    ``after_interval(end_iteration)``; ``finish()`` at the end."""
+
+    def __init__(self, torch, lib, handle, dev, d, n_chains_total, world, adapt_start, stream):
+        self.torch, self.lib, self.handle, self.dev, self.d = torch, lib, handle, dev, d
+        self.world, self.adapt_start, self.stream = world, int(adapt_start), stream
+        self.tri = d * (d + 1) // 2
+        g, self.rows = _lib.POOL_GROUP, _lib.POOL_ROWS
+        ng_local = int(lib.rsfm_pooled_groups(handle))
+        ng = max_pool_groups(n_chains_total, world, g) if world > 1 else ng_local
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
+        self.loc = [z(ng, self.rows), z(ng, self.rows)]
+        self.parts = [z(world * ng, self.rows), z(world * ng, self.rows)] if world > 1 else self.loc
+        self.moments = z(1 + d + self.tri)
+        self.hist = z(64, 1 + self.tri)
+        self.side = torch.cuda.Stream(dev) if world > 1 else None
+        self.main = torch.cuda.current_stream(dev)
+        self.gathered, self.ends, self.tev = {}, {}, []
+        self.j = 0
+
+    def preload(self, moments, pending_rows, end_iteration):
+        """State of a checkpoint taken on an adaptation boundary: the moments already applied and the gathered
+        rows of the interval that ended there (they are applied one interval late)."""
+        torch = self.torch
+        pend = np.asarray(pending_rows, dtype=np.float64).reshape(-1, self.rows)
+        if pend.shape[0] != self.parts[1].shape[0]:
+            raise ValueError("checkpoint was written with a different number of ranks / chains")
+        self.moments.copy_(torch.as_tensor(np.asarray(moments, dtype=np.float64)))
+        self.parts[1].copy_(torch.as_tensor(pend))
+        self.gathered[-1], self.ends[-1] = self.main.record_event(), int(end_iteration)
+
+    def _update(self, j):
+        """moments += rows(j) and, past adapt_start, install the factor they give (main stream)."""
+        torch = self.torch
+        self.main.wait_event(self.gathered[j])
+        acc = 1 if self.ends[j] > self.adapt_start // 2 else 0          # the earliest draws stay out of the moments
+        inst = 1 if self.ends[j] >= self.adapt_start else 0
+        if j + 1 >= self.hist.shape[0]:
+            self.hist = torch.cat([self.hist, torch.zeros_like(self.hist)])
+        p = self.parts[j % 2]
+        _lib.check(self.lib.rsfm_pooled_update(self.handle, _lib.ptr(p), int(p.shape[0]), _lib.ptr(self.moments), acc, inst,
+                                               _lib.ptr(self.hist[j + 1]), self.stream), "rsfm_pooled_update")
+
+    def before_interval(self):
+        if (self.j - 2) in self.gathered:
+            self._update(self.j - 2)
+
+    def after_interval(self, end_iteration):
+        torch, j = self.torch, self.j
+        self.ends[j] = int(end_iteration)
+        _lib.check(self.lib.rsfm_pooled_partials(self.handle, _lib.ptr(self.loc[j % 2]), 1, self.stream), "rsfm_pooled_partials")
+        ready = self.main.record_event()
+        if self.world > 1:
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ready)
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(self.side)
+                all_gather_rows(self.parts[j % 2], self.loc[j % 2])
+                t1.record(self.side)
+                self.tev.append((t0, t1))
+                self.gathered[j] = self.side.record_event()
+        else:
+            self.gathered[j] = ready
+        self.j += 1
+
+    def finish(self):
+        """Apply what an uninterrupted run would have applied before its next interval; the last interval's rows
+        stay pending (one-interval lag) and are returned with the moments for a checkpoint.  Synchronises."""
+        torch = self.torch
+        if (self.j - 2) in self.gathered:
+            self._update(self.j - 2)
+        pending = None
+        if (self.j - 1) in self.gathered:
+            self.main.wait_event(self.gathered[self.j - 1])
+            pending = self.parts[(self.j - 1) % 2].clone()
+        torch.cuda.synchronize(self.dev)
+        h = self.hist.cpu().numpy()
+        self.history = [(self.ends[k], h[k + 1, 1:].copy()) for k in sorted(self.ends) if h[k + 1, 0] == 1.0]
+        self.stats = {"n_adaptations": len(self.history), "n_intervals": self.j,
+                      "collective_ms_on_side_stream": float(sum(a.elapsed_time(b) for a, b in self.tev)),
+                      "pool_rows_gathered": int(self.parts[0].shape[0])}
+        return self.moments, pending
 
 
 def moments_from_suffstats(s, d):

@@ -27,7 +27,7 @@ import time
 import numpy as np
 
 from . import _lib
-from .sharding import ChainShard, all_gather_rows, max_pool_groups, rank_and_world
+from .sharding import ChainShard, rank_and_world
 
 # result arrays larger than this are copied to the host in chunks while the chains are still running
 _OVERLAP_BYTES = 128 << 20
@@ -366,89 +366,29 @@ class MCMC:
         factor in closed form and installs it for every chain -- the same bits on every rank and for any
         number of ranks.  The all-gather of interval j overlaps run(j+1); its factor is used from
         interval j+2 on (adaptation lags one interval, as SURVEY 8e allows)."""
-        tri = d * (d + 1) // 2
+        from .adaptation import PooledAdaptation
         w = max(1, int(self.adapt_interval))
         rank, world = rank_and_world() if self.shard else (0, 1)
-        g, rows = _lib.POOL_GROUP, _lib.POOL_ROWS
-        ng_local = int(lib.rsfm_pooled_groups(handle))
-        ng = max_pool_groups(self.n_chains, world, g) if world > 1 else ng_local
-        loc = [torch.zeros((ng, rows), dtype=torch.float64, device=dev) for _ in range(2)]
-        parts = [torch.zeros((world * ng, rows), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else loc
-        moments = torch.zeros(1 + d + tri, dtype=torch.float64, device=dev)
+        pool = PooledAdaptation(torch, lib, handle, dev, d, self.n_chains, world, self.adapt_start, stream)
         done = int(lib.rsfm_iteration(handle))            # > 0 after a resume
-        first = done
         if self.resume is not None and "pooled_moments" in self.resume:
             if done % w:
                 raise ValueError("a pooled-adaptation checkpoint continues exactly only from an adaptation "
                                  f"boundary (iteration {done} is not a multiple of adapt_interval = {w})")
-            moments.copy_(torch.as_tensor(np.asarray(self.resume["pooled_moments"], dtype=np.float64)))
-            pend = np.asarray(self.resume["pooled_pending"], dtype=np.float64).reshape(-1, rows)
-            if pend.shape[0] != parts[0].shape[0]:
-                raise ValueError("checkpoint was written with a different number of ranks / chains")
-        n_int = (first + ns + w - 1) // w - first // w
-        hist = torch.zeros((n_int + 2, 1 + tri), dtype=torch.float64, device=dev)
-        side = torch.cuda.Stream(dev)
-        main = torch.cuda.current_stream(dev)
-        gathered, ends, tev = {}, {}, []
-        half = self.adapt_start // 2
-
-        def update(j, install_ok=True):
-            """moments += rows(j) and, past adapt_start, install the factor they give (on the main stream)."""
-            main.wait_event(gathered[j])
-            acc = 1 if ends[j] > half else 0
-            inst = 1 if (install_ok and ends[j] >= self.adapt_start) else 0
-            _lib.check(lib.rsfm_pooled_update(handle, _lib.ptr(parts[j % 2]), int(parts[j % 2].shape[0]), _lib.ptr(moments),
-                                              acc, inst, _lib.ptr(hist[j + 1]), stream), "rsfm_pooled_update")
-
-        j = 0
-        if self.resume is not None and "pooled_moments" in self.resume:
-            # the interval that ended at the checkpoint was gathered but not yet applied (see below)
-            parts[1].copy_(torch.as_tensor(pend))
-            gathered[-1], ends[-1] = main.record_event(), done
+            pool.preload(self.resume["pooled_moments"], self.resume["pooled_pending"], done)
         pos = 0
         while pos < ns:
-            k = min(w - (done % w), ns - pos)
-            if (j - 2) in gathered:
-                update(j - 2)
-            elif j == 1 and -1 in gathered:
-                update(-1)
+            k = min(w - (done % w), ns - pos)             # intervals end on absolute multiples of adapt_interval
+            pool.before_interval()
             run_iters(k, pos)
             pos += k
             done += k
-            ends[j] = done
-            _lib.check(lib.rsfm_pooled_partials(handle, _lib.ptr(loc[j % 2]), 1, stream), "rsfm_pooled_partials")
-            ready = main.record_event()
-            if world > 1:
-                with torch.cuda.stream(side):
-                    side.wait_event(ready)
-                    t0 = torch.cuda.Event(enable_timing=True)
-                    t1 = torch.cuda.Event(enable_timing=True)
-                    t0.record(side)
-                    all_gather_rows(parts[j % 2], loc[j % 2])
-                    t1.record(side)
-                    tev.append((t0, t1))
-                    gathered[j] = side.record_event()
-            else:
-                gathered[j] = ready
+            pool.after_interval(done)
             pipe.push([1 + pos, 1 + pos, pos])
-            j += 1
-        # drain: what an uninterrupted run would have applied before its next interval; the last interval's
-        # rows stay pending (they would be applied one interval later) and go into the checkpoint
-        if j >= 2:
-            update(j - 2)
-        elif j == 1 and -1 in gathered:
-            update(-1)
-        main.wait_event(gathered[j - 1])
-        self._pooled_state = (moments, parts[(j - 1) % 2].clone())
-        torch.cuda.synchronize(dev)
-        h = hist.cpu().numpy()
-        keys = sorted(k_ for k_ in ends if k_ + 1 < h.shape[0] and k_ + 1 >= 0)
-        self.adapt_history = [(ends[k_], h[k_ + 1, 1:].copy()) for k_ in keys if h[k_ + 1, 0] == 1.0]
-        coll_ms = sum(a.elapsed_time(b) for a, b in tev)
-        self._pooled_stats = {"n_adaptations": len(self.adapt_history), "n_intervals": j,
-                              "collective_ms_on_side_stream": coll_ms, "pool_rows_gathered": int(parts[0].shape[0])}
+        self._pooled_state = pool.finish()
+        self.adapt_history = pool.history
+        self._pooled_stats = pool.stats
 
-    # ------------------------------------------------------------------
     # ------------------------------------------------------------------
     def checkpoint(self, filename=None):
         """State needed to continue the chains exactly where they stopped (the reference has no

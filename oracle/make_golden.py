@@ -12,6 +12,8 @@ so parity is pinned on outputs of the reference itself, imported from
         run with np.random.seed(...), with every random draw logged
         (proposal, uniform, unit-scale gamma) plus accept flags, chain and std2.
   G3  sse_grid.json   SSE(Dc) on a grid for the seeded data set (MCMC.py:387).
+  G4  rhs_values.json   the nested RHS ``friction(t, y)`` (RateStateModel.py:277-355) at fixed states
+        (``python oracle/make_golden.py rhs``).
 
 Everything is written in the reference's own ``__ndarray__`` JSON wire format
 (json_save_load.py:37-38).  Versions of numpy/scipy are stamped into each file:
@@ -142,9 +144,69 @@ def record_chain(rsm, mcm, data, dc_true, qpriors, qstart, nsamples, seed):
     }
 
 
+def capture_friction(rsm, model):
+    """The reference's RHS is a function nested inside evaluate() (RateStateModel.py:277-355); it is handed to
+    ``integrate.ode(friction)`` (:374).  Swapping that class for a recorder for the duration of ONE evaluate()
+    call yields the unmodified closure, callable at any (t, y); the integration loop sees successful() False
+    and exits at once."""
+    got = {}
+
+    class Recorder:
+        def __init__(self, f):
+            got["f"] = f
+
+        def set_integrator(self, *a, **k):
+            return self
+
+        def set_initial_value(self, *a, **k):
+            return self
+
+        def successful(self):
+            return False
+
+    real = rsm.integrate.ode
+    rsm.integrate.ode = Recorder
+    try:
+        model.evaluate()
+    finally:
+        rsm.integrate.ode = real
+    return got["f"]
+
+
+def make_rhs_values(rsm):
+    """G4 rhs_values.json: friction(t, y) of the unmodified reference at fixed (t, y, Dc), both damping modes:
+    states near sliding steady state (where the CUDA path uses its short series) and far from it (where it
+    uses the general-range formulas)."""
+    rng = np.random.default_rng(2718)
+    rows = []
+    for damping in (True, False):
+        for dc in (0.05, 1.0, 50.0, 130.0, 1000.0, 1350.0, 10000.0):
+            m = rsm.RateStateModel()
+            m.RadiationDamping = damping
+            m.Dc = dc
+            f = capture_friction(rsm, m)
+            for near in (True, False):
+                for _ in range(6):
+                    t = float(rng.uniform(0.0, 50.0))
+                    if near:
+                        th = dc * (1.0 + rng.uniform(-1.5e-4, 1.5e-4))
+                        mu = 0.6 + rng.uniform(-3e-5, 3e-5)
+                    else:
+                        th = dc * float(np.exp(rng.uniform(-1.0, 1.0)))
+                        mu = 0.6 + rng.uniform(-0.02, 0.02)
+                    y = np.array([mu, th, 1.0 + rng.uniform(-1e-3, 1e-3)])
+                    out = np.asarray(f(t, y), dtype=np.float64).reshape(3)
+                    rows.append([float(damping), dc, t, y[0], y[1], y[2], out[0], out[1], out[2]])
+    return {"columns": ["RadiationDamping", "Dc", "t", "mu", "theta", "V", "dmu", "dtheta", "dV"],
+            "rows": np.array(rows)}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     rsm, mcm = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "rhs":
+        dump("rhs_values.json", make_rhs_values(rsm))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
         data_cfg1 = make_data(rsm, 1325.0, 2024)
         dump("chain_cfg1_full.json",
@@ -193,6 +255,7 @@ def main():
     # a chain that starts near the upper bound so that out-of-bounds proposals occur (q10)
     dump("chain_bounds.json",
          record_chain(rsm, mcm, data, 1350.0, ["Uniform", 900.0, 1500.0], 1450.0, nsamples=60, seed=99))
+    dump("rhs_values.json", make_rhs_values(rsm))
 
 
 if __name__ == "__main__":

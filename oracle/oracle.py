@@ -17,6 +17,8 @@ _SO = os.path.join(_HERE, "librsf_oracle.so")
 
 LOAD_SINE_DECAY = 0
 LOAD_VSTEP = 1
+OBS_ACC = 0
+OBS_MU = 1
 
 
 class OrcModel(C.Structure):
@@ -31,6 +33,7 @@ class OrcModel(C.Structure):
         ("vstep_period", C.c_double), ("vstep_factor", C.c_double),
         ("rtol", C.c_double), ("atol", C.c_double),
         ("nmax", C.c_int),
+        ("observable", C.c_int),
     ]
 
 
@@ -76,6 +79,11 @@ def lib():
         _lib.orc_chain_replay.restype = C.c_int
         _lib.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                            C.POINTER(C.c_uint32)]
+        _lib.orc_chain_replay_nd.argtypes = [C.POINTER(OrcModel), dp, C.c_int, C.c_int, dp, dp, dp, C.c_int, C.c_int,
+                                             dp, dp, dp, dp, dp, C.POINTER(C.c_uint8), C.POINTER(C.c_int64)]
+        _lib.orc_chain_replay_nd.restype = C.c_int
+        _lib.orc_philox_draws.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_double, dp]
+        _lib.orc_philox_draws.restype = None
     return _lib
 
 
@@ -174,3 +182,33 @@ def philox4x32_10(ctr, key) -> np.ndarray:
     o = (C.c_uint32 * 4)()
     lib().orc_philox4x32_10(c, k, o)
     return np.array(list(o), dtype=np.uint32)
+
+
+def chain_replay_nd(m: OrcModel, data, qstart, lo, hi, n_prior_len, nsamples, proposals, uniforms, gammas):
+    """d-parameter replay (d = 1: Dc; d = 3: a, b, Dc) with ABSOLUTE proposals [nsamples, d] and per-parameter
+    bounds.  Returns (chain [nsamples+1, d], s2 [nsamples+1], accepts [nsamples], nsolves)."""
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    qstart = np.ascontiguousarray(np.atleast_1d(qstart), dtype=np.float64)
+    d = qstart.size
+    lo = np.ascontiguousarray(np.broadcast_to(lo, (d,)), dtype=np.float64)
+    hi = np.ascontiguousarray(np.broadcast_to(hi, (d,)), dtype=np.float64)
+    proposals = np.ascontiguousarray(proposals, dtype=np.float64).reshape(nsamples, d)
+    uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+    gammas = np.ascontiguousarray(gammas, dtype=np.float64)
+    chain = np.zeros((nsamples + 1, d))
+    s2 = np.zeros(nsamples + 1)
+    acc = np.zeros(nsamples, dtype=np.uint8)
+    nsolves = C.c_int64()
+    rc = lib().orc_chain_replay_nd(C.byref(m), _dp(data), data.size, d, _dp(qstart), _dp(lo), _dp(hi),
+                                   int(n_prior_len), int(nsamples), _dp(proposals), _dp(uniforms), _dp(gammas),
+                                   _dp(chain), _dp(s2), acc.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(nsolves))
+    if rc != 0:
+        raise RuntimeError(f"oracle chain_replay_nd failed ({rc})")
+    return chain, s2, acc, nsolves.value
+
+
+def philox_draws(seed: int, chain: int, iteration: int, shape: float) -> np.ndarray:
+    """(z0, z1, z2, U, unit gamma, gamma attempts) of one chain and iteration on the CUDA path's Philox stream."""
+    out = np.zeros(6)
+    lib().orc_philox_draws(C.c_uint64(seed), C.c_uint64(chain), C.c_uint32(iteration), float(shape), _dp(out))
+    return out

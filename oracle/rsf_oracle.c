@@ -2,6 +2,7 @@
  * See rsf_oracle.h for scope, citations and the pinning statement.
  * Build: make -C oracle      (gcc -O2 -ffp-contract=off -pthread)
  */
+#define _GNU_SOURCE   /* M_PI */
 #include "rsf_oracle.h"
 #include "dop853_coeffs.h"
 
@@ -42,6 +43,7 @@ void orc_model_defaults(orc_model *m)
     m->loading = ORC_LOAD_SINE_DECAY;
     m->vstep_period = 1000.0; m->vstep_factor = 10.0;
     m->rtol = 1e-6; m->atol = 1e-10; m->nmax = 500;
+    m->observable = ORC_OBS_ACC;
 }
 
 /* load-point velocity.  SINE_DECAY is the reference (RateStateModel.py:327-329);
@@ -274,6 +276,14 @@ int orc_forward(const orc_model *m, double *t_out, double *mu_out,
     return num_steps;
 }
 
+/* the series the sampler scores: model.evaluate()[1] (MCMC.py:127) -- acc for the reference, mu for the
+ * friction-series extension (mu[0] = mu_ref, :367; mu[k] = r.y[0], :385) */
+static int orc_observe(const orc_model *m, double *obs, orc_stats *st)
+{
+    if (m->observable == ORC_OBS_MU) return orc_forward(m, NULL, obs, NULL, NULL, NULL, st);
+    return orc_forward(m, NULL, NULL, NULL, NULL, obs, st);
+}
+
 /* sum((acc - data)**2) with numpy's pairwise reduction (blocks of 128, eight
  * partial sums), MCMC.py:387 */
 static double pairwise_sq(const double *a, const double *d, int n)
@@ -321,7 +331,7 @@ static void *batch_worker(void *arg)
         mm.Dc = j->dc[c];
         orc_stats st;
         double *acc = j->acc_out ? j->acc_out + (size_t)c * j->n : scratch;
-        int ns = orc_forward(&mm, NULL, NULL, NULL, NULL, acc, &st);
+        int ns = orc_observe(&mm, acc, &st);
         if (ns != j->n) { atomic_fetch_add(&j->bad, 1); continue; }
         if (j->sse_out && j->data) j->sse_out[c] = orc_sse(acc, j->data, j->n);
         if (j->nrhs_out) j->nrhs_out[c] = st.nrhs;
@@ -370,9 +380,9 @@ int orc_chain_replay(const orc_model *m0, const double *data, int n,
     int64_t solves = 0;
     /* compute_initial_covariance, MCMC.py:245-266 */
     m.Dc = qstart;
-    if (orc_forward(&m, 0, 0, 0, 0, acc, 0) != n) { free(acc); free(acc_dq); return -1; }
+    if (orc_observe(&m, acc, 0) != n) { free(acc); free(acc_dq); return -1; }
     m.Dc = m.Dc * (1 + 1e-6);
-    orc_forward(&m, 0, 0, 0, 0, acc_dq, 0);
+    orc_observe(&m, acc_dq, 0);
     solves += 2;
     s2[0] = orc_sse(acc, data, n) / (n - n_prior_len);        /* :261 */
     double xtx = 0.0;
@@ -385,7 +395,7 @@ int orc_chain_replay(const orc_model *m0, const double *data, int n,
     if (vstart_out) *vstart_out = V;
     /* SSqprev = SSqcalc(qstart), :468 */
     m.Dc = qstart;
-    orc_forward(&m, 0, 0, 0, 0, acc, 0);
+    orc_observe(&m, acc, 0);
     solves++;
     double ss = orc_sse(acc, data, n);
     double q = qstart;
@@ -395,7 +405,7 @@ int orc_chain_replay(const orc_model *m0, const double *data, int n,
         int ok = (qn > lo) && (qn < hi);                      /* :318-320, strict */
         if (ok) {
             m.Dc = qn;
-            orc_forward(&m, 0, 0, 0, 0, acc, 0);              /* :324 */
+            orc_observe(&m, acc, 0);              /* :324 */
             solves++;
             double ssn = orc_sse(acc, data, n);
             double la = 0.5 * (ss - ssn) / s2[i];             /* :327 */
@@ -426,6 +436,59 @@ int orc_chain_replay(const orc_model *m0, const double *data, int n,
     return 0;
 }
 
+/* d-parameter replay with absolute proposals: q = (Dc) or (a, b, Dc) */
+static void set_params(orc_model *m, int d, const double *q)
+{
+    if (d == 3) { m->a = q[0]; m->b = q[1]; m->Dc = q[2]; }
+    else m->Dc = q[0];
+}
+
+int orc_chain_replay_nd(const orc_model *m0, const double *data, int n, int d,
+                        const double *qstart, const double *lo, const double *hi,
+                        int n_prior_len, int nsamples, const double *proposals,
+                        const double *uniforms, const double *gammas, double *chain,
+                        double *s2, uint8_t *accept, int64_t *nsolves)
+{
+    if (d != 1 && d != 3) return -2;
+    orc_model m = *m0;
+    const double n0 = 0.01;                                   /* MCMC.py:97 */
+    double *obs = (double *)malloc(sizeof(double) * n);
+    int64_t solves = 0;
+    double q[3];
+    for (int j = 0; j < d; j++) q[j] = qstart[j];
+    set_params(&m, d, q);
+    if (orc_observe(&m, obs, 0) != n) { free(obs); return -1; }
+    solves++;
+    double ss = orc_sse(obs, data, n);                        /* :468 */
+    s2[0] = ss / (n - n_prior_len);                           /* :261 */
+    for (int j = 0; j < d; j++) chain[j] = q[j];
+    for (int i = 0; i < nsamples; i++) {
+        const double *qn = proposals + (size_t)i * d;
+        int ok = 1;
+        for (int j = 0; j < d; j++) ok = ok && (qn[j] > lo[j]) && (qn[j] < hi[j]);   /* :318-320, strict */
+        if (ok) {
+            set_params(&m, d, qn);
+            orc_observe(&m, obs, 0);                          /* :324 */
+            solves++;
+            double ssn = orc_sse(obs, data, n);
+            double la = 0.5 * (ss - ssn) / s2[i];             /* :327 */
+            if (la > 0.0) la = 0.0;
+            ok = la > log(uniforms[i]);                       /* :331 */
+            if (ok) { for (int j = 0; j < d; j++) q[j] = qn[j]; ss = ssn; }
+        }
+        accept[i] = (uint8_t)ok;
+        for (int j = 0; j < d; j++) chain[(size_t)(i + 1) * d + j] = q[j];   /* :507-517 */
+        {
+            double bval = 0.5 * (n0 * s2[i] + ss);            /* :158-160 */
+            double scale = 1 / bval;
+            s2[i + 1] = 1 / (gammas[i] * scale);
+        }
+    }
+    if (nsolves) *nsolves = solves;
+    free(obs);
+    return 0;
+}
+
 /* Philox4x32-10 */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {
@@ -442,4 +505,72 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* ---- samplers on Philox (stream layout: rsf_oracle.h) ---- */
+static double philox_u53(uint32_t hi, uint32_t lo)
+{
+    const uint64_t k = (((uint64_t)hi << 32) | lo) >> 11;
+    return ((double)k + 0.5) * 0x1.0p-53;
+}
+
+static void philox_block(uint64_t seed, uint64_t chain, uint32_t iter, uint32_t slot, uint32_t out[4])
+{
+    const uint32_t ctr[4] = { (uint32_t)chain, (uint32_t)(chain >> 32), iter, slot };
+    const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    orc_philox4x32_10(ctr, key, out);
+}
+
+/* sin(pi x), cos(pi x) for x in [0, 2): exact reduction to |r| <= 1/4 of a quadrant, then libm */
+static void sincospi_02(double x, double *s, double *c)
+{
+    const double q = floor(2.0 * x + 0.5);            /* nearest multiple of 1/2 */
+    const double r = x - 0.5 * q;                     /* exact */
+    const double sr = sin(M_PI * r), cr = cos(M_PI * r);
+    switch (((int)q) & 3) {
+        case 0: *s = sr;  *c = cr;  break;
+        case 1: *s = cr;  *c = -sr; break;
+        case 2: *s = -sr; *c = -cr; break;
+        default: *s = -cr; *c = sr; break;
+    }
+}
+
+static void philox_normal2(uint64_t seed, uint64_t chain, uint32_t iter, uint32_t slot, double *z0, double *z1)
+{
+    uint32_t r[4];
+    philox_block(seed, chain, iter, slot, r);
+    const double u1 = philox_u53(r[0], r[1]), u2 = philox_u53(r[2], r[3]);
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi_02(2.0 * u2, &s, &c);
+    *z0 = rad * c;
+    *z1 = rad * s;
+}
+
+void orc_philox_draws(uint64_t seed, uint64_t chain, uint32_t iter, double shape, double out[6])
+{
+    double zz;
+    uint32_t r[4];
+    philox_normal2(seed, chain, iter, 0u, &out[0], &out[1]);
+    philox_normal2(seed, chain, iter, 1u, &out[2], &zz);
+    philox_block(seed, chain, iter, 2u, r);
+    out[3] = philox_u53(r[0], r[1]);
+    /* Marsaglia & Tsang (2000), shape > 1: the algorithm of NumPy's legacy standard_gamma */
+    const double d = shape - 1.0 / 3.0;
+    const double c = 1.0 / sqrt(9.0 * d);
+    out[4] = d; out[5] = 64.0;
+    for (uint32_t j = 0; j < 64; j++) {
+        double x, unused;
+        philox_normal2(seed, chain, iter, 4u + 2u * j, &x, &unused);
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        philox_block(seed, chain, iter, 5u + 2u * j, r);
+        const double u = philox_u53(r[0], r[1]);
+        const double x2 = x * x;
+        if (u < 1.0 - 0.0331 * x2 * x2 || log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) {
+            out[4] = d * v; out[5] = (double)(j + 1);
+            return;
+        }
+    }
 }

@@ -31,13 +31,21 @@ class PortModel:
         self.RadiationDamping = True
         self.Dc = None
         self.n_rhs = 0
+        # extensions of the build; the defaults are the reference
+        self.loading = "sine_decay"          # "vstep": ONLY the load-point line of the RHS is swapped
+        self.vstep_period, self.vstep_factor = 1000.0, 10.0
+        self.observable = "acc"              # "mu": evaluate()[1] is the friction series (:385)
 
     def _rhs(self, t, y):
         # RateStateModel.py:318-355
         self.n_rhs += 1
         a, b, dc, v_ref = self.a, self.b, self.Dc, self.V_ref
         kprime = 1e-2 * 10 / dc
-        v_l = v_ref * (1 + exp(-t / 20) * sin(10 * t))
+        if self.loading == "vstep":
+            odd = int(np.floor((t - self.t_start) / self.vstep_period)) & 1
+            v_l = self.vstep_factor * v_ref if odd else v_ref
+        else:
+            v_l = v_ref * (1 + exp(-t / 20) * sin(10 * t))            # RateStateModel.py:327-329
         out = np.zeros((len(y), 1))
         temp = 1 / a * (y[0] - self.mu_ref - b * log(v_ref * y[1] / dc))
         v = v_ref * exp(temp)
@@ -52,9 +60,10 @@ class PortModel:
     def evaluate(self):
         """(t, acc, acc_noise) as RateStateModel.evaluate(), :357-395."""
         n = int(np.floor((self.t_final - self.t_start) / self.delta_t))
-        t, vel, acc = np.zeros(n), np.zeros(n), np.zeros(n)
+        t, vel, acc, mu = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
         t[0] = self.t_start
         vel[0] = self.V_ref
+        mu[0] = self.mu_ref
         solver = integrate.ode(self._rhs).set_integrator("dop853", rtol=1e-6, atol=1e-10)
         # the reference stores Dc/V_ref into a float array slot first (:369), so y0 holds scalars even
         # when Dc is the 1-element array MCMC.SSqcalc sets (q6); the RHS keeps using the array
@@ -64,10 +73,13 @@ class PortModel:
         while solver.successful() and k < n:
             solver.integrate(solver.t + self.delta_t)
             t[k] = solver.t
+            mu[k] = solver.y[0]
             vel[k] = solver.y[2]
             acc[k] = (vel[k] - vel[k - 1]) / self.delta_t
             k += 1
         acc_noise = acc + 1.0 * np.abs(acc) * np.random.randn(acc.shape[0])
+        if self.observable == "mu":
+            return t, mu, mu + np.abs(mu - mu[0]) * np.random.randn(n)
         return t, acc, acc_noise
 
 
@@ -117,7 +129,52 @@ def run_chain(data, qstart, lo, hi, nsamples, n_prior_len=3, seed=None, model=No
             "n_solves": solves, "n_rhs": model.n_rhs}
 
 
+def run_chain_abdc(data, qstart, lo, hi, nsamples, step_sd, seed=None, model=None):
+    """The same loop for the joint (a, b, Dc) posterior (extension, SURVEY 8f.4 / cfg 3): q = (a, b, Dc), per-parameter
+    strict bounds, a fixed diagonal random-walk proposal (a bounded CPU sample cannot pool a covariance over
+    65,536 chains; the cost per iteration -- one forward solve per in-bounds proposal -- is what is timed)."""
+    import warnings
+    from scipy.stats import gamma
+    if seed is not None:
+        np.random.seed(seed)
+    model = model or PortModel(number_time_steps=len(data))
+    n0, n = 0.01, len(data)
+    lo, hi, step_sd = (np.asarray(x, dtype=np.float64) for x in (lo, hi, step_sd))
+
+    def sse3(q):
+        model.a, model.b = float(q[0]), float(q[1])
+        return sse(model, q[2], data)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        q = np.asarray(qstart, dtype=np.float64).copy()
+        ss = sse3(q)
+        std2 = [ss / (n - 3)]
+        solves = 1
+        chain, accepts = [q.copy()], []
+        for _ in range(nsamples):
+            qn = q + step_sd * np.random.randn(3)
+            ok = bool(np.all((qn > lo) & (qn < hi)))
+            if ok:
+                ssn = sse3(qn)
+                solves += 1
+                ok = min(0.0, 0.5 * (ss - ssn) / std2[-1]) > np.log(np.random.rand(1))[0]
+                if ok:
+                    q, ss = qn, ssn
+            chain.append(q.copy())
+            accepts.append(ok)
+            std2.append(1 / gamma.rvs(0.5 * (n0 + n), scale=1 / (0.5 * (n0 * std2[-1] + ss)), size=1)[0])
+    return {"chain": np.array(chain), "std2": np.array(std2), "accepts": np.array(accepts),
+            "n_solves": solves, "n_rhs": model.n_rhs}
+
+
 def _worker(args):
+    if len(args) == 7:
+        data, qstart, lo, hi, nsamples, seed, step_sd = args
+        import time
+        t0 = time.perf_counter()
+        r = run_chain_abdc(data, qstart, lo, hi, nsamples, step_sd, seed=seed)
+        return r["n_solves"], time.perf_counter() - t0, r["chain"]
     data, qstart, lo, hi, nsamples, seed = args
     import time
     t0 = time.perf_counter()
@@ -125,13 +182,17 @@ def _worker(args):
     return r["n_solves"], time.perf_counter() - t0, r["chain"]
 
 
-def run_chains_parallel(data, qstarts, lo, hi, nsamples, seeds, processes):
+def run_chains_parallel(data, qstarts, lo, hi, nsamples, seeds, processes, step_sd=None):
     """Independent chains on `processes` host cores (the reference itself is single-threaded and not
-    re-entrant -- global RNG, shared model.Dc -- so separate processes are the only valid way)."""
+    re-entrant -- global RNG, shared model.Dc -- so separate processes are the only valid way).
+    step_sd given: joint (a, b, Dc) chains (qstarts [C, 3], lo / hi [3])."""
     import multiprocessing as mp
     import time
     ctx = mp.get_context("fork")
-    jobs = [(data, float(q), lo, hi, nsamples, int(s)) for q, s in zip(qstarts, seeds)]
+    if step_sd is not None:
+        jobs = [(data, np.asarray(q, dtype=np.float64), lo, hi, nsamples, int(s), step_sd) for q, s in zip(qstarts, seeds)]
+    else:
+        jobs = [(data, float(q), lo, hi, nsamples, int(s)) for q, s in zip(qstarts, seeds)]
     t0 = time.perf_counter()
     with ctx.Pool(processes) as pool:
         res = pool.map(_worker, jobs)

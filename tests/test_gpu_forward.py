@@ -3,13 +3,46 @@ and with golden vectors from the unmodified reference."""
 import numpy as np
 import pytest
 
-from conftest import load_golden
+import json
+import os
+
+from conftest import ROOT, load_golden, oracle_ulp_floor
 
 pytestmark = pytest.mark.gpu
 
 # |acc_gpu - acc_ref| <= 1e-9 * max|acc_ref| + 1e-12 outside the stiff regime,
 # 1e-6 * max|acc_ref| for Dc < 50 where accepted-step sequences may legitimately differ.
 RTOL, ATOL, RTOL_STIFF = 1e-9, 1e-12, 1e-6
+# Velocity-step loading in the stability-limited regime: the reference solver itself is reproducible only to its
+# own tolerance there -- a ONE-ulp change of Dc moves the CPU oracle's trajectory by 2-4e-6 of its scale, and SciPy
+# and the C oracle differ by the same amount (tests/test_oracle_vs_scipy.py) -- so the stated 1e-6 is below what any
+# two correct implementations can agree to.  The gate is max(1e-6, STIFF_FLOOR_MULT x the floor measured on the
+# oracle for the very case under test); the observed errors are recorded (gpurun_out/observed_parity.json).
+STIFF_FLOOR_MULT = 4.0
+
+
+def _record(name, **values):
+    path = os.path.join(ROOT, "gpurun_out", "observed_parity.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        try:
+            log = json.load(open(path))
+        except (OSError, ValueError):
+            log = {}
+        log[name] = values
+        json.dump(log, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def _check_stiff(orc, acc_g, dc, tag, **model_kw):
+    """GPU trajectory against the oracle with the measured-floor gate; returns (err, floor), both relative."""
+    acc_o, scale, floor = oracle_ulp_floor(orc, dc, **model_kw)
+    err = float(np.max(np.abs(acc_g - acc_o))) / scale
+    gate = max(RTOL_STIFF, STIFF_FLOOR_MULT * floor)
+    _record(tag, Dc=dc, err_rel=err, oracle_ulp_floor_rel=floor, gate_rel=gate)
+    assert err <= gate, f"{tag}: err {err:.3e} > gate {gate:.3e} (oracle floor {floor:.3e})"
+    return err, floor
 
 
 def _check(acc_g, acc_ref, dc):
@@ -195,11 +228,9 @@ def test_unstable_step_is_rejected_after_velocity_jump(cuda, pkg, orc):
     out = m.evaluate_batch(dcs)
     assert np.all(out["status"].cpu().numpy() == 0)
     acc_g = out["acc"].t().cpu().numpy()
-    _, acc_o, _ = orc.forward_batch(orc.make_model(number_time_steps=n, end_time=t_end, **kw), dcs, want_acc=True)
     for i in range(len(dcs)):
         assert np.all(np.isfinite(acc_g[i]))
-        scale = np.max(np.abs(acc_o[i]))
-        assert np.max(np.abs(acc_g[i] - acc_o[i])) <= 2e-5 * scale
+        _check_stiff(orc, acc_g[i], dcs[i], f"vstep_jump_n2400_Dc{dcs[i]}", number_time_steps=n, end_time=t_end, **kw)
 
 
 def test_batch_position_invariance_at_131072(cuda, pkg):
@@ -276,7 +307,7 @@ def test_stiff_variant_on_reference_loading_and_both_variants_on_vstep(cuda, pkg
     dcs = np.array([0.05, 0.3, 2.0, 40.0, 400.0])
     m = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
     m.loading, m.vstep_period, m.vstep_factor = "vstep", 30.0, 10.0
-    _, acc_o, _ = orc.forward_batch(orc.make_model(number_time_steps=n, end_time=t_end, **kw), dcs, want_acc=True)
+    floors = [oracle_ulp_floor(orc, dc, number_time_steps=n, end_time=t_end, **kw) for dc in dcs]
     # "1x": the stiff variant scoring every step that left the fast ranges with the general-range stages
     # (cfg.stiff_exact) instead of taking the exploding trial steps as rejected
     res = {}
@@ -287,10 +318,14 @@ def test_stiff_variant_on_reference_loading_and_both_variants_on_vstep(cuda, pkg
         assert np.all(o["status"].cpu().numpy() == 0)
         res[v + ("x" if exact == "1" else "")] = (o["acc"].t().cpu().numpy(), o["nstep"].cpu().numpy())
     for i in range(len(dcs)):
-        scale = np.max(np.abs(acc_o[i]))
+        acc_o, scale, floor = floors[i]
+        gate = max(RTOL_STIFF if dcs[i] < 50 else RTOL, STIFF_FLOOR_MULT * floor)
+        errs = {v: float(np.max(np.abs(res[v][0][i] - acc_o))) / scale for v in res}
+        _record(f"vstep_variants_n1200_Dc{dcs[i]}", Dc=dcs[i], oracle_ulp_floor_rel=floor, gate_rel=gate,
+                **{"err_rel_" + v: e for v, e in errs.items()})
         for v in res:
-            assert np.max(np.abs(res[v][0][i] - acc_o[i])) <= 2e-5 * scale, (v, dcs[i])
-        assert np.max(np.abs(res["0"][0][i] - res["1"][0][i])) <= 2e-5 * scale
+            assert errs[v] <= gate, (v, dcs[i], errs[v], gate)
+        assert np.max(np.abs(res["0"][0][i] - res["1"][0][i])) <= 2 * gate * scale
     # same controller semantics: attempted-step counts of the variants differ by well under 1 %
     for v in ("1", "1x"):
         assert np.all(np.abs(res["0"][1].astype(float) - res[v][1]) <= 0.01 * res["0"][1]), v
@@ -310,7 +345,35 @@ def test_stiff_variant_per_chain_a_b(cuda, pkg, orc):
     assert np.all(out["status"].cpu().numpy() == 0)
     acc_g = out["acc"].t().cpu().numpy()
     for i in range(c):
-        _, acc_o, _ = orc.forward(orc.make_model(Dc=dc[i], a=a[i], b=b[i], number_time_steps=n, end_time=t_end,
-                                                 loading=orc.LOAD_VSTEP, vstep_period=15.0, vstep_factor=10.0))
-        scale = np.max(np.abs(acc_o))
-        assert np.max(np.abs(acc_g[i] - acc_o)) <= 2e-5 * scale, (i, dc[i])
+        _check_stiff(orc, acc_g[i], dc[i], f"vstep_abdc_n600_chain{i}", a=a[i], b=b[i], number_time_steps=n, end_time=t_end,
+                     loading=orc.LOAD_VSTEP, vstep_period=15.0, vstep_factor=10.0)
+
+
+@pytest.mark.parametrize("dcs", [(0.03, 0.05, 0.08)])
+def test_cfg4_full_size_trajectories_vs_oracle(cuda, pkg, orc, dcs):
+    """cfg 4 at its stated size: N = 100,000 output points over 10,000 s, load velocity x10 every
+    1,000 s, Dc in the stability-limited regime -- single trajectories on the GPU (stiff kernel variant, TMA-streamed
+    series) against the C oracle (about 2e7 RHS evaluations each).  Gate and recorded numbers as in _check_stiff;
+    the SSE accumulated against a streamed series equals the oracle's sum over ITS trajectory to the same level."""
+    n, t_end = 100_000, 10_000.0
+    kw = dict(number_time_steps=n, end_time=t_end, loading=orc.LOAD_VSTEP, vstep_period=1000.0, vstep_factor=10.0)
+    m = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
+    m.loading, m.vstep_period, m.vstep_factor = "vstep", 1000.0, 10.0
+    rng = np.random.default_rng(4)
+    truth = orc.forward(orc.make_model(Dc=0.05, **kw))[1]
+    data = truth + 0.2 * np.abs(truth) * rng.standard_normal(n)
+    out = m.evaluate_batch(np.array(dcs), data=data, want_t=True)
+    assert np.all(out["status"].cpu().numpy() == 0) and np.all(out["filled"].cpu().numpy() == n)
+    acc_g = out["acc"].t().cpu().numpy()
+    sse_g = out["sse"].cpu().numpy()
+    nrhs_g = out["nrhs"].cpu().numpy()
+    for i, dc in enumerate(dcs):
+        err, floor = _check_stiff(orc, acc_g[i], dc, f"cfg4_full_N100000_Dc{dc}", **kw)
+        acc_o = orc.forward(orc.make_model(Dc=dc, **kw))[1]
+        sse_o = float(np.sum((acc_o - data) ** 2))
+        sse_self = float(np.sum((acc_g[i] - data) ** 2))
+        assert sse_g[i] == pytest.approx(sse_self, rel=1e-11)                 # streamed SSE = sum over its own trajectory
+        assert sse_g[i] == pytest.approx(sse_o, rel=max(1e-5, 50 * floor))
+        assert 1.0e7 < nrhs_g[i] < 6.0e7                                      # ~2e7 RHS per solve (SURVEY 8d)
+    # the likelihood the sampler sees is usable at this size: SSE is smallest at the true Dc
+    assert np.argmin(sse_g) == 1

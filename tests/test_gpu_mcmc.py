@@ -456,3 +456,292 @@ def test_stiff_velocity_step_chains_replay_through_oracle(cuda, pkg, orc, spec_d
         assert np.array_equal(acc[:, ch], acc_o)
         assert np.array_equal(samples[:, 0, ch], chain_o[1:])
         assert np.allclose(s2[:, ch], s2_o[1:], rtol=1e-4, atol=0)          # SSE to ~1e-6 in the stiff regime
+
+
+def _run_with_draws(torch, pkg, cfg, c, seed, id0, q0, data, ns_list):
+    """rsfm_create / init / run through the C ABI with the draws dumped; returns per-iteration arrays."""
+    import ctypes as C
+    lib = pkg._lib.load()
+    d = cfg.n_params
+    q0_t = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(q0, dtype=np.float64).reshape(d, -1), (d, c)))).cuda()
+    data_t = torch.from_numpy(np.ascontiguousarray(data)).cuda()
+    h = lib.rsfm_create(C.byref(cfg), c, seed, id0)
+    assert h, lib.rsfm_last_error()
+    outs = []
+    try:
+        pkg._lib.check(lib.rsfm_init(h, q0_t.data_ptr(), data_t.data_ptr(), None))
+        depth = lib.rsfm_spec_depth(h)
+        for ns in ns_list:
+            samples = torch.empty((ns, d, c), dtype=torch.float64, device="cuda")
+            s2 = torch.empty((ns, c), dtype=torch.float64, device="cuda")
+            acc = torch.empty((ns, c), dtype=torch.uint8, device="cuda")
+            draws = torch.empty((ns, d + 2, c), dtype=torch.float64, device="cuda")
+            pkg._lib.check(lib.rsfm_run(h, ns, samples.data_ptr(), s2.data_ptr(), acc.data_ptr(), draws.data_ptr(), None))
+            torch.cuda.synchronize()
+            outs.append([x.cpu().numpy() for x in (samples, s2, acc, draws)])
+        tot = (C.c_uint64 * 9)()
+        pkg._lib.check(lib.rsfm_get_totals(h, tot, None))
+    finally:
+        lib.rsfm_destroy(h)
+    cat = [np.concatenate([o[i] for o in outs]) for i in range(4)]
+    return cat + [depth, list(tot)]
+
+
+@pytest.mark.parametrize("spec_depth", [1, 3])
+def test_joint_abdc_chains_replay_step_for_step_through_oracle(cuda, pkg, orc, spec_depth):
+    """d = 3 (a, b, Dc), Philox-driven: the SEQUENTIAL kernel -- whose lanes walk ahead through their own
+    out-of-bounds iterations between solves (rsfm_kernels.cu, SKIP_T) -- and the speculative one, replayed on
+    the CPU oracle with the draws they report: the same accept / reject decision at every step of every checked
+    chain, the same samples, sigma^2 to 1e-8; and the proposals are q + L z with the documented Philox stream
+    and the Cholesky factor of Vstart."""
+    torch = cuda
+    rng = np.random.default_rng(12)
+    om = orc.make_model(Dc=1325.0)
+    truth = orc.forward(om)[1]
+    data = truth + np.abs(truth) * rng.standard_normal(truth.size)
+    cfg = pkg.RateStateModel().to_cfg()
+    cfg.n_params, cfg.n_prior_len, cfg.spec_depth = 3, 3, spec_depth
+    lo, hi = np.array([0.0104, 0.0134, 1100.0]), np.array([0.0116, 0.0146, 1500.0])      # about half the proposals leave the box
+    for j in range(3):
+        cfg.lo[j], cfg.hi[j] = lo[j], hi[j]
+    c, seed, id0, ns = 70, 2025, 4000, 36                # 70 chains: 2 full warps + a ragged one
+    q0 = np.array([0.011, 0.014, 1300.0])
+    samples, s2, acc, draws, depth, tot = _run_with_draws(torch, pkg, cfg, c, seed, id0, q0, data, [20, 16])
+    assert depth == (0 if spec_depth == 1 else 3)
+    oob = np.isnan(draws[:, 3])
+    assert 0.15 < oob.mean() < 0.9 and 0 < acc.mean() < 1
+    in_box = np.all((draws[:, :3] > lo[None, :, None]) & (draws[:, :3] < hi[None, :, None]), axis=1)
+    assert np.array_equal(in_box, ~oob)
+    assert tot[0] == in_box.sum() + 4 * c                # one solve per in-bounds proposal (+ the 1 + d set-up solves)
+    for ch in (0, 1, 31, 32, 63, 64, 69):
+        prop = draws[:, :3, ch]
+        chain_o, s2_o, acc_o, nsolves = orc.chain_replay_nd(om, data, q0, lo, hi, 3, ns, prop,
+                                                            np.nan_to_num(draws[:, 3, ch], nan=0.5), draws[:, 4, ch])
+        assert np.array_equal(acc[:, ch], acc_o), ch
+        assert np.array_equal(samples[:, :, ch], chain_o[1:]), ch
+        assert np.allclose(s2[:, ch], s2_o[1:], rtol=1e-8, atol=0)
+    # the proposals themselves: q_cur + L z, z = the chain's Philox normals, L = chol(Vstart) (no adaptation)
+    lib = pkg._lib.load()
+    hook = torch.empty((ns, 6, c), dtype=torch.float64, device="cuda")
+    pkg._lib.check(lib.rsfm_philox_draws(seed, id0, c, 0, ns, 0.5 * (0.01 + 500), hook.data_ptr(), None))
+    hook = hook.cpu().numpy()
+    mc = pkg.MCMC(pkg.RateStateModel(), data, 1325.0, ["Uniform", 0.0, 1e4], q0, nsamples=2, n_chains=c, verbose=False,
+                  seed=seed, chain_id0=id0, param_names=("a", "b", "Dc"), bounds=np.stack([lo, hi], axis=1), spec_depth=1)
+    mc.sample(False)
+    L = np.zeros((3, 3))
+    L[np.tril_indices(3)] = mc.checkpoint()["chol"][:, 0]                       # row-major lower triangle
+    assert np.allclose(L @ L.T, mc.Vstart, rtol=1e-12)
+    cur = np.concatenate([np.broadcast_to(q0.reshape(1, 3, 1), (1, 3, c)), samples[:-1]])
+    z = hook[:, :3]                                                             # [ns, 3, c]
+    expect = cur + np.einsum("ij,njc->nic", L, z)
+    assert np.allclose(draws[:, :3], expect, rtol=1e-9, atol=0)
+    assert np.array_equal(draws[:, 3][~oob], hook[:, 3][~oob]) and np.array_equal(draws[:, 4], hook[:, 4])
+
+
+@pytest.mark.parametrize("d,c,spec_depth", [(1, 37, 1), (1, 1, 0), (1, 200, 0), (3, 45, 1), (1, 4100, 1)])
+def test_series_of_513_to_1024_points(cuda, pkg, orc, d, c, spec_depth):
+    """number_time_steps = 1000 (the value of the reference's docstring examples): a series of two resident
+    tiles.  Warps whose lanes are all rejected early, out of bounds or inactive leave the output loop before the
+    second tile -- sequential d = 1, the d = 3 out-of-bounds walk, the speculative kernel with ONE chain (idle
+    tree lanes), and chain counts that are no multiple of the block size -- and the chains must still be the
+    oracle's, step for step."""
+    torch = cuda
+    n, t_end = 1000, 100.0
+    rng = np.random.default_rng(3)
+    om = orc.make_model(Dc=1325.0, number_time_steps=n, end_time=t_end)
+    truth = orc.forward(om)[1]
+    data = truth + np.abs(truth) * rng.standard_normal(n)
+    model = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
+    cfg = model.to_cfg()
+    cfg.n_params, cfg.n_prior_len, cfg.spec_depth = d, 3, spec_depth
+    if d == 1:
+        lo, hi, q0 = np.array([1250.0]), np.array([1420.0]), np.array([1330.0])
+    else:
+        lo, hi, q0 = np.array([0.0104, 0.0134, 1100.0]), np.array([0.0116, 0.0146, 1500.0]), np.array([0.011, 0.014, 1300.0])
+    for j in range(d):
+        cfg.lo[j], cfg.hi[j] = lo[j], hi[j]
+    ns = 14
+    samples, s2, acc, draws, depth, tot = _run_with_draws(torch, pkg, cfg, c, 5, 0, q0, data, [ns])
+    assert (depth >= 2) == (spec_depth == 0)
+    assert tot[5] > 0 or c == 1                           # solves were stopped early (rejection certain)
+    for ch in sorted({0, c // 2, c - 1}):
+        chain_o, s2_o, acc_o, _ = orc.chain_replay_nd(om, data, q0, lo, hi, 3, ns, draws[:, :d, ch],
+                                                      np.nan_to_num(draws[:, d, ch], nan=0.5), draws[:, d + 1, ch])
+        assert np.array_equal(acc[:, ch], acc_o), ch
+        assert np.array_equal(samples[:, :, ch], chain_o[1:]), ch
+        assert np.allclose(s2[:, ch], s2_o[1:], rtol=1e-8, atol=0)
+
+
+def test_mu_observable_end_to_end(cuda, pkg, orc):
+    """RSFM_OBS_MU (north_star's "observed friction series"): the solver scores mu_k, the series
+    the reference integrates and stores (RateStateModel.py:367, 385): trajectories against the oracle's mu,
+    SSE against the oracle's, and Philox-driven chains replayed on the oracle with observable = mu."""
+    torch = cuda
+    rng = np.random.default_rng(8)
+    om = orc.make_model(Dc=1325.0, observable=orc.OBS_MU)
+    _, mu_true, _, _, _, _ = orc.forward(orc.make_model(Dc=1325.0), full=True)
+    sig = 2e-7
+    data = mu_true + sig * rng.standard_normal(mu_true.size)
+    m = pkg.RateStateModel()
+    m.observable = "mu"
+    dcs = np.array([1.0, 60.0, 300.0, 1000.0, 1325.0, 5000.0])
+    out = m.evaluate_batch(dcs, data=data)
+    mu_g = out["acc"].t().cpu().numpy()
+    for i, dc in enumerate(dcs):
+        _, mu_o, _, _, _, _ = orc.forward(orc.make_model(Dc=dc), full=True)
+        assert mu_g[i, 0] == 0.6
+        tol = (1e-6 if dc < 50 else 1e-9) * np.max(np.abs(mu_o - 0.6)) + 2e-16
+        assert np.max(np.abs(mu_g[i] - mu_o)) <= tol, dc
+    sse_o, _, _ = orc.forward_batch(om, dcs, data=data)
+    assert np.allclose(out["sse"].cpu().numpy()[1:], sse_o[1:], rtol=1e-8, atol=0)
+    # evaluate() returns the observable in slot 1, like the reference's protocol (MCMC.py:127)
+    m.Dc = 1325.0
+    t, mu1, mu_noise = m.evaluate()
+    assert np.array_equal(mu1, mu_g[4]) and mu_noise.shape == mu1.shape and mu_noise[0] == 0.6
+    # chains on the friction series, replayed through the oracle
+    cfg = m.to_cfg()
+    cfg.n_params, cfg.n_prior_len = 1, 3
+    cfg.lo[0], cfg.hi[0] = 1200.0, 1450.0
+    for spec_depth in (1, 0):
+        cfg.spec_depth = spec_depth
+        samples, s2, acc, draws, depth, tot = _run_with_draws(torch, pkg, cfg, 48, 31, 100, np.array([1300.0]), data, [30])
+        assert 0 < acc.mean() < 1
+        for ch in (0, 20, 47):
+            chain_o, s2_o, acc_o, _ = orc.chain_replay_nd(om, data, [1300.0], [1200.0], [1450.0], 3, 30, draws[:, :1, ch],
+                                                          np.nan_to_num(draws[:, 1, ch], nan=0.5), draws[:, 2, ch])
+            assert np.array_equal(acc[:, ch], acc_o), (spec_depth, ch)
+            assert np.array_equal(samples[:, 0, ch], chain_o[1:, 0])
+            assert np.allclose(s2[:, ch], s2_o[1:], rtol=1e-7, atol=0)
+    # the public sampler on the friction series recovers Dc
+    mc = pkg.MCMC(m, data, 1325.0, ["Uniform", 0.0, 1e4], 1000.0, nsamples=400, n_chains=256, verbose=False, seed=2)
+    post = mc.sample(False)
+    assert abs(post[:, 0, :].mean() - 1325.0) < 4 * post[:, 0, :].std() and post[:, 0, :].std() < 100.0
+
+
+def test_device_pooled_update_matches_host_algebra(cuda, pkg):
+    """rsfm_pooled_partials / rsfm_pooled_update (sharding-invariant partial sums, moments, closed-form Cholesky,
+    install -- all on the device) against the NumPy restatement in adaptation.py, d = 1 and d = 3; and the
+    partial rows of a sampler are the same bits whether it holds the whole range of chains or a shard of it."""
+    import ctypes as C
+    import importlib
+    torch = cuda
+    ad = importlib.import_module("bayesian-markov-chain-monte-carlo_b200.adaptation")
+    lib = pkg._lib.load()
+    g = load_golden("sse_grid.json")
+    data_t = torch.from_numpy(g["data"]).cuda()
+    rows = pkg._lib.POOL_ROWS
+    for d, q0, lo, hi in ((1, [1300.0], [0.0], [1e4]),
+                          (3, [0.011, 0.014, 1300.0], [0.0100, 0.0130, 800.0], [0.0120, 0.0150, 2200.0])):
+        cfg = pkg.RateStateModel().to_cfg()
+        cfg.n_params, cfg.n_prior_len, cfg.adapt_mode = d, 3, pkg._lib.ADAPT_POOLED
+        for j in range(d):
+            cfg.lo[j], cfg.hi[j] = lo[j], hi[j]
+        tri = d * (d + 1) // 2
+
+        def run(c, id0, ns):
+            q = torch.from_numpy(np.repeat(np.array(q0).reshape(d, 1), c, axis=1).copy()).cuda()
+            h = lib.rsfm_create(C.byref(cfg), c, 77, id0)
+            assert h
+            try:
+                pkg._lib.check(lib.rsfm_init(h, q.data_ptr(), data_t.data_ptr(), None))
+                samples = torch.empty((ns, d, c), dtype=torch.float64, device="cuda")
+                pkg._lib.check(lib.rsfm_run(h, ns, samples.data_ptr(), None, None, None, None))
+                ng = lib.rsfm_pooled_groups(h)
+                part = torch.full((ng, rows), -1.0, dtype=torch.float64, device="cuda")
+                pkg._lib.check(lib.rsfm_pooled_partials(h, part.data_ptr(), 1, None))
+                mom = torch.zeros(1 + d + tri, dtype=torch.float64, device="cuda")
+                fac = torch.zeros(1 + tri, dtype=torch.float64, device="cuda")
+                pkg._lib.check(lib.rsfm_pooled_update(h, part.data_ptr(), ng, mom.data_ptr(), 1, 1, fac.data_ptr(), None))
+                chol = torch.empty((tri, c), dtype=torch.float64, device="cuda")
+                pkg._lib.check(lib.rsfm_get_state(h, None, None, None, chol.data_ptr(), None, None, None, None, None))
+                torch.cuda.synchronize()
+                return samples.cpu().numpy(), part.cpu().numpy(), mom.cpu().numpy(), fac.cpu().numpy(), chol.cpu().numpy()
+            finally:
+                lib.rsfm_destroy(h)
+
+        c, ns = 3072, 12
+        samples, part, mom, fac, chol = run(c, 2048, ns)
+        assert part.shape == (3, rows) and np.all(part[:, 1 + d + tri:] == 0.0)
+        x = samples.transpose(0, 2, 1).reshape(-1, d)                      # all draws of all chains
+        assert mom[0] == ns * c
+        assert np.allclose(mom[1:1 + d], x.sum(axis=0), rtol=1e-12)
+        sec = x.T @ x
+        assert np.allclose(mom[1 + d:], sec[np.tril_indices(d)], rtol=1e-12)
+        want = ad.proposal_from_suffstats(mom, d)
+        assert fac[0] == 1.0 and np.allclose(fac[1:], want, rtol=1e-7, atol=1e-12 * np.abs(want).max())
+        assert np.all(chol == fac[1:, None])                               # installed for every chain
+        # shard invariance of the partial rows: chains [2048, 5120) as [2048, 4096) + [4096, 5120)
+        _, part_a, _, _, _ = run(2048, 2048, ns)
+        _, part_b, _, _, _ = run(1024, 4096, ns)
+        assert np.array_equal(np.concatenate([part_a, part_b]), part)
+        # a range that does not start on a group boundary: more groups, same total
+        _, part_u, mom_u, _, _ = run(3072, 2048 + 100, ns)
+        assert part_u.shape[0] == 4 and part_u[:, 0].sum() == ns * 3072
+    # degenerate moments: identical samples -> no factor, the proposal stays
+    cfg = pkg.RateStateModel().to_cfg()
+    cfg.n_params, cfg.adapt_mode = 1, pkg._lib.ADAPT_POOLED
+    q = torch.full((1, 64), 1300.0, dtype=torch.float64, device="cuda")
+    h = lib.rsfm_create(C.byref(cfg), 64, 1, 0)
+    try:
+        pkg._lib.check(lib.rsfm_init(h, q.data_ptr(), data_t.data_ptr(), None))
+        before = torch.empty((1, 64), dtype=torch.float64, device="cuda")
+        pkg._lib.check(lib.rsfm_get_state(h, None, None, None, before.data_ptr(), None, None, None, None, None))
+        mom = torch.tensor([640.0, 640.0 * 1300.0, 640.0 * 1300.0 ** 2], dtype=torch.float64, device="cuda")
+        fac = torch.ones(2, dtype=torch.float64, device="cuda")
+        pkg._lib.check(lib.rsfm_pooled_update(h, None, 0, mom.data_ptr(), 0, 1, fac.data_ptr(), None))
+        after = torch.empty((1, 64), dtype=torch.float64, device="cuda")
+        pkg._lib.check(lib.rsfm_get_state(h, None, None, None, after.data_ptr(), None, None, None, None, None))
+        torch.cuda.synchronize()
+        assert fac[0].item() == 0.0 and torch.equal(before, after)
+    finally:
+        lib.rsfm_destroy(h)
+
+
+def test_pooled_sampler_single_chain_and_checkpoint(cuda, pkg, tmp_path):
+    """adapt='pooled' with n_chains = 1 (the draws buffer is filled: model.Dc and the per-iteration printout are
+    the chain's own values), and exact continuation from a checkpoint on an adaptation boundary: the pooled
+    moments and the gathered rows of the last interval are part of the state."""
+    g = load_golden("sse_grid.json")
+    model = pkg.RateStateModel()
+    one = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], 1000.0, nsamples=40, verbose=False, seed=3,
+                   adapt="pooled", adapt_start=20)
+    out = one.sample(False)
+    assert out.shape == (1, 21) and np.all(np.isfinite(out)) and 0.0 < float(model.Dc[0]) < 1e4
+    kw = dict(n_chains=2048, verbose=False, adapt="pooled", adapt_start=20, adapt_interval=10)
+    q0 = np.linspace(900.0, 2000.0, 2048)
+    full = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=70, seed=9, **kw)
+    full.sample(False)
+    assert full.stats["n_adaptations"] >= 4 and len(full.adapt_history) == full.stats["n_adaptations"]
+    part1 = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=40, seed=9, **kw)
+    part1.sample(False)
+    fn = str(tmp_path / "pooled.json")
+    part1.checkpoint(fn)
+    part2 = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=30, resume=fn, **kw)
+    part2.sample(False)
+    a = full.samples_device.cpu().numpy()
+    assert np.array_equal(part1.samples_device.cpu().numpy(), a[:41])
+    assert np.array_equal(part2.samples_device.cpu().numpy()[1:], a[41:])
+    # a checkpoint in the middle of an adaptation interval is refused, not silently inexact
+    mid = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=25, seed=9, **kw)
+    mid.sample(False)
+    with pytest.raises(ValueError, match="adaptation boundary"):
+        pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=10, resume=mid.checkpoint(), **kw).sample(False)
+
+
+def test_compat_checkpoint_mid_window_resumes_exactly(cuda, pkg):
+    """dict priors (the reference's windowed adaptation): the 10-sample ring is part of the checkpoint, so a
+    resume in the middle of a window continues the same chains, bit for bit."""
+    g = load_golden("sse_grid.json")
+    model = pkg.RateStateModel()
+    pri = {1: 0.0, 2: 1e4}
+    kw = dict(n_chains=24, verbose=False)
+    full = pkg.MCMC(model, g["data"], 1350.0, pri, 1000.0, nsamples=47, seed=4, **kw)
+    full.sample(False)
+    p1 = pkg.MCMC(model, g["data"], 1350.0, pri, 1000.0, nsamples=23, seed=4, **kw)
+    p1.sample(False)
+    p2 = pkg.MCMC(model, g["data"], 1350.0, pri, 1000.0, nsamples=24, resume=p1.checkpoint(), **kw)
+    p2.sample(False)
+    a = full.samples_device.cpu().numpy()
+    assert np.array_equal(p1.samples_device.cpu().numpy(), a[:24])
+    assert np.array_equal(p2.samples_device.cpu().numpy()[1:], a[24:])
+    assert np.array_equal(p2.checkpoint()["chol"], full.checkpoint()["chol"])

@@ -165,3 +165,63 @@ def test_world_size_2_gloo_reductions(tmp_path):
     assert rows[0]["n"] == rows[1]["n"] == 1001 * 50
     assert rows[0]["fac"] == rows[1]["fac"]
     assert rows[0]["fac"] == pytest.approx(rows[0]["expect"], rel=1e-9)
+
+
+def test_world_size_2_gloo_pooled_rows_are_sharding_invariant(tmp_path, pkg):
+    """The pooled-adaptation exchange on CPU (gloo): group rows (sums over 1,024 chains aligned on the global
+    chain id) are all-gathered in rank order and summed sequentially; with shard boundaries on group boundaries
+    the pooled moments are the SAME BITS for one and for two ranks (otherwise equal up to summation order)."""
+    sh = importlib.import_module(PKG + ".sharding")
+    g, rows = pkg._lib.POOL_GROUP, pkg._lib.POOL_ROWS
+    assert sh.pool_groups(0, 4096, g) == 4 and sh.pool_groups(2048, 3072, g) == 3 and sh.pool_groups(2148, 3072, g) == 4
+    assert sh.max_pool_groups(4096, 2, g) == 2 and sh.max_pool_groups(5000, 2, g) == 3 and sh.max_pool_groups(1 << 20, 8, g) == 128
+    script = tmp_path / "w2.py"
+    script.write_text(textwrap.dedent(f"""
+        import importlib, os, sys, json
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch, torch.distributed as dist
+        dist.init_process_group("gloo")
+        pkg = importlib.import_module({PKG!r})
+        sh = importlib.import_module({PKG!r} + ".sharding")
+        G, R = pkg._lib.POOL_GROUP, pkg._lib.POOL_ROWS
+        rank, world = sh.rank_and_world()
+        out = {{}}
+        for total in (4096, 5000):
+            rng = np.random.default_rng(total)
+            x = rng.normal(1300.0, 60.0, size=total)                    # one draw per chain, same on both ranks
+            shard = pkg.ChainShard.for_current_rank(total)
+            ng = sh.max_pool_groups(total, world, G)
+            loc = torch.zeros((ng, R), dtype=torch.float64)
+            first = shard.start // G
+            for c in range(shard.start, shard.stop):
+                r = c // G - first
+                loc[r, 0] += 1.0; loc[r, 1] += x[c]; loc[r, 2] += x[c] * x[c]
+            parts = torch.zeros((world * ng, R), dtype=torch.float64)
+            sh.all_gather_rows(parts, loc)
+            mom = np.zeros(3)
+            for p in parts.numpy():
+                mom += p[:3]
+            out[str(total)] = [float(v).hex() for v in mom]
+        json.dump(out, open(os.path.join({str(tmp_path)!r}, f"rows_rank{{rank}}.json"), "w"))
+        dist.destroy_process_group()
+    """))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+    run = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert run.returncode == 0, run.stderr[-2000:]
+    got = [json.load(open(tmp_path / f"rows_rank{r}.json")) for r in (0, 1)]
+    assert got[0] == got[1]                                              # every rank holds the same moments
+    for total in (4096, 5000):
+        x = np.random.default_rng(total).normal(1300.0, 60.0, size=total)
+        mom = np.zeros(3)
+        for g0 in range(0, total, g):                                    # world = 1: the same group rows, in order
+            row = np.zeros(3)
+            for c in range(g0, min(g0 + g, total)):
+                row += np.array([1.0, x[c], x[c] * x[c]])
+            mom += row
+        one = [float(v).hex() for v in mom]
+        if total % (2 * g) == 0:
+            assert got[0][str(total)] == one                             # aligned shards: bit-identical
+        else:
+            two = np.array([float.fromhex(v) for v in got[0][str(total)]])
+            assert two[0] == total and np.allclose(two, mom, rtol=1e-13)

@@ -130,3 +130,78 @@ def test_scipy_port_chain_bit_exact():
         g["nsamples"], g["proposals"], np.nan_to_num(g["uniforms"], nan=0.5), g["gammas_unit"])[0:5]
     assert np.array_equal(r["chain"], full_ref[:ns + 1])
     assert r["n_solves"] == 3 + ns
+
+
+def test_philox_samplers_of_the_oracle_have_the_right_laws(orc):
+    """The oracle's restatement of the CUDA path's draw layout (normals by Box-Muller, 53-bit uniforms,
+    Marsaglia-Tsang gamma at the sampler's shape (n0 + N)/2 = 250.005) is pinned here against the laws
+    themselves -- Kolmogorov-Smirnov against N(0,1), U(0,1), Gamma(250.005) and their first two moments --
+    so that the element-by-element comparison of the DEVICE draws with this oracle (tests/test_gpu_rng.py)
+    also pins the distributions: a wrong counter layout or a biased gamma cannot pass both."""
+    from scipy import stats
+    shape = 0.5 * (0.01 + 500)
+    n = 40000
+    d = np.array([orc.philox_draws(987654321, 1000 + (i % 200), i // 200, shape) for i in range(n)])
+    z = np.concatenate([d[:, 0], d[:, 1], d[:, 2]])
+    assert stats.kstest(z, "norm").pvalue > 1e-3
+    assert abs(z.mean()) < 4 / np.sqrt(z.size) and abs(z.var() - 1) < 4 * np.sqrt(2 / z.size)
+    assert abs(np.corrcoef(d[:, 0], d[:, 1])[0, 1]) < 4 / np.sqrt(n)
+    assert stats.kstest(d[:, 3], "uniform").pvalue > 1e-3
+    assert np.all((d[:, 3] > 0) & (d[:, 3] < 1))
+    g = d[:, 4]
+    assert stats.kstest(g, "gamma", args=(shape,)).pvalue > 1e-3
+    assert abs(g.mean() - shape) < 4 * np.sqrt(shape / n)
+    assert abs(g.var() / shape - 1) < 4 * np.sqrt(2 / n) * 1.1
+    assert np.all(d[:, 5] >= 1) and 1.0 <= d[:, 5].mean() < 1.05        # squeeze accepts > 95 % of the attempts
+    # small shapes too (the rejection loop is exercised): Gamma(1.5)
+    g2 = np.array([orc.philox_draws(5, i, 0, 1.5)[4] for i in range(20000)])
+    assert stats.kstest(g2, "gamma", args=(1.5,)).pvalue > 1e-3
+    # streams: distinct chains / iterations give distinct draws, same counter gives the same draw
+    assert np.array_equal(orc.philox_draws(7, 3, 9, shape), orc.philox_draws(7, 3, 9, shape))
+    assert orc.philox_draws(7, 3, 9, shape)[0] != orc.philox_draws(7, 4, 9, shape)[0]
+    assert orc.philox_draws(7, 3, 9, shape)[0] != orc.philox_draws(7, 3, 10, shape)[0]
+    assert orc.philox_draws(7, 3, 9, shape)[0] != orc.philox_draws(8, 3, 9, shape)[0]
+    assert orc.philox_draws(7, 3 + (1 << 32), 9, shape)[0] != orc.philox_draws(7, 3, 9, shape)[0]
+
+
+def test_nd_replay_reduces_to_the_reference_chain_for_d1(orc):
+    """orc_chain_replay_nd (absolute proposals, per-parameter bounds, d = 1 or 3) is the same loop as the
+    d = 1 replay that reproduces the recorded reference chains bit for bit."""
+    g = load_golden("chain_bounds.json")
+    ns = g["nsamples"]
+    uni = np.nan_to_num(g["uniforms"], nan=0.5)
+    chain, s2, acc, _, nsolves = orc.chain_replay(orc.make_model(), g["data"], g["qstart"], g["lo"], g["hi"],
+                                                  g["n_prior_len"], ns, g["proposals"], uni, g["gammas_unit"])
+    chain_n, s2_n, acc_n, nsolves_n = orc.chain_replay_nd(orc.make_model(), g["data"], [g["qstart"]], [g["lo"]], [g["hi"]],
+                                                         g["n_prior_len"], ns, g["proposals"], uni, g["gammas_unit"])
+    assert np.array_equal(acc_n, acc) and np.array_equal(acc_n, g["accepts"])
+    assert np.array_equal(chain_n[:, 0], chain) and np.array_equal(s2_n, s2)
+    assert nsolves_n == nsolves - 2                    # no covariance set-up solves in the nd form
+    # d = 3: proposals outside any one bound are rejected without a solve; the (a, b) of an accepted
+    # proposal are used by the next solve
+    rng = np.random.default_rng(0)
+    q0 = np.array([0.011, 0.014, 1300.0])
+    lo, hi = np.array([0.0105, 0.0135, 1200.0]), np.array([0.0115, 0.0145, 1400.0])
+    props = q0 + rng.standard_normal((12, 3)) * np.array([2e-4, 2e-4, 40.0])
+    props[3, 0] = 0.02
+    ch3, s23, acc3, ns3 = orc.chain_replay_nd(orc.make_model(), g["data"], q0, lo, hi, 3, 12, props,
+                                              rng.random(12), rng.gamma(250.005, size=12))
+    inb = np.all((props > lo) & (props < hi), axis=1)
+    assert ns3 == 1 + inb.sum() and not acc3[3] and acc3.sum() > 0
+    for i in range(12):
+        assert np.array_equal(ch3[i + 1], props[i] if acc3[i] else ch3[i])
+
+
+def test_rhs_matches_reference_friction(orc):
+    """SURVEY section 4, unit level: the RHS restatement against values of the reference's own nested
+    ``friction(t, y)`` (captured unmodified by oracle/make_golden.py), both damping modes, near and far from
+    sliding steady state: agreement to 1e-15 of the magnitude of the terms each component is a difference of."""
+    from conftest import rhs_term_scales
+    g = load_golden("rhs_values.json")
+    assert g["columns"][:2] == ["RadiationDamping", "Dc"] and g["rows"].shape[1] == 9
+    worst = 0.0
+    for row in g["rows"]:
+        m = orc.make_model(Dc=row[1], radiation_damping=int(row[0]))
+        out = orc.rhs(m, row[2], row[3:6])
+        worst = max(worst, float(np.max(np.abs(out - row[6:9]) / rhs_term_scales(row))))
+    assert worst <= 1e-15, worst

@@ -88,3 +88,56 @@ def test_scipy_reject_rule_is_constant_shrink():
     h2 = after[np.nonzero(after)[0][0]] / c2
     assert h1 == pytest.approx(0.011, rel=1e-12)
     assert h2 / h1 == pytest.approx(0.3, rel=1e-12)
+
+
+@pytest.mark.parametrize("dc,n,t_end,period,factor", [(200.0, 300, 30.0, 10.0, 3.0), (2.0, 300, 30.0, 10.0, 3.0),
+                                                       (0.05, 120, 12.0, 5.0, 10.0)])
+def test_vstep_loading_pinned_on_scipy(orc, dc, n, t_end, period, factor):
+    """The VSTEP extension has no reference counterpart: its CPU oracle is 'the same SciPy driver
+    with only the loading line swapped' (RateStateModel.py:327-329).  oracle/scipy_port.py is that driver --
+    scipy.integrate.ode('dop853') + the reference's Python RHS with the one line replaced -- and the C oracle's
+    velocity-step trajectories (RHS and DOP853 restated) must reproduce it: same accepted steps, so agreement
+    is at the level of libm-vs-NumPy rounding, far inside the 1e-9 trajectory gate."""
+    from oracle import scipy_port
+    pm = scipy_port.PortModel(number_time_steps=n, end_time=t_end)
+    pm.loading, pm.vstep_period, pm.vstep_factor = "vstep", period, factor
+    pm.Dc = dc
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t_p, acc_p, _ = pm.evaluate()
+    om = orc.make_model(Dc=dc, number_time_steps=n, end_time=t_end, loading=orc.LOAD_VSTEP, vstep_period=period,
+                        vstep_factor=factor)
+    t_o, acc_o, st = orc.forward(om)
+    assert st.filled == n and np.array_equal(t_o, t_p)
+    scale = np.max(np.abs(acc_p))
+    assert scale > 0
+    # non-stiff: rounding level.  Stiff (Dc = 0.05): the step sequences of two correct solvers part at the first
+    # differently rounded exp / log, and the trajectories then agree to the solver's tolerance only -- the gate is
+    # a multiple of the oracle's own one-ulp reproducibility floor (conftest.oracle_ulp_floor)
+    from conftest import oracle_ulp_floor
+    _, _, floor = oracle_ulp_floor(orc, dc, number_time_steps=n, end_time=t_end, loading=orc.LOAD_VSTEP,
+                                   vstep_period=period, vstep_factor=factor)
+    assert (floor < 1e-11) == (dc >= 2.0)
+    assert np.max(np.abs(acc_o - acc_p)) <= max(1e-11, 4.0 * floor) * scale
+    # the loading is felt: nothing moves before the first velocity step, a transient right after it
+    k_step = int(round(period / (t_end / n)))
+    assert np.max(np.abs(acc_p[k_step:k_step + 20])) > 0.5 * scale > 1e3 * np.max(np.abs(acc_p[:k_step - 1]))
+    # same number of RHS evaluations as SciPy made through the Python callback (benign repeats aside)
+    if dc >= 2.0:
+        assert pm.n_rhs >= st.nrhs and pm.n_rhs - st.nrhs <= st.nstep + n
+    else:
+        assert abs(pm.n_rhs - st.nrhs) <= 0.02 * st.nrhs
+
+
+def test_mu_observable_pinned_on_scipy(orc):
+    """The friction series mu[k] (RateStateModel.py:367, 385) of the C oracle against the SciPy driver."""
+    from oracle import scipy_port
+    pm = scipy_port.PortModel()
+    pm.observable = "mu"
+    pm.Dc = 1350.0
+    _, mu_p, _ = pm.evaluate()
+    _, mu_o, _, _, _, _ = orc.forward(orc.make_model(Dc=1350.0), full=True)
+    assert mu_p[0] == 0.6 and np.max(np.abs(mu_o - mu_p)) <= 1e-15
+    # forward_batch / chain replay score the same series when the model says so
+    _, obs, _ = orc.forward_batch(orc.make_model(observable=orc.OBS_MU), [1350.0], want_acc=True)
+    assert np.array_equal(obs[0], mu_o)
