@@ -265,11 +265,22 @@ __device__ __forceinline__ double loading_of(const ModelK &M, double t)
 }
 
 struct ChainConst {
-    double b, inv_a, w, kV, voa0, k1e, mu_ref;
+    double b, inv_a, w, kV, voa0, k1e, mu_ref, th_eq;
     double cq[6], qscale;      // (1+f)^q - 1 = f (cq0 + cq1 f + ... + cq5 f^5), q = -b/a; qscale = 1 + |q|
     // w = V_ref/Dc, kV = k' V_ref with k' = 0.1/Dc (RateStateModel.py:324), voa0 = V_ref/a,
-    // k1e = k1 when RadiationDamping else 0 (:349)
+    // k1e = k1 when RadiationDamping else 0 (:349); th_eq = Dc/V_ref, the sliding steady state AND the reference's
+    // start value (:367-370), see state_excess
 };
+
+// f = V_ref theta/Dc - 1 as w (theta - theta_eq): the subtraction is exact near theta_eq, so f is accurate to 2 ulp
+// OF ITSELF and EXACTLY zero at the start value theta_eq = Dc/V_ref.  The reference evaluates V_ref*theta/Dc (:336,
+// :340), which is exactly 1 there (V_ref = 1) and carries 1e-16 of absolute rounding anywhere else, so the two forms
+// agree to the reference's own noise -- but only this one reproduces a derivative of EXACTLY zero while the slider
+// rests in steady state under a constant load (velocity-step loading before the first step): there SciPy's hinit
+// takes its `der12 <= 1e-15` branch (h = 1e-6, eight steps per call), and fma(w, theta, -1) = 400 fl(1/400) - 1 =
+// 5e-17 would send it down the other one (h = 1e-4, five steps) and the trajectory after the jump onto another
+// accepted-step sequence (5e-6 of max|acc| at Dc = 400; found by the round-2 parity gate).
+__device__ __forceinline__ double state_excess(const ChainConst &c, double th) { return c.w * (th - c.th_eq); }
 
 __device__ __forceinline__ ChainConst make_chain_const(const ModelK &M, double a, double b, double dc)
 {
@@ -277,6 +288,7 @@ __device__ __forceinline__ ChainConst make_chain_const(const ModelK &M, double a
     c.b = b;
     c.inv_a = 1.0 / a;
     c.w = M.V_ref / dc;
+    c.th_eq = dc / M.V_ref;
     c.kV = (1e-2 * 10 / dc) * M.V_ref;
     c.voa0 = M.V_ref * c.inv_a;
     c.k1e = M.damping ? M.k1 : 0.0;
@@ -311,7 +323,7 @@ template <bool FAST>
 __device__ __forceinline__ void rsf_rhs(const ChainConst &c, double L, double mu, double th, double &rth,
                                         double &dmu, double &dth, double &dV, bool &bad)
 {
-    const double f = fma(c.w, th, -1.0);
+    const double f = state_excess(c, th);
     double lg, E, r;
     const double dmu0 = mu - c.mu_ref;
     if (FAST) {
@@ -334,7 +346,7 @@ __device__ __forceinline__ void rsf_rhs(const ChainConst &c, double L, double mu
     } else {
         // general range (stiff regime, large excursions): the reference's formulas as written,
         // v = V_ref exp((mu - mu_ref - b log(V_ref theta/Dc))/a), RateStateModel.py:336-346
-        const double x = c.w * th;
+        const double x = 1.0 + f;                                   // V_ref theta / Dc
         const double temp = c.inv_a * fma(-c.b, log(x), dmu0);
         const double ev = exp(temp);                                // v / V_ref
         r = 1.0 / th;
@@ -538,7 +550,7 @@ __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const Ste
     const double h = I.h, mu = I.mu, th = I.th, k1m = I.k1m, k1t = I.k1t, k1v = I.k1v;
     double rth = I.rth;
     const double hw = h * cc.w, ih = h * cc.inv_a;
-    const double f0 = fma(cc.w, th, -1.0), A0 = (mu - cc.mu_ref) * cc.inv_a;
+    const double f0 = state_excess(cc, th), A0 = (mu - cc.mu_ref) * cc.inv_a;
     double k2m, k2t, k3m, k3t, k4m, k4t, k5m, k5t, k6m, k6t, k7m, k7t, k8m, k8t, k9m, k9t, k10m, k10t;
     double k9v, k12v, bV, eV;
     StageOut so;
@@ -626,10 +638,10 @@ __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const Ste
 
 // Re-based copy of the chain constants: reference velocity lam V_ref, mu_ref' = mu_ref_r (see rsf_solve_mode).
 // lam = 1 reproduces the constants bit for bit.
-__device__ __forceinline__ ChainConst rebase_const(const ChainConst &c, double lam, double mu_ref_r)
+__device__ __forceinline__ ChainConst rebase_const(const ChainConst &c, double lam, double rl, double mu_ref_r)
 {
     ChainConst r = c;
-    r.w = c.w * lam; r.kV = c.kV * lam; r.voa0 = c.voa0 * lam; r.mu_ref = mu_ref_r;
+    r.w = c.w * lam; r.kV = c.kV * lam; r.voa0 = c.voa0 * lam; r.mu_ref = mu_ref_r; r.th_eq = c.th_eq * rl;   // rl = 1/lam
     return r;
 }
 
@@ -638,41 +650,41 @@ __device__ __forceinline__ ChainConst rebase_const(const ChainConst &c, double l
 __device__ __noinline__ void dop853_step_general(const ChainConst *cc, double lam, double mu_ref_r, const StepIn *I,
                                                  const double *Lp, int ls, double Lc, double rl, StepOut *O)
 {
-    const ChainConst cr = rebase_const(*cc, lam, mu_ref_r);
+    const ChainConst cr = rebase_const(*cc, lam, rl, mu_ref_r);
     dop853_step_impl(cr, *I, Lp, ls, Lc, rl, *O);
 }
 
 // fast step in a re-based frame (rsf_interval_general); returns whether a stage left the fast ranges
-__device__ __forceinline__ bool dop853_step_fast_rb(const ChainConst *cc, double lam, double mu_ref_r, const StepIn *I,
-                                                    const double *Lp, int ls, double Lc, StepOut *O)
+__device__ __forceinline__ bool dop853_step_fast_rb(const ChainConst *cc, double lam, double rl, double mu_ref_r,
+                                                    const StepIn *I, const double *Lp, int ls, double Lc, StepOut *O)
 {
-    const ChainConst cr = rebase_const(*cc, lam, mu_ref_r);
+    const ChainConst cr = rebase_const(*cc, lam, rl, mu_ref_r);
     bool bad = false;
     dop853_step_fast<true>(cr, *I, Lp, ls, cc->kV, Lc, *O, bad);
     return bad;
 }
 
-__device__ __noinline__ void rsf_rhs_general(const ChainConst *c, double lam, double mu_ref_r, double L, double mu,
-                                             double th, double *res)
+__device__ __noinline__ void rsf_rhs_general(const ChainConst *c, double lam, double rl, double mu_ref_r, double L,
+                                             double mu, double th, double *res)
 {
     bool unused = false;
     double rth = 0.0;
-    const ChainConst cr = rebase_const(*c, lam, mu_ref_r);
+    const ChainConst cr = rebase_const(*c, lam, rl, mu_ref_r);
     rsf_rhs<false>(cr, L, mu, th, rth, res[0], res[1], res[2], unused);
     res[3] = rth;
 }
 
 // single evaluation with fallback (start value, hinit probe, FSAL).  c = the (possibly re-based) constants
 // the fast evaluation uses; c0, lam, mu_ref_r = what they were re-based from; L is relative to c's frame.
-__device__ __forceinline__ void rsf_rhs_checked(const ChainConst &c, const ChainConst &c0, double lam, double mu_ref_r,
-                                                double L, double mu, double th, double &rth, double &dmu, double &dth,
-                                                double &dV)
+__device__ __forceinline__ void rsf_rhs_checked(const ChainConst &c, const ChainConst &c0, double lam, double rl,
+                                                double mu_ref_r, double L, double mu, double th, double &rth, double &dmu,
+                                                double &dth, double &dV)
 {
     bool bad = false;
     rsf_rhs<true>(c, L, mu, th, rth, dmu, dth, dV, bad);
     if (bad) {
         double res[4];
-        rsf_rhs_general(&c0, lam, mu_ref_r, L, mu, th, res);
+        rsf_rhs_general(&c0, lam, rl, mu_ref_r, L, mu, th, res);
         dmu = res[0]; dth = res[1]; dV = res[2]; rth = res[3];
     }
 }
@@ -713,6 +725,14 @@ __device__ __forceinline__ void dop853_step_fast(const ChainConst &cc, const Ste
 #ifdef RSFM_DEBUG_COUNT
 // tuning builds only (profiles/microbench/stiff_paths.py): where the step loop spends its trips
 __device__ unsigned long long g_dbg[16];
+__device__ double g_dbgrec[64 * 8];
+__device__ unsigned int g_dbgrec_n;
+#define RSFM_DBGREC(pred, a0, a1, a2, a3, a4, a5, a6, a7)                                  \
+    if (pred) {                                                                            \
+        const unsigned int i__ = atomicAdd(&g_dbgrec_n, 1u);                               \
+        if (i__ < 64) { double *r__ = g_dbgrec + 8 * i__; r__[0] = a0; r__[1] = a1; r__[2] = a2; r__[3] = a3; \
+                        r__[4] = a4; r__[5] = a5; r__[6] = a6; r__[7] = a7; }              \
+    }
 #define RSFM_DBG(i, pred)                                                                  \
     {                                                                                      \
         const unsigned m__ = __ballot_sync(FULL_MASK, (pred));                             \
@@ -726,6 +746,7 @@ __device__ unsigned long long g_dbg[16];
 #else
 #define RSFM_DBG(i, pred)
 #define RSFM_DBGW(i, pred)
+#define RSFM_DBGREC(pred, a0, a1, a2, a3, a4, a5, a6, a7)
 #endif
 
 struct SolveOut {
@@ -827,7 +848,7 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
             mu_ref_r = fma(1.0 / cc.inv_a - cc.b, M.vstep_lnf, cc.mu_ref);     // (a - b) ln lam: a, b not kept live
         }
     }
-    const ChainConst cr = rebase_const(cc, lam, mu_ref_r);
+    const ChainConst cr = rebase_const(cc, lam, rl, mu_ref_r);
     if (parity || k == 1) {
         // ---- HINIT (dop853.f, iord = 8).  The common outcome h0 = h = hmax is recognised by
         // comparisons in the squared / 16th-power domain, without sqrt or division. ----
@@ -852,7 +873,7 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
             if (running && !(t == tab_t && h0 == tab_h)) Lp = loading_of(M, t + h0);
         }
         double f1m, f1t, f1v, rprobe = rth;
-        rsf_rhs_checked(cr, cc, lam, mu_ref_r, (Lp - Lc) * rl, mu + h0 * k1m, th + h0 * k1t, rprobe, f1m, f1t, f1v);
+        rsf_rhs_checked(cr, cc, lam, rl, mu_ref_r, (Lp - Lc) * rl, mu + h0 * k1m, th + h0 * k1t, rprobe, f1m, f1t, f1v);
         if (running) out.nrhs++;
         const double e0 = (f1m - k1m) * p0, e1 = (f1t - k1t) * p1, e2 = (f1v - k1v) * p2;
         const double Ne = e0 * e0 + e1 * e1 + e2 * e2;                      // ||(f1-f0)/sk||^2 = Ne/D
@@ -890,6 +911,7 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         if (!pwc) ensure_table(stepping, h);
         const bool hit = !pwc && (t == tab_t && h == tab_h);
         int lstride = hit ? 1 : nthr;
+        bool on_base = false;                                 // the load stays at the frame's base level over the step
         if (stepping && !hit) {
             // private stage values (this lane is not on the warp's (t, h)).  A piecewise-constant load
             // that does not switch between t and t + h has one value for the whole step.
@@ -903,6 +925,7 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
             if (flat) {
                 ptab[0] = La;                                 // one value for every stage (stride 0)
                 lstride = 0;
+                on_base = pwc && La == Lc;
             } else {
 #pragma unroll 1
                 for (int i = 0; i < 11; i++) ptab[i * nthr] = loading_of(M, __dadd_rn(t, __dmul_rn(TB.c[i], h)));
@@ -918,18 +941,23 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         // The fast step is tried when some stepping lane STARTS inside the fast ranges (with a margin).
         // A step that starts inside and leaves them at a late stage (the trial step the controller grew
         // past the stability limit) says nothing about the state: the next one is tried again.
-        const double f0s = fma(cr.w, th, -1.0), A0s = (mu - cr.mu_ref) * cr.inv_a;
+        const double f0s = state_excess(cr, th), A0s = (mu - cr.mu_ref) * cr.inv_a;
         const bool start_in = fabs(f0s) * cr.qscale < 0.5 * 0.001953125 && fabs(A0s) < 0.5 * 0.015625;
         const bool try_fast = __any_sync(FULL_MASK, stepping && start_in);
-        if (try_fast) bad = dop853_step_fast_rb(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, &so);
+        if (try_fast) bad = dop853_step_fast_rb(&cc, lam, rl, mu_ref_r, &in, Lsrc, lstride, Lc, &so);
         else bad = true;
-        // A step that STARTS well inside the fast ranges and leaves them at an internal stage is the trial step the
+        // A step under a CONSTANT load at the frame's base level that STARTS well inside the fast ranges (i.e. close to
+        // the sliding steady state of that very level) and leaves them at an internal stage is the trial step the
         // controller grew past the stability limit: it explodes and SciPy rejects it.  It is taken as rejected without
         // scoring it with the general-range stages (a rejected step shrinks by exactly 0.3 whatever its error was).
-        // CPU-oracle count over seven stiff solves (profiles/microbench/forward_stiff_r1b.txt): of ~49,000 such steps
-        // none is accepted by the exact arithmetic; were one ever, the retry at 0.3 h only costs a step.
-        // M.stiff_exact (RSFM_STIFF_EXACT=1) scores them with the general-range step instead.
-        const bool presumed_wild = bad && start_in && !M.stiff_exact;
+        // The load condition matters: the accumulated output times put a velocity jump a few ulp INSIDE an interval
+        // whose frame is still the old level; the first steps after the jump start at the old steady state, leave the
+        // ranges because the state really moves, and are accepted (err ~ 1e-13) -- those are scored
+        // (profiles/microbench/stiff_wild_probe.py: one such step per downward/upward jump, 1e-6 of the trajectory).
+        // CPU-oracle count (tests/test_stiff_rule.py; profiles/microbench/forward_stiff_r1b.txt): of ~49,000 steps that
+        // meet the condition none is accepted by the exact arithmetic; were one ever, the retry at 0.3 h only costs a
+        // step.  cfg.stiff_exact scores them with the general-range step instead.
+        const bool presumed_wild = bad && start_in && on_base && !M.stiff_exact;
         if (stepping && bad && !presumed_wild) dop853_step_general(&cc, lam, mu_ref_r, &in, Lsrc, lstride, Lc, rl, &so);
         RSFM_DBG(0, stepping) RSFM_DBG(1, stepping && try_fast) RSFM_DBG(2, stepping && bad)
         RSFM_DBGW(3, stepping) RSFM_DBGW(4, stepping && bad) RSFM_DBGW(5, stepping && try_fast)
@@ -940,13 +968,16 @@ __device__ __forceinline__ void rsf_interval_general(const ModelK *Mp, const Cha
         const bool accept = !presumed_wild && so.errA < 1e140 && (h * h) * (so.errA * so.errA) <= so.den3;
 
         RSFM_DBG(6, stepping && accept) RSFM_DBG(10, stepping && !accept && bad)
+        RSFM_DBG(11, stepping && accept && bad && start_in)
+        RSFM_DBGREC(stepping && accept && bad && start_in, t, h, f0s * cr.qscale / 0.001953125, A0s / 0.015625, so.errA, so.den3,
+                    cc.w, lam)
         if (stepping) {
             out.nstep++;
             out.nrhs += 11;
             if (accept) {
                 // FSAL: f(x + h, y_new) is k1 of the next step and of the next interval's restart
                 rth = so.rth;
-                rsf_rhs_checked(cr, cc, lam, mu_ref_r, (so.L12 - Lc) * rl, so.muN, so.thN, rth, k1m, k1t, k1v);
+                rsf_rhs_checked(cr, cc, lam, rl, mu_ref_r, (so.L12 - Lc) * rl, so.muN, so.thN, rth, k1m, k1t, k1v);
                 out.nrhs++;
                 const double hold = h;
                 mu = so.muN; th = so.thN; V = so.VN; t = t + h;

@@ -1825,4 +1825,12 @@ extern "C" int rsfm_debug_counters(unsigned long long *out16, int reset)
     if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(rsfm::g_dbg, z, sizeof(z)); }
     return 0;
 }
+extern "C" int rsfm_debug_records(double *out512, unsigned int *n_out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out512, rsfm::g_dbgrec, sizeof(double) * 512);
+    cudaMemcpyFromSymbol(n_out, rsfm::g_dbgrec_n, sizeof(unsigned int));
+    if (reset) { unsigned int z = 0; cudaMemcpyToSymbol(rsfm::g_dbgrec_n, &z, sizeof(z)); }
+    return 0;
+}
 #endif

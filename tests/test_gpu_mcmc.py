@@ -501,11 +501,16 @@ def test_joint_abdc_chains_replay_step_for_step_through_oracle(cuda, pkg, orc, s
     data = truth + np.abs(truth) * rng.standard_normal(truth.size)
     cfg = pkg.RateStateModel().to_cfg()
     cfg.n_params, cfg.n_prior_len, cfg.spec_depth = 3, 3, spec_depth
-    lo, hi = np.array([0.0104, 0.0134, 1100.0]), np.array([0.0116, 0.0146, 1500.0])      # about half the proposals leave the box
-    for j in range(3):
-        cfg.lo[j], cfg.hi[j] = lo[j], hi[j]
     c, seed, id0, ns = 70, 2025, 4000, 36                # 70 chains: 2 full warps + a ragged one
     q0 = np.array([0.011, 0.014, 1300.0])
+    # rsfm_init caps every marginal proposal s.d. at 1/20 of the prior width (no reference behaviour exists for
+    # d = 3), so a box centred on the start value is hardly ever left; the start value sits half an s.d. from the
+    # lower corner instead: a third to a half of the proposals leave the box
+    width = np.array([0.0012, 0.0012, 400.0])
+    lo = q0 - width / 40.0
+    hi = lo + width
+    for j in range(3):
+        cfg.lo[j], cfg.hi[j] = lo[j], hi[j]
     samples, s2, acc, draws, depth, tot = _run_with_draws(torch, pkg, cfg, c, seed, id0, q0, data, [20, 16])
     assert depth == (0 if spec_depth == 1 else 3)
     oob = np.isnan(draws[:, 3])
@@ -668,7 +673,22 @@ def test_device_pooled_update_matches_host_algebra(cuda, pkg):
         sec = x.T @ x
         assert np.allclose(mom[1 + d:], sec[np.tril_indices(d)], rtol=1e-12)
         want = ad.proposal_from_suffstats(mom, d)
-        assert fac[0] == 1.0 and np.allclose(fac[1:], want, rtol=1e-7, atol=1e-12 * np.abs(want).max())
+        assert fac[0] == 1.0
+        if d == 1:
+            assert np.allclose(fac[1:], want, rtol=1e-7)
+        else:
+            # compared as covariances: after 12 iterations from one start value the three parameters are almost
+            # perfectly correlated, and the last pivot l22^2 = v22 - l20^2 - l21^2 is 2e-10 of v22 -- the factor's
+            # last entries carry the rounding of the raw moments amplified by that ratio (7e-4 observed), in the
+            # host algebra just as on the device; L L^T is what the proposals see and is well conditioned
+            def cov_of(f):
+                low = np.zeros((d, d))
+                low[np.tril_indices(d)] = f
+                return low @ low.T
+            v_dev, v_host = cov_of(fac[1:]), cov_of(want)
+            scale = np.sqrt(np.outer(np.diag(v_host), np.diag(v_host)))
+            assert np.max(np.abs(v_dev - v_host) / scale) < 1e-9
+            assert np.allclose(fac[1:4], want[:3], rtol=1e-7)
         assert np.all(chol == fac[1:, None])                               # installed for every chain
         # shard invariance of the partial rows: chains [2048, 5120) as [2048, 4096) + [4096, 5120)
         _, part_a, _, _, _ = run(2048, 2048, ns)

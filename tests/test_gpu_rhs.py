@@ -59,10 +59,12 @@ def test_device_rhs_fast_and_general_forms_agree(cuda, pkg):
         outs.append(out.cpu().numpy())
     L = np.longdouble
     a, b, kp = L(0.011), L(0.014), L(0.1) / dc.astype(L)
-    tl, mul, thl, dcl = t.astype(L), mu.astype(L), th.astype(L), dc.astype(L)
+    mul, thl, dcl = mu.astype(L), th.astype(L), dc.astype(L)
     v = np.exp((mul - L(0.6) - b * np.log(thl / dcl)) / a)
     dth = 1 - v * thl / dcl
-    dmu = kp * (1 + np.exp(-tl / 20) * np.sin(10 * tl)) - kp * v
+    # the ARGUMENTS of the load term are formed in double, as the reference forms them (RateStateModel.py:327-329:
+    # np.exp(-t/a1) * np.sin(a2*t)); 10 t carries up to 5e-14 of rounding at t = 50, which is not the RHS's error
+    dmu = kp * (1 + np.exp((-t / 20.0).astype(L)) * np.sin((10.0 * t).astype(L))) - kp * v
     dv = v / a * (dmu - b / thl * dth)
     dmu = dmu - L(1e-7) * dv
     dv = v / a * (dmu - b / thl * dth)
