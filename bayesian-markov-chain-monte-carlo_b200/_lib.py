@@ -12,14 +12,15 @@ LIB_PATH = os.path.join(_PKG_DIR, "librsfm.so")
 
 RSFM_MAX_PARAMS = 3
 
-LOAD_SINE_DECAY, LOAD_VSTEP = 0, 1
+LOAD_SINE_DECAY, LOAD_VSTEP, LOAD_TABLE = 0, 1, 2
+LAW_AGING, LAW_SLIP = 0, 1
 INTEG_PARITY, INTEG_CARRY = 0, 1
 ADAPT_NONE, ADAPT_COMPAT, ADAPT_POOLED = 0, 1, 2
 CHAIN_OK, CHAIN_NMAX, CHAIN_HSMALL, CHAIN_NONFINITE = 0, 2, 3, 4
 OBS_ACC, OBS_MU = 0, 1
 VARIANT_AUTO, VARIANT_DEFAULT, VARIANT_STIFF = 0, 1, 2
 POOL_GROUP, POOL_ROWS = 1024, 16
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/rsfm.h declares (tests check the library exports them all)
 EXPORTED_SYMBOLS = (
@@ -49,6 +50,7 @@ class RsfmCfg(C.Structure):
         ("spec_depth", C.c_int32),
         ("observable", C.c_int32), ("solver_variant", C.c_int32), ("stiff_exact", C.c_int32),
         ("block_threads", C.c_int32),
+        ("state_law", C.c_int32), ("n_load_table", C.c_int32), ("load_dt", C.c_double), ("load_table_dev", C.c_void_p),
     ]
 
 

@@ -47,6 +47,10 @@ struct ModelK {
     int stiff_exact;                   // stiff variant: score every step that left the fast ranges (tuning / tests)
     int observable;                    // RSFM_OBS_ACC (reference) / RSFM_OBS_MU
     int n_out, nmax, damping, loading, integ_mode;
+    int state_law;                     // RSFM_LAW_AGING (reference, :340) / RSFM_LAW_SLIP
+    int load_n;                        // RSFM_LOAD_TABLE: entries of load_tab
+    double load_dt;                    //   spacing of the table (first entry at t_start)
+    const double *load_tab;            //   device pointer, V_l/V_ref - 1
 };
 
 // ---------------------------------------------------------------------------
@@ -261,11 +265,24 @@ __device__ __forceinline__ double loading_of(const ModelK &M, double t)
         const long long i = (long long)vstep_index(M, t);
         return (i & 1) ? M.vstep_factor - 1.0 : 0.0;
     }
+    if (M.loading == RSFM_LOAD_TABLE) {
+        // piecewise linear through the table, constant beyond its ends: one rounded division for the position and
+        // T[i] + fr (T[i+1] - T[i]) without contraction, the same operations, in the same order, as the CPU restatement the parity tests compare with
+        const double x = __ddiv_rn(t - M.t_start, M.load_dt);
+        double fi = floor(x);
+        fi = fmin(fmax(fi, 0.0), (double)(M.load_n - 2));
+        double fr = x - fi;
+        fr = fmin(fmax(fr, 0.0), 1.0);
+        const int i = (int)fi;
+        const double t0 = M.load_tab[i], t1 = M.load_tab[i + 1];
+        return __dadd_rn(t0, __dmul_rn(fr, __dadd_rn(t1, -t0)));
+    }
     return loading_rel(M.loading, M.t_start, M.vstep_period, M.vstep_factor, t);
 }
 
 struct ChainConst {
     double b, inv_a, w, kV, voa0, k1e, mu_ref, th_eq;
+    int slip;                  // state law: 0 aging (reference), 1 slip -- general-range formulas only, see make_chain_const
     double cq[6], qscale;      // (1+f)^q - 1 = f (cq0 + cq1 f + ... + cq5 f^5), q = -b/a; qscale = 1 + |q|
     // w = V_ref/Dc, kV = k' V_ref with k' = 0.1/Dc (RateStateModel.py:324), voa0 = V_ref/a,
     // k1e = k1 when RadiationDamping else 0 (:349); th_eq = Dc/V_ref, the sliding steady state AND the reference's
@@ -301,6 +318,12 @@ __device__ __forceinline__ ChainConst make_chain_const(const ModelK &M, double a
     c.cq[4] = c.cq[3] * (q - 4.0) / 5.0;
     c.cq[5] = c.cq[4] * (q - 5.0) / 6.0;
     c.qscale = 1.0 + fabs(q);
+    // Slip law (extension): theta' = -(v theta/Dc) ln(v theta/Dc) has no short-series form here; an
+    // infinite range scale makes every fast stage report "out of range" (inf * |f| < limit is false, inf * 0 = NaN
+    // too), so steps are scored by the general-range stages, which carry the law (rsf_rhs<false>), without a single
+    // extra instruction in the fast stage of the aging law.
+    c.slip = M.state_law == RSFM_LAW_SLIP ? 1 : 0;
+    if (c.slip) c.qscale = INFINITY;
     return c;
 }
 
@@ -351,6 +374,7 @@ __device__ __forceinline__ void rsf_rhs(const ChainConst &c, double L, double mu
         const double ev = exp(temp);                                // v / V_ref
         r = 1.0 / th;
         dth = 1.0 - ev * x;
+        if (c.slip) { const double z = ev * x; dth = -z * log(z); }      // Ruina slip law
         const double voa_g = c.voa0 * ev;
         const double d0_g = c.kV * ((L + 1.0) - ev);
         const double s_g = (c.b * r) * dth;
@@ -682,7 +706,7 @@ __device__ __forceinline__ void rsf_rhs_checked(const ChainConst &c, const Chain
 {
     bool bad = false;
     rsf_rhs<true>(c, L, mu, th, rth, dmu, dth, dV, bad);
-    if (bad) {
+    if (bad || c.slip) {
         double res[4];
         rsf_rhs_general(&c0, lam, rl, mu_ref_r, L, mu, th, res);
         dmu = res[0]; dth = res[1]; dV = res[2]; rth = res[3];
@@ -709,7 +733,7 @@ __device__ __forceinline__ void rsf_rhs_checked(const ChainConst &c, double L, d
 {
     bool bad = false;
     rsf_rhs<true>(c, L, mu, th, rth, dmu, dth, dV, bad);
-    if (bad) {
+    if (bad || c.slip) {
         double res[4];
         rsf_rhs_general(&c, L, mu, th, res);
         dmu = res[0]; dth = res[1]; dV = res[2]; rth = res[3];

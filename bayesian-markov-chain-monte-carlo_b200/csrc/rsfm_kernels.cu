@@ -98,8 +98,12 @@ static int check_cfg(const rsfm_cfg *c)
     if (!c) return set_err(RSFM_ERR_INVALID, "cfg is NULL%s", "");
     if (c->n_out < 1 || c->nmax < 1 || !(c->delta_t > 0.0)) return set_err(RSFM_ERR_INVALID, "bad grid in cfg%s", "");
     if (c->n_params != 1 && c->n_params != 3) return set_err(RSFM_ERR_INVALID, "n_params must be 1 or 3%s", "");
-    if (c->loading != RSFM_LOAD_SINE_DECAY && c->loading != RSFM_LOAD_VSTEP)
+    if (c->loading != RSFM_LOAD_SINE_DECAY && c->loading != RSFM_LOAD_VSTEP && c->loading != RSFM_LOAD_TABLE)
         return set_err(RSFM_ERR_INVALID, "bad loading selector%s", "");
+    if (c->loading == RSFM_LOAD_TABLE && (!c->load_table_dev || c->n_load_table < 2 || !(c->load_dt > 0.0)))
+        return set_err(RSFM_ERR_INVALID, "RSFM_LOAD_TABLE needs load_table_dev, n_load_table >= 2 and load_dt > 0%s", "");
+    if (c->state_law != RSFM_LAW_AGING && c->state_law != RSFM_LAW_SLIP)
+        return set_err(RSFM_ERR_INVALID, "bad state_law selector%s", "");
     if (c->integ_mode != RSFM_INTEG_PARITY && c->integ_mode != RSFM_INTEG_CARRY)
         return set_err(RSFM_ERR_INVALID, "bad integ_mode%s", "");
     if (c->loading == RSFM_LOAD_VSTEP && !(c->vstep_period > 0.0))
@@ -139,6 +143,8 @@ static ModelK make_model(const rsfm_cfg *c)
     M.vstep_rper = (c->loading == RSFM_LOAD_VSTEP) ? 1.0 / c->vstep_period : 1.0;
     M.stiff_exact = c->stiff_exact != 0;
     M.observable = c->observable;
+    M.state_law = c->state_law;
+    if (c->loading == RSFM_LOAD_TABLE) { M.load_n = c->n_load_table; M.load_dt = c->load_dt; M.load_tab = c->load_table_dev; }
     return M;
 }
 
@@ -389,9 +395,14 @@ extern "C" int rsfm_forward_batch(const rsfm_cfg *cfg, int32_t C, const double *
     const int block = pick_block(C, cfg);
     const int grid = (C + block - 1) / block;
     const ModelK M = make_model(cfg);
+    // The nominal load table (fast interval) serves the aging law; a tabulated load is not cached per process (the
+    // cache is keyed by the model constants, and the caller may rewrite the table behind the same pointer): those
+    // batches run the state-by-state interval path, whose warp-shared stage table is built from the table on the fly.
     const double *nom = nullptr;
-    rc = get_nominal_table(M, (cudaStream_t)stream, &nom);
-    if (rc) return rc;
+    if (cfg->state_law == RSFM_LAW_AGING && cfg->loading != RSFM_LOAD_TABLE) {
+        rc = get_nominal_table(M, (cudaStream_t)stream, &nom);
+        if (rc) return rc;
+    }
     const bool vs = stiff_variant(cfg);
     const int vgrid = (C + STIFF_BLOCK - 1) / STIFF_BLOCK;
 #define RSFM_FWD(MB, VS)                                                                                              \
@@ -438,6 +449,7 @@ struct rsfm_sampler {
     int initialised;
     int device;
     SamplerDev d;
+    double *nom_buf;               // the sampler's nominal load table (d.nom points at it, or is NULL for the slip law)
     double *scratch;               // [n_out][C] base trajectory for rsfm_init
     size_t scratch_bytes;
     char *slab;                    // one device buffer behind every array of `d`, `totals` and `reduce_out`
@@ -480,7 +492,7 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     char *b = s->slab;
     s->d.q = (double *)(b + o_q); s->d.sse = (double *)(b + o_sse); s->d.sigma2 = (double *)(b + o_s2);
     s->d.chol = (double *)(b + o_chol); s->d.ring = (double *)(b + o_ring); s->d.suff = (double *)(b + o_suff);
-    s->d.data = (double *)(b + o_data); s->d.nom = (double *)(b + o_nom);
+    s->d.data = (double *)(b + o_data); s->nom_buf = (double *)(b + o_nom); s->d.nom = s->nom_buf;
     s->d.accepted = (unsigned int *)(b + o_acc); s->d.status = (int *)(b + o_status);
     s->d.nrhs = (unsigned long long *)(b + o_cnt[0]); s->d.nstep = (unsigned long long *)(b + o_cnt[1]);
     s->d.nsolve = (unsigned long long *)(b + o_cnt[2]); s->d.nearly = (unsigned long long *)(b + o_cnt[3]);
@@ -646,8 +658,13 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * (d + tri(d)) * (size_t)C, stream));
     const int block = pick_block(C, &s->cfg), grid = (C + block - 1) / block;
     const ModelK M = make_model(&s->cfg);
-    loading_table_kernel<<<1, 1024, 0, stream>>>(M, s->d.nom);
-    CUDA_TRY(cudaGetLastError());
+    // nominal load table of this sampler (a tabulated load is read HERE: the table must not change afterwards); the
+    // slip law has no fast interval and runs without it
+    s->d.nom = s->cfg.state_law == RSFM_LAW_AGING ? s->nom_buf : nullptr;
+    if (s->d.nom) {
+        loading_table_kernel<<<1, 1024, 0, stream>>>(M, s->d.nom);
+        CUDA_TRY(cudaGetLastError());
+    }
     for (int pass = 0; pass <= d; pass++) {
 #define RSFM_INIT(D, VS)                                                                                              \
     rsf_init_kernel<D, VS><<<VS ? (C + STIFF_BLOCK - 1) / STIFF_BLOCK : grid, VS ? STIFF_BLOCK : block, 0, stream>>>( \
@@ -1694,18 +1711,32 @@ __global__ void chain_diag_kernel(const double *__restrict__ x, int n, int d, in
     // P_k = rho_{2k} + rho_{2k+1}, truncated at the first non-positive pair and made monotone.
     double tau = 0.0, prev_pair = 1e300;
     const int L = max_lag < n ? max_lag : n - 1;
-    for (int t = 0; t + 1 <= L; t += 2) {
-        double ca = 0.0, cb = 0.0;
-        for (int i = 0; i + t < n; i++) {
-            const double ei = xc[i * stride] - mean;
-            ca += ei * (xc[(i + t) * stride] - mean);
-            if (i + t + 1 < n) cb += ei * (xc[(i + t + 1) * stride] - mean);
+    // Eight lags (four pairs) per pass over the series: a register window e_{i+t0} .. e_{i+t0+7} slides along, so a
+    // pass costs two loads per draw for eight lags instead of three per pair.  Every c_t is the same left-to-right
+    // sum as before (same bits); the pairs are then judged in order and the first non-positive one ends the sum.
+    bool done = false;
+    for (int t0 = 0; t0 + 1 <= L && !done; t0 += 8) {
+        double cs[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        double w[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) w[j] = (t0 + j < n) ? xc[(size_t)(t0 + j) * stride] - mean : 0.0;
+        for (int i = 0; i + t0 < n; i++) {
+            const double ei = xc[(size_t)i * stride] - mean;
+#pragma unroll
+            for (int j = 0; j < 8; j++) cs[j] += ei * w[j];           // w[j] = e_{i+t0+j}, 0 beyond the end
+#pragma unroll
+            for (int j = 0; j < 7; j++) w[j] = w[j + 1];
+            w[7] = (i + t0 + 8 < n) ? xc[(size_t)(i + t0 + 8) * stride] - mean : 0.0;
         }
-        double pair = (ca + cb) / c0;
-        if (pair <= 0.0) break;
-        if (pair > prev_pair) pair = prev_pair;
-        prev_pair = pair;
-        tau += 2.0 * pair;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            if (done || t0 + j + 1 > L) { done = true; continue; }
+            double pair = (cs[j] + cs[j + 1]) / c0;
+            if (pair <= 0.0) { done = true; continue; }
+            if (pair > prev_pair) pair = prev_pair;
+            prev_pair = pair;
+            tau += 2.0 * pair;
+        }
     }
     tau -= 1.0;
     if (tau < 1.0 / n) tau = 1.0 / n;

@@ -28,7 +28,8 @@ K1 = 1.0e-7
 START_TIME = 0.0
 END_TIME = 50.0
 
-_LOADING = {"sine_decay": _lib.LOAD_SINE_DECAY, "vstep": _lib.LOAD_VSTEP}
+_LOADING = {"sine_decay": _lib.LOAD_SINE_DECAY, "vstep": _lib.LOAD_VSTEP, "table": _lib.LOAD_TABLE}
+_LAW = {"aging": _lib.LAW_AGING, "slip": _lib.LAW_SLIP}
 _INTEG = {"parity": _lib.INTEG_PARITY, "carry": _lib.INTEG_CARRY}
 _OBSERVABLE = {"acc": _lib.OBS_ACC, "mu": _lib.OBS_MU}
 _VARIANT = {"auto": _lib.VARIANT_AUTO, "default": _lib.VARIANT_DEFAULT, "stiff": _lib.VARIANT_STIFF}
@@ -61,6 +62,10 @@ class RateStateModel:
         self.vstep_factor = 10.0
         self.integ_mode = "parity"
         self.observable = "acc"
+        self.state_law = "aging"       # "slip": Ruina's law instead of Dieterich's (RateStateModel.py:340); extension
+        self.load_table = None         # loading = "table": V_l/V_ref - 1 at t_start + i * load_dt (piecewise linear)
+        self.load_dt = None            #   spacing of the table; None = delta_t
+        self._load_table_dev = None
         self.solver_variant = "auto"   # "default" / "stiff": force a kernel variant (tests, tuning)
         self.stiff_exact = False       # stiff variant: score every step that left the fast ranges
         self.block_threads = 0         # threads per block of the one-thread-per-chain kernels (0 = auto)
@@ -91,6 +96,20 @@ class RateStateModel:
         cfg.solver_variant = _VARIANT[self.solver_variant]
         cfg.stiff_exact = 1 if self.stiff_exact else 0
         cfg.block_threads = int(self.block_threads)
+        cfg.state_law = _LAW[self.state_law]
+        if self.loading == "table":
+            # the table lives on the device next to the model (the library reads it through the pointer)
+            torch = _lib.require_cuda()
+            tab = np.ascontiguousarray(self.load_table, dtype=np.float64).reshape(-1)
+            if tab.size < 2:
+                raise ValueError("load_table needs at least two entries")
+            dev = self._device(torch)
+            cur = self._load_table_dev
+            if cur is None or cur[0].device != dev or cur[1].shape != tab.shape or not np.array_equal(cur[1], tab):
+                self._load_table_dev = (torch.from_numpy(tab.copy()).to(dev), tab.copy())
+            cfg.load_table_dev = self._load_table_dev[0].data_ptr()
+            cfg.n_load_table = int(tab.size)
+            cfg.load_dt = float(self.delta_t if self.load_dt is None else self.load_dt)
         return cfg
 
     def _device(self, torch):

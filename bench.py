@@ -17,7 +17,7 @@ steps of a workload are its stated number of iterations, started from the start 
     cfg2   configs[1]: 1,024 chains, Dc posterior, no adaptation (list priors as main.py), 10 x 200 iterations
     cfg4r  configs[3] reduced: velocity-step loading x10 every 1,000 s, stiff regime (Dc ~ 0.05), 16,384 chains,
            series of 20,000 points (2,000 s: one velocity step; the stated 100,000 points are a parity test and
-           profiles/ record, 5.5 s of latency per solve), 2 x 2 iterations
+           profiles/ record, 5.5 s of latency per solve), 4 x 1 iterations
 At N = 1 the line is the cfg3 record and carries cfg2 / cfg5 (one shard) / cfg4r as `sub_records`, each with its own
 roofline (flops from ITS counters over ITS kernel time) and its own `traffic` (ncu capture of the same launch,
 profiles/ncu_traffic.json).  `--workload X` runs one workload alone as the headline.
@@ -67,7 +67,7 @@ WORKLOADS = {
                  truth=(0.011, 0.014, 1325.0), lo=[0.0], hi=[10000.0], loading="sine_decay",
                  text="cfg5: 131,072 chains per GPU (1,048,576 on 8), Dc posterior, N=500, proposal variance pooled over all "
                       "chains of all ranks every 10 iterations after 100, split-R-hat / ESS pooled over ranks"),
-    "cfg4r": dict(d=1, chains=16384, iters=2, steps=2, n_out=20000, t_end=2000.0, adapt=None, truth=(0.011, 0.014, 0.05),
+    "cfg4r": dict(d=1, chains=16384, iters=1, steps=4, n_out=20000, t_end=2000.0, adapt=None, truth=(0.011, 0.014, 0.05),
                   lo=[0.01], hi=[1.0], loading="vstep",
                   text="cfg4 reduced: velocity steps x10 every 1,000 s, stiff regime Dc ~ 0.05, 16,384 chains, series of "
                        "20,000 points (cfg 4 states 100,000)"),

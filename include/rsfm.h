@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RSFM_ABI_VERSION 2
+#define RSFM_ABI_VERSION 3
 #define RSFM_MAX_PARAMS 3
 
 typedef enum {
@@ -43,7 +43,14 @@ typedef enum {
 
 /* load-point velocity */
 enum { RSFM_LOAD_SINE_DECAY = 0,   /* RateStateModel.py:327-329 (reference) */
-       RSFM_LOAD_VSTEP = 1 };      /* piecewise-constant extension */
+       RSFM_LOAD_VSTEP = 1,        /* piecewise-constant extension */
+       RSFM_LOAD_TABLE = 2 };      /* tabulated extension: V_l/V_ref - 1 at t_start + i load_dt (load_table_dev,
+                                      n_load_table entries), piecewise linear in between, constant beyond the ends */
+
+/* state-evolution law */
+enum { RSFM_LAW_AGING = 0,         /* Dieterich: theta' = 1 - v theta/Dc, RateStateModel.py:340 (reference) */
+       RSFM_LAW_SLIP = 1 };        /* Ruina: theta' = -(v theta/Dc) ln(v theta/Dc) (extension; every step is scored
+                                      with the general-range stages, about 3x the cost of the aging law) */
 
 /* time-integration mode */
 enum { RSFM_INTEG_PARITY = 0,      /* fresh dop853 call + hinit per output interval:
@@ -102,6 +109,10 @@ typedef struct rsfm_cfg {
                                             general-range stages instead of taking exploding trial steps as rejected */
     int32_t block_threads;               /* threads per block of the one-thread-per-chain kernels: 0 auto, or
                                             32 / 64 / 96 / 128 (tuning; results never depend on it) */
+    int32_t state_law;                   /* RSFM_LAW_* */
+    int32_t n_load_table;                /* RSFM_LOAD_TABLE: entries (>= 2), spacing and DEVICE pointer of the table; */
+    double  load_dt;                     /*   read by every call that gets this cfg and by rsfm_init, which tabulates */
+    const double *load_table_dev;        /*   it for the sampler: keep it valid and unchanged while they run */
 } rsfm_cfg;
 
 typedef struct rsfm_sampler rsfm_sampler;   /* opaque; owns per-chain device state */

@@ -17,8 +17,11 @@ _SO = os.path.join(_HERE, "librsf_oracle.so")
 
 LOAD_SINE_DECAY = 0
 LOAD_VSTEP = 1
+LOAD_TABLE = 2
 OBS_ACC = 0
 OBS_MU = 1
+LAW_AGING = 0
+LAW_SLIP = 1
 
 
 class OrcModel(C.Structure):
@@ -34,6 +37,8 @@ class OrcModel(C.Structure):
         ("rtol", C.c_double), ("atol", C.c_double),
         ("nmax", C.c_int),
         ("observable", C.c_int),
+        ("state_law", C.c_int),
+        ("load_table", C.POINTER(C.c_double)), ("n_load_table", C.c_int), ("load_dt", C.c_double),
     ]
 
 
@@ -101,6 +106,12 @@ def make_model(Dc=1000.0, number_time_steps=500, start_time=0.0, end_time=50.0, 
     for k, v in kw.items():
         if not hasattr(m, k):
             raise AttributeError(k)
+        if k == "load_table":
+            tab = np.ascontiguousarray(v, dtype=np.float64)
+            m._load_table_keepalive = tab                     # the struct only holds the pointer
+            m.load_table = tab.ctypes.data_as(C.POINTER(C.c_double))
+            m.n_load_table = tab.size
+            continue
         setattr(m, k, v)
     return m
 

@@ -44,6 +44,8 @@ void orc_model_defaults(orc_model *m)
     m->vstep_period = 1000.0; m->vstep_factor = 10.0;
     m->rtol = 1e-6; m->atol = 1e-10; m->nmax = 500;
     m->observable = ORC_OBS_ACC;
+    m->state_law = ORC_LAW_AGING;
+    m->load_table = 0; m->n_load_table = 0; m->load_dt = 0.1;
 }
 
 /* load-point velocity.  SINE_DECAY is the reference (RateStateModel.py:327-329);
@@ -55,6 +57,22 @@ static double loading_velocity(const orc_model *m, double t)
         double ph = floor((t - m->t_start) / m->vstep_period);
         int odd = ((long long)ph) & 1;
         return odd ? m->vstep_factor * m->V_ref : m->V_ref;
+    }
+    if (m->loading == ORC_LOAD_TABLE) {
+        /* piecewise linear through the tabulated relative perturbation; x = (t - t_start)/load_dt as ONE rounded
+         * division, the interpolation T[i] + fr (T[i+1] - T[i]) as written (no fused multiply-add) */
+        const int n = m->n_load_table;
+        const double x = (t - m->t_start) / m->load_dt;
+        double fi = floor(x);
+        if (fi < 0.0) fi = 0.0;
+        if (fi > (double)(n - 2)) fi = (double)(n - 2);
+        double fr = x - fi;
+        if (fr < 0.0) fr = 0.0;
+        if (fr > 1.0) fr = 1.0;
+        const int i = (int)fi;
+        const double d = m->load_table[i + 1] - m->load_table[i];
+        volatile double prod = fr * d;                          /* keep the product rounded on its own */
+        return m->V_ref * (1.0 + (m->load_table[i] + prod));
     }
     const double a1 = 20.0, a2 = 10.0;
     return m->V_ref * (1.0 + exp(-t / a1) * sin(a2 * t));
@@ -70,6 +88,10 @@ void orc_rhs(const orc_model *m, double t, const double y[3], double dydt[3])
     const double temp = 1 / a * (y[0] - m->mu_ref - b * log(V_ref * y[1] / dc));  /* :336 */
     const double v = V_ref * exp(temp);                         /* :337 */
     dydt[1] = 1. - v * y[1] / dc;                               /* :340 */
+    if (m->state_law == ORC_LAW_SLIP) {                         /* Ruina slip law (extension) */
+        const double z = v * y[1] / dc;
+        dydt[1] = -z * log(z);
+    }
     dydt[0] = kprime * V_l - kprime * v;                        /* :343 */
     dydt[2] = v / a * (dydt[0] - b / y[1] * dydt[1]);           /* :346 */
     if (m->radiation_damping) {                                 /* :349-353 */

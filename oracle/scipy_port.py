@@ -35,6 +35,8 @@ class PortModel:
         self.loading = "sine_decay"          # "vstep": ONLY the load-point line of the RHS is swapped
         self.vstep_period, self.vstep_factor = 1000.0, 10.0
         self.observable = "acc"              # "mu": evaluate()[1] is the friction series (:385)
+        self.state_law = "aging"             # "slip": ONLY the state-evolution line (:340) is swapped (Ruina)
+        self.load_table, self.load_dt = None, 0.1   # loading = "table": piecewise-linear V_l/V_ref - 1
 
     def _rhs(self, t, y):
         # RateStateModel.py:318-355
@@ -44,12 +46,22 @@ class PortModel:
         if self.loading == "vstep":
             odd = int(np.floor((t - self.t_start) / self.vstep_period)) & 1
             v_l = self.vstep_factor * v_ref if odd else v_ref
+        elif self.loading == "table":
+            tab = self.load_table
+            x = (t - self.t_start) / self.load_dt
+            fi = min(max(np.floor(x), 0.0), float(len(tab) - 2))
+            fr = min(max(x - fi, 0.0), 1.0)
+            i = int(fi)
+            v_l = v_ref * (1 + (tab[i] + fr * (tab[i + 1] - tab[i])))
         else:
             v_l = v_ref * (1 + exp(-t / 20) * sin(10 * t))            # RateStateModel.py:327-329
         out = np.zeros((len(y), 1))
         temp = 1 / a * (y[0] - self.mu_ref - b * log(v_ref * y[1] / dc))
         v = v_ref * exp(temp)
         out[1] = 1. - v * y[1] / dc
+        if self.state_law == "slip":
+            z = v * y[1] / dc
+            out[1] = -z * log(z)
         out[0] = kprime * v_l - kprime * v
         out[2] = v / a * (out[0] - b / y[1] * out[1])
         if self.RadiationDamping:

@@ -24,7 +24,7 @@ def test_header_symbols_all_exported(built_lib, pkg):
 
 
 def test_abi_version_and_defaults(built_lib, pkg):
-    assert built_lib.rsfm_abi_version() == 2
+    assert built_lib.rsfm_abi_version() == 3
     cfg = pkg._lib.default_cfg()
     # RateStateModel.py:5-11 / :374 / MCMC.py:97
     assert (cfg.a, cfg.b, cfg.mu_ref, cfg.V_ref, cfg.k1) == (0.011, 0.014, 0.6, 1.0, 1e-7)
@@ -89,6 +89,7 @@ def test_cfg_validation_needs_no_device(built_lib, pkg):
                      ({"rtol": 0.0}, "rtol"), ({"n_params": 2}, "n_params"), ({"loading": 7}, "loading"),
                      ({"adapt_interval": 1, "adapt_mode": pkg._lib.ADAPT_COMPAT}, "adapt_interval"),
                      ({"observable": 5}, "observable"), ({"solver_variant": 9}, "solver_variant"),
+                     ({"state_law": 3}, "state_law"), ({"loading": 2}, "RSFM_LOAD_TABLE"),
                      ({"block_threads": 48}, "block_threads"), ({"spec_depth": 6}, "spec_depth"),
                      ({"delta_t": 0.0}, "grid"), ({"a": -1.0}, "positive")):
         rc, msg = refused(**kw)

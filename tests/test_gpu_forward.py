@@ -402,3 +402,77 @@ def test_cfg4_full_size_trajectories_vs_oracle(cuda, pkg, orc, dcs):
         assert 1.0e7 < nrhs_g[i] < 6.0e7                                      # ~2e7 RHS per solve
     # the likelihood the sampler sees is usable at this size: SSE is smallest at the true Dc
     assert np.argmin(sse_g) == 1
+
+
+def _load_table(n, dt):
+    tt = np.arange(n + 1) * dt
+    return 0.5 * np.sin(0.7 * tt) * np.exp(-tt / 30.0) + 0.3 * (tt > 20.0)
+
+
+@pytest.mark.parametrize("law, loading", [("slip", "sine_decay"), ("aging", "table"), ("slip", "table")])
+def test_slip_law_and_tabulated_loading_vs_oracle(cuda, pkg, orc, law, loading):
+    """SURVEY 8f.4 extensions on the device: Ruina's slip law (general-range stages only) and a piecewise-linear
+    tabulated load, against the C oracle (itself bit-identical to SciPy with the one line swapped,
+    tests/test_oracle_vs_scipy.py): trajectory gate 1e-9 outside the stiff regime, SSE and step counters too."""
+    tab = _load_table(500, 0.1)
+    dcs = np.array([120.0, 300.0, 1350.0, 5000.0, 9000.0])
+    for damping in (True, False):
+        m = pkg.RateStateModel()
+        m.RadiationDamping = damping
+        m.state_law, m.loading = law, loading
+        m.load_table, m.load_dt = tab, 0.1
+        rng = np.random.default_rng(7)
+        kw = dict(radiation_damping=int(damping), state_law=orc.LAW_SLIP if law == "slip" else orc.LAW_AGING)
+        if loading == "table":
+            kw.update(loading=orc.LOAD_TABLE, load_table=tab, load_dt=0.1)
+        truth = orc.forward(orc.make_model(Dc=1350.0, **kw))[1]
+        data = truth + np.abs(truth) * rng.standard_normal(truth.size)
+        out = m.evaluate_batch(dcs, data=data)
+        assert np.all(out["status"].cpu().numpy() == 0)
+        acc_g = out["acc"].t().cpu().numpy()
+        for i, dc in enumerate(dcs):
+            t_o, acc_o, st = orc.forward(orc.make_model(Dc=dc, **kw))
+            err = _check(acc_g[i], acc_o, dc)
+            _record(f"ext_{law}_{loading}_damp{int(damping)}_Dc{dc}", Dc=dc, err_rel=err)
+            assert int(out["nstep"][i]) == st.nstep
+            assert out["sse"][i].item() == pytest.approx(float(np.sum((acc_o - data) ** 2)), rel=1e-9)
+    # evaluate() through the model protocol
+    m.Dc = 1350.0
+    _, acc1, _ = m.evaluate()
+    assert np.array_equal(acc1, acc_g[2])
+
+
+def test_slip_law_in_the_stiff_regime_and_rhs(cuda, pkg, orc):
+    """The slip law under velocity steps (stiff variant; gate = measured floor as for the aging law) and the RHS
+    hook: rsfm_rhs_eval(general = 1) evaluates theta' = -(v theta/Dc) ln(v theta/Dc) like the oracle."""
+    import ctypes as C
+    torch = cuda
+    n, t_end = 600, 60.0
+    kw = dict(number_time_steps=n, end_time=t_end, loading=orc.LOAD_VSTEP, vstep_period=15.0, vstep_factor=10.0,
+              state_law=orc.LAW_SLIP)
+    m = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
+    m.loading, m.vstep_period, m.vstep_factor, m.state_law = "vstep", 15.0, 10.0, "slip"
+    dcs = np.array([0.08, 0.5, 30.0, 400.0])
+    out = m.evaluate_batch(dcs)
+    assert np.all(out["status"].cpu().numpy() == 0)
+    acc_g = out["acc"].t().cpu().numpy()
+    for i, dc in enumerate(dcs):
+        _check_stiff(orc, acc_g[i], dc, f"vstep_slip_n600_Dc{dc}", **kw)
+    # RHS at states away from steady state
+    rng = np.random.default_rng(2)
+    k = 64
+    dc = rng.uniform(50.0, 5000.0, k)
+    th = dc * rng.uniform(0.7, 1.4, k)
+    mu = 0.6 + rng.uniform(-0.01, 0.01, k)
+    t = rng.uniform(0.0, 50.0, k)
+    m2 = pkg.RateStateModel()
+    m2.state_law = "slip"
+    cfg = m2.to_cfg()
+    args = [torch.from_numpy(x).cuda() for x in (t, mu, th, dc)]
+    got = torch.empty((3, k), dtype=torch.float64, device="cuda")
+    pkg._lib.check(pkg._lib.load().rsfm_rhs_eval(C.byref(cfg), k, *[a.data_ptr() for a in args], None, None, 1,
+                                                 got.data_ptr(), None))
+    got = got.cpu().numpy().T
+    for i in range(k):
+        want = orc.rhs(orc.make_model(Dc=dc[i], state_law=orc.LAW_SLIP), t[i], [mu[i], th[i], 1.0])
+        assert np.allclose(got[i], want, rtol=1e-12, atol=1e-15 * np.abs(want).max()), i

@@ -765,3 +765,32 @@ def test_compat_checkpoint_mid_window_resumes_exactly(cuda, pkg):
     assert np.array_equal(p1.samples_device.cpu().numpy(), a[:24])
     assert np.array_equal(p2.samples_device.cpu().numpy()[1:], a[24:])
     assert np.array_equal(p2.checkpoint()["chol"], full.checkpoint()["chol"])
+
+
+@pytest.mark.parametrize("spec_depth", [1, 0])
+def test_slip_law_and_tabulated_load_chains_replay_through_oracle(cuda, pkg, orc, spec_depth):
+    """Sampler level for the SURVEY 8f.4 extensions: Philox-driven chains under Ruina's slip law with a tabulated
+    load (sequential and speculative kernel) replayed on the CPU oracle with the draws they report -- the same
+    accept / reject decision at every step, the same samples, sigma^2 to 1e-8."""
+    torch = cuda
+    tt = np.arange(501) * 0.1
+    tab = 0.5 * np.sin(0.7 * tt) * np.exp(-tt / 30.0) + 0.3 * (tt > 20.0)
+    om = orc.make_model(Dc=1325.0, state_law=orc.LAW_SLIP, loading=orc.LOAD_TABLE, load_table=tab, load_dt=0.1)
+    rng = np.random.default_rng(21)
+    truth = orc.forward(om)[1]
+    data = truth + np.abs(truth) * rng.standard_normal(truth.size)
+    model = pkg.RateStateModel()
+    model.state_law, model.loading, model.load_table, model.load_dt = "slip", "table", tab, 0.1
+    cfg = model.to_cfg()
+    cfg.n_params, cfg.n_prior_len, cfg.spec_depth = 1, 3, spec_depth
+    cfg.lo[0], cfg.hi[0] = 0.0, 1e4
+    c, ns = 40, 24
+    samples, s2, acc, draws, depth, tot = _run_with_draws(torch, pkg, cfg, c, 11, 500, [1100.0], data, [ns])
+    assert (depth >= 2) == (spec_depth == 0)
+    assert 0 < acc.mean() < 1
+    for ch in (0, 7, 33, 39):
+        chain_o, s2_o, acc_o, _, _ = orc.chain_replay(om, data, 1100.0, 0.0, 1e4, 3, ns, draws[:, 0, ch],
+                                                      np.nan_to_num(draws[:, 1, ch], nan=0.5), draws[:, 2, ch])
+        assert np.array_equal(acc[:, ch], acc_o), ch
+        assert np.array_equal(samples[:, 0, ch], chain_o[1:]), ch
+        assert np.allclose(s2[:, ch], s2_o[1:], rtol=1e-8, atol=0)

@@ -141,3 +141,40 @@ def test_mu_observable_pinned_on_scipy(orc):
     # forward_batch / chain replay score the same series when the model says so
     _, obs, _ = orc.forward_batch(orc.make_model(observable=orc.OBS_MU), [1350.0], want_acc=True)
     assert np.array_equal(obs[0], mu_o)
+
+
+def _table(n, dt):
+    tt = np.arange(n + 1) * dt
+    return 0.5 * np.sin(0.7 * tt) * np.exp(-tt / 30.0) + 0.3 * (tt > 20.0)
+
+
+@pytest.mark.parametrize("dc", [300.0, 1350.0])
+def test_slip_law_and_tabulated_loading_pinned_on_scipy(orc, dc):
+    """Extensions of SURVEY 8f.4, each ONE line of the reference's RHS swapped in the SciPy driver
+    (RateStateModel.py:340 for Ruina's slip law, :327-329 for a piecewise-linear tabulated load): the C oracle
+    reproduces SciPy's trajectories to the last bit, as it does for the reference's own RHS."""
+    from oracle import scipy_port
+    tab = _table(500, 0.1)
+    for law, loading in (("slip", "sine_decay"), ("aging", "table"), ("slip", "table")):
+        pm = scipy_port.PortModel()
+        pm.Dc, pm.state_law, pm.loading, pm.load_table, pm.load_dt = dc, law, loading, tab, 0.1
+        _, acc_p, _ = pm.evaluate()
+        kw = dict(state_law=orc.LAW_SLIP if law == "slip" else orc.LAW_AGING)
+        if loading == "table":
+            kw.update(loading=orc.LOAD_TABLE, load_table=tab, load_dt=0.1)
+        t_o, acc_o, st = orc.forward(orc.make_model(Dc=dc, **kw))
+        assert st.istate == 1 and st.filled == 500
+        assert np.max(np.abs(acc_o - acc_p)) <= 1e-13 * np.max(np.abs(acc_p)), (law, loading)
+    # the swapped lines are felt: the slip law moves the trajectory at the 1e-7 .. 1e-5 level (both laws share
+    # their linearisation about steady state), the tabulated load changes it altogether
+    base = orc.forward(orc.make_model(Dc=dc))[1]
+    slip = orc.forward(orc.make_model(Dc=dc, state_law=orc.LAW_SLIP))[1]
+    tabd = orc.forward(orc.make_model(Dc=dc, loading=orc.LOAD_TABLE, load_table=tab, load_dt=0.1))[1]
+    scale = np.max(np.abs(base))
+    assert 1e-8 * scale < np.max(np.abs(slip - base)) < 1e-3 * scale
+    assert np.max(np.abs(tabd - base)) > 0.1 * scale
+    # beyond the ends the table is held constant
+    short = orc.forward(orc.make_model(Dc=dc, loading=orc.LOAD_TABLE, load_table=np.append(tab[:201], tab[200]), load_dt=0.1))[1]
+    const = orc.forward(orc.make_model(Dc=dc, loading=orc.LOAD_TABLE, load_table=np.concatenate([tab[:201], np.full(300, tab[200])]),
+                                       load_dt=0.1))[1]
+    assert np.array_equal(short, const)
