@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "rsfm_kde_grid", "rsfm_measure_fp64_peak", "rsfm_trim",
     "rsfm_pooled_groups", "rsfm_pooled_partials", "rsfm_pooled_update",
     "rsfm_philox_raw", "rsfm_philox_draws", "rsfm_rhs_eval", "rsfm_get_ring", "rsfm_set_ring",
+    "rsfm_chain_groups", "rsfm_join", "rsfm_pooled_install",
 )
 
 
@@ -49,7 +50,7 @@ class RsfmCfg(C.Structure):
         ("n_prior_len", C.c_int32), ("adapt_interval", C.c_int32), ("adapt_mode", C.c_int32),
         ("spec_depth", C.c_int32),
         ("observable", C.c_int32), ("solver_variant", C.c_int32), ("stiff_exact", C.c_int32),
-        ("block_threads", C.c_int32),
+        ("block_threads", C.c_int32), ("chain_groups", C.c_int32),
         ("state_law", C.c_int32), ("n_load_table", C.c_int32), ("load_dt", C.c_double), ("load_table_dev", C.c_void_p),
     ]
 
@@ -90,6 +91,12 @@ def load():
     lib.rsfm_run.restype = C.c_int
     lib.rsfm_spec_depth.argtypes = [vp]
     lib.rsfm_spec_depth.restype = C.c_int
+    lib.rsfm_chain_groups.argtypes = [vp]
+    lib.rsfm_chain_groups.restype = C.c_int
+    lib.rsfm_join.argtypes = [vp, vp]
+    lib.rsfm_join.restype = C.c_int
+    lib.rsfm_pooled_install.argtypes = [vp, vp]
+    lib.rsfm_pooled_install.restype = C.c_int
     lib.rsfm_run_deterministic.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.rsfm_run_deterministic.restype = C.c_int
     lib.rsfm_get_state.argtypes = [vp] + [vp] * 8 + [vp]

@@ -19,15 +19,18 @@ class PooledAdaptation:
     """Device-side pooled adaptive Metropolis around a ``rsfm_sampler`` (generalises
     MCMC.py:162-204, 523-527).  Per interval j of ``adapt_interval`` iterations, with no host synchronisation:
 
-        main stream   [update(j-2)]  rsfm_run(j)  rsfm_pooled_partials(j)
-        side stream                               all-gather(j) ............
+        main stream   [install(j-2)] [form(j-1)]  rsfm_run(j)  rsfm_pooled_partials(j)
+        side stream                                            all-gather(j) ............
 
     ``partials`` are sums over fixed groups of 1,024 chains aligned on the global chain id; the all-gather
     (NCCL over NVLink; nothing for one rank) puts every rank's rows in global chain order and
     ``rsfm_pooled_update`` adds them to the running moments in that order, forms (2.38^2/d) cov and its
     Cholesky factor in closed form and installs it for every chain -- the same bits on every rank and for any
-    number of ranks.  The all-gather of interval j overlaps the kernel of interval j+1; its factor is used from
-    interval j+2 on (adaptation lags one interval, as SURVEY 8e allows).
+    number of ranks.  The all-gather of interval j overlaps the kernel of interval j+1; its factor is FORMED before
+    interval j+1 is launched and used from interval j+2 on (adaptation lags one interval, as SURVEY 8e allows).
+    Forming early matters with chain groups (``rsfm_chain_groups``: the chains of a large sampler are served by
+    several launches on the sampler's own streams): a group's install waits for the forming of the factor, which
+    happened an interval ago, and never for the other groups' launches still running.
 
     Use: ``before_interval()`` -> launch the interval's iterations on the current stream ->
     ``after_interval(end_iteration)``; ``finish()`` at the end."""
@@ -48,6 +51,7 @@ class PooledAdaptation:
         self.main = torch.cuda.current_stream(dev)
         self.gathered, self.ends, self.tev = {}, {}, []
         self.j = 0
+        self.formed = -10                      # last interval whose factor has been formed
 
     def preload(self, moments, pending_rows, end_iteration):
         """State of a checkpoint taken on an adaptation boundary: the moments already applied and the gathered
@@ -60,21 +64,30 @@ class PooledAdaptation:
         self.parts[1].copy_(torch.as_tensor(pend))
         self.gathered[-1], self.ends[-1] = self.main.record_event(), int(end_iteration)
 
-    def _update(self, j):
-        """moments += rows(j) and, past adapt_start, install the factor they give (main stream)."""
+    def _form(self, j):
+        """moments += rows(j) and, past adapt_start, form the factor they give (main stream); it is installed one
+        interval later (``_install``)."""
         torch = self.torch
         self.main.wait_event(self.gathered[j])
         acc = 1 if self.ends[j] > self.adapt_start // 2 else 0          # the earliest draws stay out of the moments
-        inst = 1 if self.ends[j] >= self.adapt_start else 0
+        inst = 2 if self.ends[j] >= self.adapt_start else 0
         if j + 1 >= self.hist.shape[0]:
             self.hist = torch.cat([self.hist, torch.zeros_like(self.hist)])
         p = self.parts[j % 2]
         _lib.check(self.lib.rsfm_pooled_update(self.handle, _lib.ptr(p), int(p.shape[0]), _lib.ptr(self.moments), acc, inst,
                                                _lib.ptr(self.hist[j + 1]), self.stream), "rsfm_pooled_update")
+        self.formed = j
+
+    def _install(self):
+        """The factor formed last (if any) replaces every chain's proposal factor."""
+        _lib.check(self.lib.rsfm_pooled_install(self.handle, self.stream), "rsfm_pooled_install")
 
     def before_interval(self):
-        if (self.j - 2) in self.gathered:
-            self._update(self.j - 2)
+        j = self.j
+        if self.formed == j - 2:
+            self._install()                       # factor of interval j-2, formed before interval j-1 was launched
+        if (j - 1) in self.gathered and self.formed < j - 1:
+            self._form(j - 1)
 
     def after_interval(self, end_iteration):
         torch, j = self.torch, self.j
@@ -98,8 +111,8 @@ class PooledAdaptation:
         """Apply what an uninterrupted run would have applied before its next interval; the last interval's rows
         stay pending (one-interval lag) and are returned with the moments for a checkpoint.  Synchronises."""
         torch = self.torch
-        if (self.j - 2) in self.gathered:
-            self._update(self.j - 2)
+        if self.formed == self.j - 2:
+            self._install()
         pending = None
         if (self.j - 1) in self.gathered:
             self.main.wait_event(self.gathered[self.j - 1])

@@ -126,6 +126,8 @@ static int check_cfg(const rsfm_cfg *c)
         c->block_threads != 128)
         return set_err(RSFM_ERR_INVALID, "block_threads must be 0, 32, 64, 96 or 128%s", "");
     if (c->spec_depth < 0 || c->spec_depth > 5) return set_err(RSFM_ERR_INVALID, "spec_depth must be in [0, 5]%s", "");
+    if (c->chain_groups < 0 || c->chain_groups > RSFM_MAX_GROUPS)
+        return set_err(RSFM_ERR_INVALID, "chain_groups must be in [0, 4]%s", "");
     return RSFM_OK;
 }
 
@@ -456,9 +458,59 @@ struct rsfm_sampler {
     size_t slab_bytes;
     double *reduce_out;            // [16] device scratch for suffstats
     unsigned long long *totals;    // [8] device scratch for rsfm_get_totals
+    // Chain groups (pooled adaptation, large batches): the chains are served by n_groups launches on the sampler's
+    // own streams, which have no barrier in common -- the tail of one group's 10-iteration launch overlaps the next
+    // launches of the others (a 65,536-chain launch is 1.15 waves and left the SMs idle 18 % of the time).
+    int n_groups;                  // 1 = off
+    cudaStream_t gstream[RSFM_MAX_GROUPS];
+    cudaEvent_t gevent[RSFM_MAX_GROUPS];
+    cudaEvent_t fork_event, fac_event[2];
+    int need_fork;                 // state was written on the caller's stream since the groups last met it
+    int in_flight;                 // group work the caller's stream has not been ordered behind yet
+    double *fac_buf[2];            // proposal factor of the pooled update, double-buffered for the group installs
+    int fac_parity;
+    int staged;                    // slot of a factor formed by rsfm_pooled_update(install = 2) and not installed yet, or -1
 };
 
 static int tri(int d) { return d * (d + 1) / 2; }
+
+// ---------------------------------------------------------------------------
+// chain groups
+// ---------------------------------------------------------------------------
+// Number of groups a sampler runs with: RSFM_ADAPT_POOLED only (there the launches are one adaptation interval
+// long), the one-thread-per-chain default kernel, group boundaries on multiples of RSFM_POOL_GROUP in the GLOBAL
+// chain numbering (each group then owns whole rows of the pooled partial sums) and at least 8,192 chains per group.
+static int pick_groups(const rsfm_cfg *c, int C, uint64_t chain_id0)
+{
+    if (c->adapt_mode != RSFM_ADAPT_POOLED || c->chain_groups == 1) return 1;
+    if (stiff_variant(c) || c->n_out > 2 * SERIES_TILE) return 1;
+    if (chain_id0 % RSFM_POOL_GROUP != 0) return 1;
+    int g = c->chain_groups >= 2 ? c->chain_groups : 4;
+    while (g > 1 && (C % (g * RSFM_POOL_GROUP) != 0 || C / g < 8192)) g--;
+    return g;
+}
+
+// Order the caller's stream behind everything the groups have been given so far.
+static int join_groups(rsfm_sampler *s, cudaStream_t stream)
+{
+    if (s->n_groups <= 1 || !s->in_flight) return RSFM_OK;
+    for (int g = 0; g < s->n_groups; g++) {
+        CUDA_TRY(cudaEventRecord(s->gevent[g], s->gstream[g]));
+        CUDA_TRY(cudaStreamWaitEvent(stream, s->gevent[g], 0));
+    }
+    s->in_flight = 0;
+    return RSFM_OK;
+}
+
+// Order the groups behind what the caller's stream holds (state written by rsfm_init / rsfm_set_*).
+static int fork_groups(rsfm_sampler *s, cudaStream_t stream)
+{
+    if (s->n_groups <= 1 || !s->need_fork) return RSFM_OK;
+    CUDA_TRY(cudaEventRecord(s->fork_event, stream));
+    for (int g = 0; g < s->n_groups; g++) CUDA_TRY(cudaStreamWaitEvent(s->gstream[g], s->fork_event, 0));
+    s->need_fork = 0;
+    return RSFM_OK;
+}
 
 extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t seed, uint64_t chain_id0)
 {
@@ -483,6 +535,7 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     size_t o_cnt[7];
     for (size_t &o : o_cnt) o = take(sizeof(unsigned long long) * Cz);
     const size_t o_totals = take(sizeof(unsigned long long) * 16), o_reduce = take(sizeof(double) * 16);
+    const size_t o_fac2 = take(sizeof(double) * 16);
     s->slab_bytes = off;
     if (scratch_acquire(off, (void **)&s->slab) != RSFM_OK || cudaMemset(s->slab, 0, off) != cudaSuccess) {
         set_err(RSFM_ERR_CUDA, "rsfm_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -499,6 +552,23 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     s->d.nexec = (unsigned long long *)(b + o_cnt[4]); s->d.urhs = (unsigned long long *)(b + o_cnt[5]);
     s->d.ustep = (unsigned long long *)(b + o_cnt[6]);
     s->totals = (unsigned long long *)(b + o_totals); s->reduce_out = (double *)(b + o_reduce);
+    s->fac_buf[0] = s->reduce_out; s->fac_buf[1] = (double *)(b + o_fac2);
+    s->n_groups = pick_groups(cfg, C, chain_id0);
+    s->need_fork = 1;
+    s->staged = -1;
+    {
+        bool ok = cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s->fac_event[0], cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s->fac_event[1], cudaEventDisableTiming) == cudaSuccess;
+        for (int g = 0; g < s->n_groups && ok && s->n_groups > 1; g++)
+            ok = cudaStreamCreateWithFlags(&s->gstream[g], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s->gevent[g], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            set_err(RSFM_ERR_CUDA, "rsfm_create: stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rsfm_destroy(s);
+            return nullptr;
+        }
+    }
     return s;
 }
 
@@ -509,6 +579,13 @@ extern "C" void rsfm_destroy(rsfm_sampler *s)
     cudaGetDevice(&cur);
     if (cur != s->device) cudaSetDevice(s->device);
     if (s->slab || s->scratch) cudaDeviceSynchronize();      // nothing may still be using the buffers
+    for (int g = 0; g < RSFM_MAX_GROUPS; g++) {
+        if (s->gstream[g]) cudaStreamDestroy(s->gstream[g]);
+        if (s->gevent[g]) cudaEventDestroy(s->gevent[g]);
+    }
+    if (s->fork_event) cudaEventDestroy(s->fork_event);
+    if (s->fac_event[0]) cudaEventDestroy(s->fac_event[0]);
+    if (s->fac_event[1]) cudaEventDestroy(s->fac_event[1]);
     if (s->scratch) scratch_release(s->scratch, s->scratch_bytes);     // only after a failed rsfm_init
     if (s->slab) scratch_release(s->slab, s->slab_bytes);
     if (cur != s->device) cudaSetDevice(cur);
@@ -636,6 +713,7 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
 {
     if (!s || !q0_dev || !data_dev) return set_err(RSFM_ERR_INVALID, "rsfm_init: NULL argument%s", "");
     cudaStream_t stream = (cudaStream_t)stream_;
+    { int rc_ = join_groups(s, stream); if (rc_) return rc_; s->need_fork = 1; }
     const int d = s->cfg.n_params, C = s->C, n = s->cfg.n_out;
     CUDA_TRY(cudaMemcpyAsync(s->d.q, q0_dev, sizeof(double) * d * (size_t)C, cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(s->d.data, data_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
@@ -716,6 +794,7 @@ struct RunArgs {
     double a0, b0, n0;
     double lo[RSFM_MAX_PARAMS], hi[RSFM_MAX_PARAMS];
     int adapt_mode, adapt_interval;
+    int c_begin, c_end;     // chains [c_begin, c_end) of the sampler are served by this launch (chain groups)
 };
 
 // (128, 3): three resident blocks per SM (<= 168 registers); measured +5 % at saturating sizes
@@ -730,9 +809,9 @@ rsf_mcmc_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunArgs A
     LoadScratch lscr;
     lscr.tab = s_ltab; lscr.priv = s_lpriv; lscr.nom = S.nom;
     constexpr int T = D * (D + 1) / 2;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = c < C;
-    const int cc = active ? c : C - 1;
+    const int c = A.c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = c < A.c_end;
+    const int cc = active ? c : A.c_end - 1;
     const size_t Cz = (size_t)C;
 
     double q[D], L[T], sq[D], sqq[T];
@@ -1256,6 +1335,17 @@ static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
     return g >= 2 ? g : 0;
 }
 
+extern "C" int rsfm_chain_groups(const rsfm_sampler *s) { return s ? s->n_groups : -1; }
+
+extern "C" int rsfm_join(rsfm_sampler *s, void *stream_)
+{
+    if (!s) return set_err(RSFM_ERR_INVALID, "rsfm_join: NULL sampler%s", "");
+    int rc = join_groups(s, (cudaStream_t)stream_);
+    if (rc) return rc;
+    s->need_fork = 1;
+    return RSFM_OK;
+}
+
 extern "C" int rsfm_spec_depth(const rsfm_sampler *s)
 {
     if (!s) return -1;
@@ -1273,9 +1363,33 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
     A.a0 = s->cfg.a; A.b0 = s->cfg.b; A.n0 = s->cfg.n0;
     for (int i = 0; i < RSFM_MAX_PARAMS; i++) { A.lo[i] = s->cfg.lo[i]; A.hi[i] = s->cfg.hi[i]; }
     A.adapt_mode = s->cfg.adapt_mode; A.adapt_interval = s->cfg.adapt_interval;
+    A.c_begin = 0; A.c_end = C;
     const ModelK M = make_model(&s->cfg);
     const int g = pick_spec_depth(s, A);
     const bool vs = stiff_variant(&s->cfg);
+    // Chain groups: Philox-driven launches of the one-thread-per-chain kernel go to the sampler's own streams, one
+    // launch per group, and are NOT joined here -- the caller's stream is ordered behind them by the next call on
+    // this sampler that needs their results (rsfm_pooled_partials and every getter / setter; rsfm_join).
+    if (s->n_groups > 1 && g < 2 && !A.deterministic && !vs) {
+        int rc = fork_groups(s, stream);
+        if (rc) return rc;
+        const int per = C / s->n_groups, ggrid = (per + block - 1) / block;
+        for (int k = 0; k < s->n_groups; k++) {
+            A.c_begin = k * per; A.c_end = (k + 1) * per;
+            if (s->cfg.n_params == 1) rsf_mcmc_kernel<1, false, false><<<ggrid, block, 0, s->gstream[k]>>>(M, C, s->d, A);
+            else rsf_mcmc_kernel<3, false, false><<<ggrid, block, 0, s->gstream[k]>>>(M, C, s->d, A);
+        }
+        CUDA_TRY(cudaGetLastError());
+        s->in_flight = 1;
+        s->iteration += A.n_iters;
+        s->suff_count += A.n_iters;
+        return RSFM_OK;
+    }
+    {
+        int rc = join_groups(s, stream);
+        if (rc) return rc;
+        s->need_fork = 1;                 // this launch writes the state on the caller's stream
+    }
     if (g >= 2) {
         const long long threads = (long long)C << g;
         const int sblock = threads <= 148 * 32 * 4 ? 32 : 128;
@@ -1337,6 +1451,7 @@ extern "C" int rsfm_get_state(rsfm_sampler *s, double *q_dev, double *sse_dev, d
 {
     if (!s) return set_err(RSFM_ERR_INVALID, "rsfm_get_state: NULL sampler%s", "");
     cudaStream_t st = (cudaStream_t)stream_;
+    { int rc_ = join_groups(s, st); if (rc_) return rc_; s->need_fork = 1; }      // chain groups meet the caller's stream
     const size_t C = s->C; const int d = s->cfg.n_params;
     if (q_dev) CUDA_TRY(cudaMemcpyAsync(q_dev, s->d.q, sizeof(double) * d * C, cudaMemcpyDeviceToDevice, st));
     if (sse_dev) CUDA_TRY(cudaMemcpyAsync(sse_dev, s->d.sse, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
@@ -1355,6 +1470,7 @@ extern "C" int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double
     if (!s) return set_err(RSFM_ERR_INVALID, "rsfm_set_state: NULL sampler%s", "");
     if (!s->initialised) return set_err(RSFM_ERR_STATE, "rsfm_set_state before rsfm_init (the data series lives in the sampler)%s", "");
     cudaStream_t st = (cudaStream_t)stream_;
+    { int rc_ = join_groups(s, st); if (rc_) return rc_; s->need_fork = 1; }      // chain groups meet the caller's stream
     const size_t C = s->C; const int d = s->cfg.n_params;
     if (q_dev) CUDA_TRY(cudaMemcpyAsync(s->d.q, q_dev, sizeof(double) * d * C, cudaMemcpyDeviceToDevice, st));
     if (sse_dev) CUDA_TRY(cudaMemcpyAsync(s->d.sse, sse_dev, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
@@ -1368,6 +1484,7 @@ static int ring_copy(rsfm_sampler *s, double *dst, const double *src, cudaStream
 {
     if (!s || !dst || !src) return set_err(RSFM_ERR_INVALID, "%s: NULL argument", who);
     if (s->cfg.adapt_mode != RSFM_ADAPT_COMPAT) return set_err(RSFM_ERR_INVALID, "%s: the sampler keeps a ring only with RSFM_ADAPT_COMPAT", who);
+    { int rc_ = join_groups(s, st); if (rc_) return rc_; s->need_fork = 1; }      // chain groups meet the caller's stream
     CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)s->cfg.adapt_interval * (size_t)s->C, cudaMemcpyDeviceToDevice, st));
     return RSFM_OK;
 }
@@ -1404,6 +1521,7 @@ extern "C" int rsfm_get_totals(rsfm_sampler *s, uint64_t *out_host, void *stream
 {
     if (!s || !out_host) return set_err(RSFM_ERR_INVALID, "rsfm_get_totals: NULL argument%s", "");
     cudaStream_t st = (cudaStream_t)stream_;
+    { int rc_ = join_groups(s, st); if (rc_) return rc_; s->need_fork = 1; }      // chain groups meet the caller's stream
     CUDA_TRY(cudaMemsetAsync(s->totals, 0, sizeof(unsigned long long) * 16, st));
     const int grid = (s->C + 255) / 256 < 592 ? (s->C + 255) / 256 : 592;
     totals_kernel<<<grid, 256, 0, st>>>(s->C, s->d, s->totals);
@@ -1440,6 +1558,7 @@ extern "C" int rsfm_get_suffstats(rsfm_sampler *s, double *out_dev, int32_t rese
 {
     if (!s || !out_dev) return set_err(RSFM_ERR_INVALID, "rsfm_get_suffstats: NULL argument%s", "");
     cudaStream_t st = (cudaStream_t)stream_;
+    { int rc_ = join_groups(s, st); if (rc_) return rc_; s->need_fork = 1; }      // chain groups meet the caller's stream
     const int d = s->cfg.n_params, rows = d + tri(d);
     const double n = (double)s->suff_count * (double)s->C;
     suffstats_kernel<<<rows, 1024, 0, st>>>(s->C, rows, n, s->d.suff, out_dev);
@@ -1462,6 +1581,7 @@ extern "C" int rsfm_set_proposal_chol(rsfm_sampler *s, const double *chol_host, 
 {
     if (!s || !chol_host) return set_err(RSFM_ERR_INVALID, "rsfm_set_proposal_chol: NULL argument%s", "");
     cudaStream_t st = (cudaStream_t)stream_;
+    { int rc_ = join_groups(s, st); if (rc_) return rc_; s->need_fork = 1; }      // chain groups meet the caller's stream
     const int T = tri(s->cfg.n_params);
     CUDA_TRY(cudaMemcpyAsync(s->reduce_out, chol_host, sizeof(double) * T, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -1478,16 +1598,18 @@ extern "C" int rsfm_set_proposal_chol(rsfm_sampler *s, const double *chol_host, 
 // order (shuffle tree inside a warp, then the 32 warp sums through the same tree), so a group's row is the same
 // bits on whichever rank, block or launch it is computed.
 __global__ void __launch_bounds__(RSFM_POOL_GROUP)
-pooled_partials_kernel(int C, int rows, unsigned long long id0, double iters, const double *__restrict__ suff,
-                       double *__restrict__ out)
+pooled_partials_kernel(int C, int rows, unsigned long long id0, double iters, double *__restrict__ suff,
+                       double *__restrict__ out, int block0, int reset)
 {
-    const unsigned long long gfirst = (id0 / RSFM_POOL_GROUP + blockIdx.x) * (unsigned long long)RSFM_POOL_GROUP;
+    const int blk = block0 + (int)blockIdx.x;                   // row of the output = 1,024-chain group of the GLOBAL numbering
+    const unsigned long long gfirst = (id0 / RSFM_POOL_GROUP + blk) * (unsigned long long)RSFM_POOL_GROUP;
     const long long c = (long long)(gfirst + threadIdx.x) - (long long)id0;
     const bool in = c >= 0 && c < (long long)C;
     __shared__ double ws[32];
-    double *o = out + (size_t)blockIdx.x * RSFM_POOL_ROWS;
+    double *o = out + (size_t)blk * RSFM_POOL_ROWS;
     for (int r = -1; r < rows; r++) {
         double v = in ? (r < 0 ? iters : suff[(size_t)r * C + c]) : 0.0;       // r = -1: the sample count
+        if (reset && in && r >= 0) suff[(size_t)r * C + c] = 0.0;
         for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(FULL_MASK, v, off);
         if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
         __syncthreads();
@@ -1513,13 +1635,24 @@ extern "C" int rsfm_pooled_partials(rsfm_sampler *s, double *out_dev, int32_t re
     if (!s || !out_dev) return set_err(RSFM_ERR_INVALID, "rsfm_pooled_partials: NULL argument%s", "");
     cudaStream_t st = (cudaStream_t)stream_;
     const int d = s->cfg.n_params, rows = d + tri(d);
-    pooled_partials_kernel<<<rsfm_pooled_groups(s), RSFM_POOL_GROUP, 0, st>>>(s->C, rows, s->chain_id0, (double)s->suff_count,
-                                                                              s->d.suff, out_dev);
-    CUDA_TRY(cudaGetLastError());
-    if (reset) {
-        CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * rows * (size_t)s->C, st));
-        s->suff_count = 0;
+    const int nrow = rsfm_pooled_groups(s);
+    if (s->n_groups > 1 && s->in_flight) {
+        // every group sums its own rows on its own stream, right behind its iterations; the caller's stream then waits
+        // for all of them: this is where the groups' work of the interval meets the caller's stream
+        const int per = nrow / s->n_groups;
+        for (int g = 0; g < s->n_groups; g++)
+            pooled_partials_kernel<<<per, RSFM_POOL_GROUP, 0, s->gstream[g]>>>(s->C, rows, s->chain_id0, (double)s->suff_count,
+                                                                               s->d.suff, out_dev, g * per, reset ? 1 : 0);
+        CUDA_TRY(cudaGetLastError());
+        int rc = join_groups(s, st);
+        if (rc) return rc;
+    } else {
+        pooled_partials_kernel<<<nrow, RSFM_POOL_GROUP, 0, st>>>(s->C, rows, s->chain_id0, (double)s->suff_count, s->d.suff,
+                                                                 out_dev, 0, reset ? 1 : 0);
+        CUDA_TRY(cudaGetLastError());
+        if (reset) s->need_fork = 1;
     }
+    if (reset) s->suff_count = 0;
     return RSFM_OK;
 }
 
@@ -1570,12 +1703,36 @@ __global__ void pooled_update_kernel(int d, int n_parts, const double *__restric
     fac[0] = 1.0;
 }
 
-__global__ void install_chol_kernel(int C, int T, const double *__restrict__ fac, double *__restrict__ chol)
+__global__ void install_chol_kernel(int C, int T, const double *__restrict__ fac, double *__restrict__ chol, int c0, int c1)
 {
     if (fac[0] == 0.0) return;                      // no valid factor: the proposal stays (cf. quirk q4)
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
     for (int j = 0; j < T; j++) chol[(size_t)j * C + c] = fac[1 + j];
+}
+
+// The factor in slot `slot` (formed behind fac_event[slot]) replaces every chain's proposal factor.  With chain groups
+// each group takes it over on its own stream, between two of its launches (the kernel keeps the factor in registers
+// and writes it back when it ends); the wait is for the event of the FORMING of the factor, not for the caller's
+// stream as it stands now, so a group is never held up by the other groups' running launches.
+static int install_factor(rsfm_sampler *s, int slot, cudaStream_t st)
+{
+    const int T = tri(s->cfg.n_params);
+    if (s->n_groups > 1) {
+        const int per = s->C / s->n_groups;
+        for (int g = 0; g < s->n_groups; g++) {
+            CUDA_TRY(cudaStreamWaitEvent(s->gstream[g], s->fac_event[slot], 0));
+            install_chol_kernel<<<(per + 255) / 256, 256, 0, s->gstream[g]>>>(s->C, T, s->fac_buf[slot], s->d.chol, g * per, (g + 1) * per);
+        }
+        CUDA_TRY(cudaGetLastError());
+        s->in_flight = 1;
+    } else {
+        CUDA_TRY(cudaStreamWaitEvent(st, s->fac_event[slot], 0));
+        install_chol_kernel<<<(s->C + 255) / 256, 256, 0, st>>>(s->C, T, s->fac_buf[slot], s->d.chol, 0, s->C);
+        CUDA_TRY(cudaGetLastError());
+        s->need_fork = 1;
+    }
+    return RSFM_OK;
 }
 
 extern "C" int rsfm_pooled_update(rsfm_sampler *s, const double *parts_dev, int32_t n_parts, double *moments_dev,
@@ -1585,15 +1742,28 @@ extern "C" int rsfm_pooled_update(rsfm_sampler *s, const double *parts_dev, int3
     if (parts_dev && n_parts < 0) return set_err(RSFM_ERR_INVALID, "rsfm_pooled_update: n_parts < 0%s", "");
     cudaStream_t st = (cudaStream_t)stream_;
     const int d = s->cfg.n_params, T = tri(d);
-    pooled_update_kernel<<<1, 32, 0, st>>>(d, n_parts, parts_dev, moments_dev, accumulate, install, s->reduce_out);
+    // (double-buffered: the install of a factor may still be queued behind a group's running launch, or not have
+    // been asked for yet, when the next factor is formed)
+    const int slot = s->fac_parity;
+    double *fac = s->fac_buf[slot];
+    s->fac_parity ^= 1;
+    pooled_update_kernel<<<1, 32, 0, st>>>(d, n_parts, parts_dev, moments_dev, accumulate, install, fac);
     CUDA_TRY(cudaGetLastError());
-    if (install) {
-        install_chol_kernel<<<(s->C + 255) / 256, 256, 0, st>>>(s->C, T, s->reduce_out, s->d.chol);
-        CUDA_TRY(cudaGetLastError());
-    }
+    CUDA_TRY(cudaEventRecord(s->fac_event[slot], st));
     if (factor_out_dev)
-        CUDA_TRY(cudaMemcpyAsync(factor_out_dev, s->reduce_out, sizeof(double) * (1 + T), cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(factor_out_dev, fac, sizeof(double) * (1 + T), cudaMemcpyDeviceToDevice, st));
+    if (install == 2) { s->staged = slot; return RSFM_OK; }       // formed now, installed by rsfm_pooled_install
+    if (install) return install_factor(s, slot, st);
     return RSFM_OK;
+}
+
+extern "C" int rsfm_pooled_install(rsfm_sampler *s, void *stream_)
+{
+    if (!s) return set_err(RSFM_ERR_INVALID, "rsfm_pooled_install: NULL sampler%s", "");
+    if (s->staged < 0) return RSFM_OK;                             // nothing staged: the proposal stays
+    const int slot = s->staged;
+    s->staged = -1;
+    return install_factor(s, slot, (cudaStream_t)stream_);
 }
 
 // ---------------------------------------------------------------------------

@@ -69,6 +69,7 @@ class RateStateModel:
         self.solver_variant = "auto"   # "default" / "stiff": force a kernel variant (tests, tuning)
         self.stiff_exact = False       # stiff variant: score every step that left the fast ranges
         self.block_threads = 0         # threads per block of the one-thread-per-chain kernels (0 = auto)
+        self.chain_groups = 0          # pooled adaptation: launches per interval on the sampler's own streams (0 auto, 1 off)
         self.rtol = 1e-6            # RateStateModel.py:374
         self.atol = 1e-10
         self.nmax = 500             # scipy dop853 nsteps default
@@ -96,6 +97,7 @@ class RateStateModel:
         cfg.solver_variant = _VARIANT[self.solver_variant]
         cfg.stiff_exact = 1 if self.stiff_exact else 0
         cfg.block_threads = int(self.block_threads)
+        cfg.chain_groups = int(getattr(self, "chain_groups", 0))
         cfg.state_law = _LAW[self.state_law]
         if self.loading == "table":
             # the table lives on the device next to the model (the library reads it through the pointer)

@@ -387,7 +387,7 @@ class MCMC:
             pipe.push([1 + pos, 1 + pos, pos])
         self._pooled_state = pool.finish()
         self.adapt_history = pool.history
-        self._pooled_stats = pool.stats
+        self._pooled_stats = dict(pool.stats, chain_groups=int(lib.rsfm_chain_groups(handle)))
 
     # ------------------------------------------------------------------
     def checkpoint(self, filename=None):

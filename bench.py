@@ -290,6 +290,7 @@ class Bench:
         # ---- synthetic data through the public forward model (GPU), same seed on every rank ----
         model = pkg.RateStateModel(number_time_steps=w["n_out"], end_time=w["t_end"])
         model.integ_mode = args.integ_mode
+        model.chain_groups = args.chain_groups
         model.a, model.b, model.Dc = w["truth"]
         if w["loading"] == "vstep":
             model.loading, model.vstep_period, model.vstep_factor = "vstep", 1000.0, 10.0
@@ -321,7 +322,7 @@ class Bench:
         samples = torch.empty((K * iters, d, cpg), dtype=torch.float64, device=dev)
         sigma2 = torch.empty((K * iters, cpg), dtype=torch.float64, device=dev)
         accept = torch.empty((K * iters, cpg), dtype=torch.uint8, device=dev)
-        launches = [0]
+        launches = [0, 0]                               # rsfm_run calls, adaptation intervals
 
         def run_iters(h, o, k):
             pkg._lib.check(lib.rsfm_run(h, k, pkg._lib.ptr(samples[o:]), pkg._lib.ptr(sigma2[o:]),
@@ -338,7 +339,7 @@ class Bench:
                 pool.before_interval()
                 run_iters(h, o + s0, k)
                 pool.after_interval(o + s0 + k)
-                launches[0] += 3                          # partial sums, moments / Cholesky, install
+                launches[1] += 1
 
         def totals(h):
             out = (C.c_uint64 * 9)()
@@ -351,13 +352,17 @@ class Bench:
             step(hw, pw, 0)
         if pw is not None:
             pw.finish()
+        if W > 0:
+            # the diagnostics kernels (and torch's reductions behind them) are part of the timed job: warm them too
+            importlib.import_module(PKG + ".diagnostics").chain_diagnostics(samples[:iters])
         torch.cuda.synchronize(dev)
         lib.rsfm_destroy(hw)
         # the timed job starts from the start values: K steps = the first K*iters iterations of every chain
         handle, pool = make_sampler()
         spec_g = int(lib.rsfm_spec_depth(handle))
+        n_groups = int(lib.rsfm_chain_groups(handle))
         tot0 = totals(handle)
-        launches[0] = 0
+        launches[0] = launches[1] = 0
         sampler = ClockSampler(self.local) if (clocks and rank == 0) else None
         if sampler:
             sampler.start()
@@ -367,6 +372,8 @@ class Bench:
         for i in range(K):
             self.flush.zero_()                          # L2 flush between timed steps (not timed)
             ev[i][0].record()
+            # chain groups (launches on the sampler's own streams): every group starts the step behind this point
+            pkg._lib.check(lib.rsfm_join(handle, stream), "rsfm_join")
             step(handle, pool, i)
             ev[i][1].record()
         # convergence diagnostics of the second half of the draws: per-chain moments / ESS on the device, the sums
@@ -388,7 +395,9 @@ class Bench:
         tot = totals(handle) - tot0                     # (solves, nrhs, nstep, accepted, failed, early, executed, urhs, ustep)
         acc_rate = float(accept.float().mean().item())
         lib.rsfm_destroy(handle)
-        n_launches = launches[0] + 3 * d                # + the diagnostics kernels
+        # kernels launched in the timed region: the MCMC kernel once per chain group and rsfm_run; per adaptation
+        # interval the partial sums (per group), moments / Cholesky (1) and install (per group); the diagnostics kernels
+        n_launches = launches[0] * n_groups + launches[1] * (2 * n_groups + 1) + 3 * d
 
         # ---- end-to-end arm: public API, host buffers in, host results out, every step ----
         e2e = None
@@ -455,6 +464,9 @@ class Bench:
             kernel = f"rsf_mcmc_spec_kernel<{d},false,{'true' if w['loading'] == 'vstep' else 'false'}> (speculation depth {spec_g}: {1 << spec_g} lanes per chain)"
         else:
             kernel = f"rsf_mcmc_kernel<{d},false,{'true' if w['loading'] == 'vstep' else 'false'}> (one thread per chain)"
+            if n_groups > 1:
+                kernel += (f"; each {per_launch_iters}-iteration launch is {n_groups} launches of {cpg // n_groups} chains on the "
+                           "sampler's own streams (chain groups), timed as one")
         tr = self.traffic.get(w["name"], {})
         traffic = tr.get("dram_bytes_per_launch") if (tr.get("chains_per_gpu") == cpg and tr.get("iters_per_launch") == per_launch_iters) else None
         rec = {
@@ -464,6 +476,7 @@ class Bench:
             "config": {"workload": w["text"] + f"; {iters} Metropolis iterations per step, {K} steps from the start values",
                        "name": w["name"], "chains_per_gpu": cpg, "chains_total": total_chains, "iters_per_step": iters,
                        "n_out": w["n_out"], "n_params": d, "integ_mode": args.integ_mode, "speculation_depth": spec_g,
+                       "chain_groups": n_groups,
                        "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": (f"chains sharded over {world} GPU(s); one NCCL all-gather of the pooled partial sums per "
                                        f"{interval} iterations on a side stream (overlapped with the next kernel, adaptation lags one "
@@ -573,6 +586,9 @@ def main():
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0 = the workload's own)")
     ap.add_argument("--iters", type=int, default=0, help="Metropolis iterations per step (0 = the workload's own)")
     ap.add_argument("--integ-mode", choices=["parity", "carry"], default="parity")
+    ap.add_argument("--chain-groups", type=int, default=0,
+                    help="pooled adaptation: launches per interval on the sampler's own streams (0 auto, 1 off); "
+                         "never affects results")
     ap.add_argument("--seed", type=int, default=20240)
     ap.add_argument("--e2e-steps", type=int, default=2, help="timed public-API calls (each = the whole job)")
     ap.add_argument("--cpu-iters", type=int, default=12, help="iterations per chain in the cpu_baseline sample")

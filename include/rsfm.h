@@ -32,6 +32,7 @@ extern "C" {
 
 #define RSFM_ABI_VERSION 3
 #define RSFM_MAX_PARAMS 3
+#define RSFM_MAX_GROUPS 4
 
 typedef enum {
     RSFM_OK = 0,
@@ -109,6 +110,10 @@ typedef struct rsfm_cfg {
                                             general-range stages instead of taking exploding trial steps as rejected */
     int32_t block_threads;               /* threads per block of the one-thread-per-chain kernels: 0 auto, or
                                             32 / 64 / 96 / 128 (tuning; results never depend on it) */
+    int32_t chain_groups;                /* RSFM_ADAPT_POOLED only: serve the chains by this many launches on the
+                                            sampler's own streams (0 auto: up to 4 when >= 8,192 chains each, group
+                                            boundaries on multiples of RSFM_POOL_GROUP; 1 off); see rsfm_join.
+                                            Results never depend on it */
     int32_t state_law;                   /* RSFM_LAW_* */
     int32_t n_load_table;                /* RSFM_LOAD_TABLE: entries (>= 2), spacing and DEVICE pointer of the table; */
     double  load_dt;                     /*   read by every call that gets this cfg and by rsfm_init, which tabulates */
@@ -169,6 +174,18 @@ int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *data_dev, voi
 int rsfm_run(rsfm_sampler *s, int32_t n_iters,
              double *samples_out_dev, double *sigma2_out_dev, uint8_t *accept_out_dev,
              double *draws_out_dev, void *stream);
+
+/* Chain groups (RSFM_ADAPT_POOLED, large batches).  A launch of rsfm_run there is one adaptation interval long,
+ * and the last, partly empty wave of its blocks would leave most SMs idle (1.15 waves at 65,536 chains: 18 % of the
+ * launch).  The sampler therefore serves its chains in rsfm_chain_groups(s) groups, each by its own launch on a
+ * stream the sampler owns; groups have no barrier in common, so one group's tail overlaps the others' next
+ * launches.  ORDERING: with more than one group, the effects of rsfm_run (state and output buffers) are ordered on
+ * the caller's `stream` only behind the next call on the same sampler that reads them back -- rsfm_pooled_partials
+ * (the pooled-adaptation pipeline calls it after every rsfm_run), every rsfm_get_* / rsfm_set_*, rsfm_run_deterministic
+ * -- or an explicit rsfm_join(s, stream).  rsfm_join also makes the groups' next launches wait for the work queued
+ * on `stream` so far (a full meeting point, e.g. around a timed region).  No reference counterpart. */
+int rsfm_chain_groups(const rsfm_sampler *s);
+int rsfm_join(rsfm_sampler *s, void *stream);
 
 /* Depth g of the speculation tree rsfm_run will use for this sampler (0 = plain
  * one-thread-per-chain kernel; g >= 2: 2^g lanes per chain evaluate the next g
@@ -235,10 +252,15 @@ int rsfm_pooled_partials(rsfm_sampler *s, double *out_dev, int32_t reset, void *
  *   when install != 0: V = (2.38^2/d) cov(moments) (ddof 1) (1 + 1e-10 on the diagonal), closed-form Cholesky
  *       (d <= 3); if V is finite and positive definite the common factor replaces every chain's proposal
  *       factor (d = 1: the proposal VARIANCE, as the reference stores it), otherwise the proposal stays (q4).
- *   factor_out_dev (optional) [1 + d(d+1)/2] receives (installed ? 1 : 0, factor).
+ *       install == 2 only FORMS the factor; a later rsfm_pooled_install(s, stream) puts it in place.  The pipeline
+ *       of adaptation.PooledAdaptation forms the factor of interval j - 1 before it launches interval j and installs
+ *       it before interval j + 1: with chain groups (rsfm_chain_groups) the install then waits for the forming of
+ *       the factor only, never for the other groups' running launches.
+ *   factor_out_dev (optional) [1 + d(d+1)/2] receives (valid ? 1 : 0, factor).
  * Stream-ordered, no synchronisation; every rank computes the same factor from the same moments. */
 int rsfm_pooled_update(rsfm_sampler *s, const double *parts_dev, int32_t n_parts, double *moments_dev,
                        int32_t accumulate, int32_t install, double *factor_out_dev, void *stream);
+int rsfm_pooled_install(rsfm_sampler *s, void *stream);
 
 /* Diagnostics over a samples buffer [n][d][C] (device): per-chain mean, variance
  * (ddof 1) and autocovariance-based effective sample size (Geyer initial positive

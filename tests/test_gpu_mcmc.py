@@ -794,3 +794,35 @@ def test_slip_law_and_tabulated_load_chains_replay_through_oracle(cuda, pkg, orc
         assert np.array_equal(acc[:, ch], acc_o), ch
         assert np.array_equal(samples[:, 0, ch], chain_o[1:]), ch
         assert np.allclose(s2[:, ch], s2_o[1:], rtol=1e-8, atol=0)
+
+
+@pytest.mark.parametrize("d", [1, 3])
+def test_chain_groups_give_the_same_chains(cuda, pkg, d):
+    """Pooled adaptation with the chains served by four launches on the sampler's own streams (rsfm_chain_groups,
+    include/rsfm.h) against one launch: the same samples, sigma^2, accept flags and pooled factors, bit for bit --
+    also when the shard does not start at chain 0 and through a checkpoint taken while the groups are in flight."""
+    rng = np.random.default_rng(8)
+    g = load_golden("sse_grid.json")
+    c, ns = 32768, 50
+    kw = dict(nsamples=ns, n_chains=c, seed=9, chain_id0=3 * 1024, verbose=False, adapt="pooled", adapt_start=20)
+    if d == 1:
+        q0 = rng.uniform(900.0, 2000.0, c)
+    else:
+        q0 = np.stack([rng.uniform(0.0105, 0.0115, c), rng.uniform(0.0135, 0.0145, c), rng.uniform(1000.0, 1800.0, c)], axis=1)
+        kw.update(param_names=("a", "b", "Dc"), bounds=[[0.0100, 0.0120], [0.0130, 0.0150], [800.0, 2200.0]])
+    res = {}
+    for groups in (1, 0):
+        m = pkg.RateStateModel()
+        m.chain_groups = groups
+        mc = pkg.MCMC(m, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, **kw)
+        out = mc.sample(False)
+        res[groups] = (np.array(out), np.array(mc.std2), np.array(mc.accepts),
+                       [(int(e), [float(x) for x in f]) for e, f in mc.adapt_history], dict(mc.stats), mc.checkpoint())
+    assert res[0][4].get("chain_groups") == 4 and res[1][4].get("chain_groups") == 1
+    assert len(res[1][3]) >= 2 and res[0][3] == res[1][3]
+    for i in range(3):
+        assert np.array_equal(res[0][i], res[1][i]), i
+    for k in ("nsolves", "nrhs", "nstep", "nsolves_stopped_early"):
+        assert res[0][4][k] == res[1][4][k], k
+    for k in ("q", "sse", "sigma2", "chol"):
+        assert np.array_equal(np.asarray(res[0][5][k]), np.asarray(res[1][5][k])), k

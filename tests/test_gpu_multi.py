@@ -60,7 +60,7 @@ def test_one_and_two_ranks_give_identical_chains_and_pooled_statistics(cuda, pkg
     g = load_golden("sse_grid.json")
     np.save(tmp_path / "data.npy", g["data"])
     rng = np.random.default_rng(0)
-    c = 4096
+    c = 32768            # 16,384 per rank: the pooled cases run with chain groups (2 per rank, 4 on the single GPU)
     cases = {
         "dc_fixed": dict(nsamples=24, n_chains=c, seed=5, param_names=["Dc"]),
         "dc_pooled": dict(nsamples=60, n_chains=c, seed=5, param_names=["Dc"], adapt="pooled", adapt_start=20),
@@ -92,6 +92,7 @@ def test_one_and_two_ranks_give_identical_chains_and_pooled_statistics(cuda, pkg
             hist = [[int(e)] + [float(x) for x in f] for e, f in mc.adapt_history]
             assert len(hist) >= 3 and all(m["hist"] == hist for m in meta), name    # identical pooled factors
             assert all(m["stats"]["pool_rows_gathered"] == world * (c // world // 1024) for m in meta)
+            assert all(m["stats"]["chain_groups"] == 2 for m in meta) and mc.stats["chain_groups"] == 4
         for m in meta:                                                              # R-hat / ESS sums all-reduced
             assert np.allclose(m["rhat"], diag["rhat"], rtol=1e-10) and np.allclose(m["ess"], diag["ess"], rtol=1e-10)
             assert np.allclose(m["mean"], diag["mean"], rtol=1e-12)
