@@ -373,8 +373,9 @@ __device__ __forceinline__ void rsf_rhs(const ChainConst &c, double L, double mu
         const double temp = c.inv_a * fma(-c.b, log(x), dmu0);
         const double ev = exp(temp);                                // v / V_ref
         r = 1.0 / th;
-        dth = 1.0 - ev * x;
-        if (c.slip) { const double z = ev * x; dth = -z * log(z); }      // Ruina slip law
+        dth = fma(-ev, x, 1.0);                                      // (one rounding, as the compiler contracted it before
+                                                                     //  the slip law shared the product below)
+        if (c.slip) { const double z = __dmul_rn(ev, x); dth = -z * log(z); }      // Ruina slip law
         const double voa_g = c.voa0 * ev;
         const double d0_g = c.kV * ((L + 1.0) - ev);
         const double s_g = (c.b * r) * dth;

@@ -355,7 +355,9 @@ class Bench:
             pw.finish()
         if W > 0:
             # the diagnostics kernels (and torch's reductions behind them) are part of the timed job: warm them too
-            importlib.import_module(PKG + ".diagnostics").chain_diagnostics(samples[:iters])
+            if samples.shape[0] >= 4:
+                samples[iters:max(iters, 4)].zero_()
+                importlib.import_module(PKG + ".diagnostics").chain_diagnostics(samples[:max(iters, 4)])
         torch.cuda.synchronize(dev)
         lib.rsfm_destroy(hw)
         # the timed job starts from the start values: K steps = the first K*iters iterations of every chain

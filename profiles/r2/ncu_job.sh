@@ -1,7 +1,7 @@
 # ncu evidence of round 2 (run on the GPU box through gpurun; every command only after bench.py ran clean without ncu)
 set -x
 mkdir -p gpurun_out/ncu
-B="python bench.py --no-cpu-baseline --e2e-steps 1"
+B="python bench.py --no-cpu-baseline --e2e-steps 1 --chain-groups 1"   # (one launch per interval: ncu serialises kernels anyway)
 export_rep() {   # the .ncu-rep with imported source is 25 MB: export what is read, drop the report
   ncu -i gpurun_out/ncu/$1.ncu-rep --page raw --csv > gpurun_out/ncu/$1_raw.csv 2>/dev/null
   ncu -i gpurun_out/ncu/$1.ncu-rep --page details --csv > gpurun_out/ncu/$1_details.csv 2>/dev/null

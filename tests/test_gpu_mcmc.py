@@ -826,3 +826,42 @@ def test_chain_groups_give_the_same_chains(cuda, pkg, d):
         assert res[0][4][k] == res[1][4][k], k
     for k in ("q", "sse", "sigma2", "chol"):
         assert np.array_equal(np.asarray(res[0][5][k]), np.asarray(res[1][5][k])), k
+
+
+def test_rsfm_join_orders_the_callers_stream_behind_the_chain_groups(cuda, pkg):
+    """C-ABI contract of the chain groups (include/rsfm.h): with more than one group rsfm_run works on the sampler's
+    own streams; rsfm_join (and every getter) orders the caller's stream behind it.  Outputs read behind the join
+    equal those of the single-launch sampler, on the default stream and on a side stream."""
+    import ctypes as C
+    torch = cuda
+    lib = pkg._lib.load()
+    g = load_golden("sse_grid.json")
+    data_t = torch.from_numpy(np.ascontiguousarray(g["data"])).cuda()
+    c, ns = 16384, 10
+    q0 = torch.from_numpy(np.random.default_rng(4).uniform(900.0, 2000.0, (1, c))).cuda()
+    outs = {}
+    for groups, use_side in ((1, False), (2, False), (2, True)):
+        cfg = pkg.RateStateModel().to_cfg()
+        cfg.adapt_mode, cfg.chain_groups = pkg._lib.ADAPT_POOLED, groups
+        st = torch.cuda.Stream() if use_side else torch.cuda.current_stream()
+        with torch.cuda.stream(st):
+            h = lib.rsfm_create(C.byref(cfg), c, 3, 0)
+            assert h and lib.rsfm_chain_groups(h) == groups
+            try:
+                sp = st.cuda_stream
+                pkg._lib.check(lib.rsfm_init(h, q0.data_ptr(), data_t.data_ptr(), sp))
+                samples = torch.zeros((2 * ns, 1, c), dtype=torch.float64, device="cuda")
+                acc = torch.zeros((2 * ns, c), dtype=torch.uint8, device="cuda")
+                for part in range(2):
+                    pkg._lib.check(lib.rsfm_run(h, ns, samples[part * ns:].data_ptr(), None, acc[part * ns:].data_ptr(), None, sp))
+                pkg._lib.check(lib.rsfm_join(h, sp))
+                host = samples.to("cpu", non_blocking=False)             # stream-ordered copy behind the join
+                tot = (C.c_uint64 * 9)()
+                pkg._lib.check(lib.rsfm_get_totals(h, tot, sp))
+                outs[(groups, use_side)] = (host.numpy().copy(), acc.cpu().numpy().copy(), list(tot))
+            finally:
+                lib.rsfm_destroy(h)
+    ref = outs[(1, False)]
+    assert 0 < ref[1].mean() < 1
+    for key in ((2, False), (2, True)):
+        assert np.array_equal(outs[key][0], ref[0]) and np.array_equal(outs[key][1], ref[1]) and outs[key][2] == ref[2], key
