@@ -1,7 +1,8 @@
 # ncu evidence of round 2 (run on the GPU box through gpurun; every command only after bench.py ran clean without ncu)
 set -x
 mkdir -p gpurun_out/ncu
-B="python bench.py --no-cpu-baseline --e2e-steps 1 --chain-groups 1"   # (one launch per interval: ncu serialises kernels anyway)
+B0="python bench.py --no-cpu-baseline --e2e-steps 1"                    # launch lists: the bench as it runs (chain groups on)
+B="$B0 --chain-groups 1"       # full captures: one launch per adaptation interval (ncu serialises kernels anyway)
 export_rep() {   # the .ncu-rep with imported source is 25 MB: export what is read, drop the report
   ncu -i gpurun_out/ncu/$1.ncu-rep --page raw --csv > gpurun_out/ncu/$1_raw.csv 2>/dev/null
   ncu -i gpurun_out/ncu/$1.ncu-rep --page details --csv > gpurun_out/ncu/$1_details.csv 2>/dev/null
@@ -12,7 +13,7 @@ export_rep() {   # the .ncu-rep with imported source is 25 MB: export what is re
 }
 if [ "$1" != "full-only" ]; then
 for w in cfg3 cfg2 cfg5 cfg4r; do
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/ncu/launches_$w.csv $B --workload $w --steps 1 --warmup 3 > gpurun_out/ncu/launches_$w.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/ncu/launches_$w.csv $B0 --workload $w --steps 1 --warmup 3 > gpurun_out/ncu/launches_$w.log 2>&1
 done
 fi
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:rsf_mcmc_spec_kernel -s 2 -c 1 -f -o gpurun_out/ncu/r2_cfg2_spec $B --workload cfg2 --steps 1 --warmup 3 > gpurun_out/ncu/full_cfg2.log 2>&1
