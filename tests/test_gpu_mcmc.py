@@ -463,7 +463,7 @@ def _run_with_draws(torch, pkg, cfg, c, seed, id0, q0, data, ns_list):
     import ctypes as C
     lib = pkg._lib.load()
     d = cfg.n_params
-    q0_t = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(q0, dtype=np.float64).reshape(d, -1), (d, c)))).cuda()
+    q0_t = torch.from_numpy(np.broadcast_to(np.asarray(q0, dtype=np.float64).reshape(d, -1), (d, c)).copy()).cuda()
     data_t = torch.from_numpy(np.ascontiguousarray(data)).cuda()
     h = lib.rsfm_create(C.byref(cfg), c, seed, id0)
     assert h, lib.rsfm_last_error()
@@ -865,3 +865,36 @@ def test_rsfm_join_orders_the_callers_stream_behind_the_chain_groups(cuda, pkg):
     assert 0 < ref[1].mean() < 1
     for key in ((2, False), (2, True)):
         assert np.array_equal(outs[key][0], ref[0]) and np.array_equal(outs[key][1], ref[1]) and outs[key][2] == ref[2], key
+
+
+@pytest.mark.parametrize("n, ns, c", [(2, 1, 1), (3, 2, 3), (5, 4, 33), (16, 6, 1)])
+def test_smallest_grids_and_runs(cuda, pkg, orc, n, ns, c):
+    """Edge sizes: a series of 2 .. 16 output points (one output interval at the least), one or two iterations
+    (nburn = int(nsamples / 2) = 0), one chain or a ragged warp -- forward solve and chains against the oracle."""
+    torch = cuda
+    t_end = 0.1 * n
+    om = orc.make_model(Dc=1325.0, number_time_steps=n, end_time=t_end)
+    rng = np.random.default_rng(n)
+    truth = orc.forward(om)[1]
+    assert truth.size == n
+    data = truth + (np.abs(truth) + 1e-4) * rng.standard_normal(n)
+    m = pkg.RateStateModel(number_time_steps=n, end_time=t_end)
+    out = m.evaluate_batch(np.array([300.0, 1325.0, 9000.0]), data=data)
+    for i, dc in enumerate((300.0, 1325.0, 9000.0)):
+        acc_o = orc.forward(orc.make_model(Dc=dc, number_time_steps=n, end_time=t_end))[1]
+        assert np.max(np.abs(out["acc"][:, i].cpu().numpy() - acc_o)) <= 1e-9 * max(np.max(np.abs(acc_o)), 1e-30) + 1e-14
+        assert out["sse"][i].item() == pytest.approx(float(np.sum((acc_o - data) ** 2)), rel=1e-9)
+    cfg = m.to_cfg()
+    cfg.n_params, cfg.n_prior_len = 1, 3
+    cfg.lo[0], cfg.hi[0] = 0.0, 1e4
+    if n <= 3:
+        return                     # N - len(qpriors) <= 0: sigma^2_0 is not positive, in the reference as here
+    samples, s2, acc, draws, depth, tot = _run_with_draws(torch, pkg, cfg, c, 5, 0, [1100.0], data, [ns])
+    for ch in sorted({0, c - 1}):
+        chain_o, s2_o, acc_o, _, _ = orc.chain_replay(om, data, 1100.0, 0.0, 1e4, 3, ns, draws[:, 0, ch],
+                                                      np.nan_to_num(draws[:, 1, ch], nan=0.5), draws[:, 2, ch])
+        assert np.array_equal(acc[:, ch], acc_o) and np.array_equal(samples[:, 0, ch], chain_o[1:])
+        assert np.allclose(s2[:, ch], s2_o[1:], rtol=1e-8, atol=0)
+    mc = pkg.MCMC(m, data, 1325.0, ["Uniform", 0.0, 1e4], 1100.0, nsamples=ns, verbose=False, seed=5)
+    res = mc.sample(False)
+    assert res.shape == (1, ns + 1 - int(ns / 2)) and mc.std2.shape == (ns + 1 - int(ns / 2),)
