@@ -50,7 +50,7 @@ class RsfmCfg(C.Structure):
         ("n_prior_len", C.c_int32), ("adapt_interval", C.c_int32), ("adapt_mode", C.c_int32),
         ("spec_depth", C.c_int32),
         ("observable", C.c_int32), ("solver_variant", C.c_int32), ("stiff_exact", C.c_int32),
-        ("block_threads", C.c_int32), ("chain_groups", C.c_int32),
+        ("block_threads", C.c_int32), ("chain_groups", C.c_int32), ("round_packing", C.c_int32),
         ("state_law", C.c_int32), ("n_load_table", C.c_int32), ("load_dt", C.c_double), ("load_table_dev", C.c_void_p),
     ]
 

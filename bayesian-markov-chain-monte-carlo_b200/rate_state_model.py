@@ -70,6 +70,7 @@ class RateStateModel:
         self.stiff_exact = False       # stiff variant: score every step that left the fast ranges
         self.block_threads = 0         # threads per block of the one-thread-per-chain kernels (0 = auto)
         self.chain_groups = 0          # pooled adaptation: launches per interval on the sampler's own streams (0 auto, 1 off)
+        self.round_packing = 0         # d = 3: in-bounds proposals of a block packed at every solve round (0 auto, 1 off)
         self.rtol = 1e-6            # RateStateModel.py:374
         self.atol = 1e-10
         self.nmax = 500             # scipy dop853 nsteps default
@@ -98,6 +99,7 @@ class RateStateModel:
         cfg.stiff_exact = 1 if self.stiff_exact else 0
         cfg.block_threads = int(self.block_threads)
         cfg.chain_groups = int(getattr(self, "chain_groups", 0))
+        cfg.round_packing = int(getattr(self, "round_packing", 0))
         cfg.state_law = _LAW[self.state_law]
         if self.loading == "table":
             # the table lives on the device next to the model (the library reads it through the pointer)

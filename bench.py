@@ -292,6 +292,7 @@ class Bench:
         model.integ_mode = args.integ_mode
         model.chain_groups = args.chain_groups
         model.block_threads = args.block_threads
+        model.round_packing = args.round_packing
         model.a, model.b, model.Dc = w["truth"]
         if w["loading"] == "vstep":
             model.loading, model.vstep_period, model.vstep_factor = "vstep", 1000.0, 10.0
@@ -592,6 +593,7 @@ def main():
     ap.add_argument("--chain-groups", type=int, default=0,
                     help="pooled adaptation: launches per interval on the sampler's own streams (0 auto, 1 off); "
                          "never affects results")
+    ap.add_argument("--round-packing", type=int, default=0, help="d = 3 kernel: 0 auto (on), 1 off; never affects results")
     ap.add_argument("--block-threads", type=int, default=0, help="threads per block of the one-thread-per-chain kernels (0 auto)")
     ap.add_argument("--seed", type=int, default=20240)
     ap.add_argument("--e2e-steps", type=int, default=2, help="timed public-API calls (each = the whole job)")

@@ -114,6 +114,10 @@ typedef struct rsfm_cfg {
                                             sampler's own streams (0 auto: up to 4 when >= 8,192 chains each, group
                                             boundaries on multiples of RSFM_POOL_GROUP; 1 off); see rsfm_join.
                                             Results never depend on it */
+    int32_t round_packing;               /* d = 3 one-thread-per-chain kernel: pack the in-bounds proposals of a block into
+                                            its lowest threads at the start of every solve round (0 auto = on for
+                                            128-thread blocks and a series of <= 1,024 points, 1 off); results never
+                                            depend on it */
     int32_t state_law;                   /* RSFM_LAW_* */
     int32_t n_load_table;                /* RSFM_LOAD_TABLE: entries (>= 2), spacing and DEVICE pointer of the table; */
     double  load_dt;                     /*   read by every call that gets this cfg and by rsfm_init, which tabulates */

@@ -89,7 +89,7 @@ def test_cfg_validation_needs_no_device(built_lib, pkg):
                      ({"rtol": 0.0}, "rtol"), ({"n_params": 2}, "n_params"), ({"loading": 7}, "loading"),
                      ({"adapt_interval": 1, "adapt_mode": pkg._lib.ADAPT_COMPAT}, "adapt_interval"),
                      ({"observable": 5}, "observable"), ({"solver_variant": 9}, "solver_variant"),
-                     ({"state_law": 3}, "state_law"), ({"loading": 2}, "RSFM_LOAD_TABLE"),
+                     ({"state_law": 3}, "state_law"), ({"round_packing": 2}, "round_packing"), ({"chain_groups": 9}, "chain_groups"), ({"loading": 2}, "RSFM_LOAD_TABLE"),
                      ({"block_threads": 48}, "block_threads"), ({"spec_depth": 6}, "spec_depth"),
                      ({"delta_t": 0.0}, "grid"), ({"a": -1.0}, "positive")):
         rc, msg = refused(**kw)

@@ -898,3 +898,41 @@ def test_smallest_grids_and_runs(cuda, pkg, orc, n, ns, c):
     mc = pkg.MCMC(m, data, 1325.0, ["Uniform", 0.0, 1e4], 1100.0, nsamples=ns, verbose=False, seed=5)
     res = mc.sample(False)
     assert res.shape == (1, ns + 1 - int(ns / 2)) and mc.std2.shape == (ns + 1 - int(ns / 2),)
+
+
+def test_round_packing_gives_the_same_chains(cuda, pkg, orc):
+    """d = 3, a batch large enough for 128-thread blocks: with the in-bounds proposals of a block packed into its
+    lowest threads at every solve round (rsf_mcmc_kernel<3, .., PACK>) and without -- the same samples, sigma^2,
+    accept flags and work totals, bit for bit, on a ragged chain count with half of the proposals out of bounds; and
+    a few chains of the packed run replayed on the oracle step for step."""
+    torch = cuda
+    rng = np.random.default_rng(31)
+    om = orc.make_model(Dc=1325.0)
+    truth = orc.forward(om)[1]
+    data = truth + np.abs(truth) * rng.standard_normal(truth.size)
+    c, ns = 19000 + 37, 20
+    q0 = np.array([0.011, 0.014, 1300.0])
+    width = np.array([0.0012, 0.0012, 400.0])
+    lo = q0 - width / 40.0
+    hi = lo + width
+    res = {}
+    for packing in (1, 0):
+        m = pkg.RateStateModel()
+        m.round_packing = packing
+        cfg = m.to_cfg()
+        cfg.n_params, cfg.n_prior_len, cfg.spec_depth = 3, 3, 1
+        for j in range(3):
+            cfg.lo[j], cfg.hi[j] = lo[j], hi[j]
+        res[packing] = _run_with_draws(torch, pkg, cfg, c, 77, 2048, q0, data, [12, 8])
+    for i in range(4):
+        assert np.array_equal(res[0][i], res[1][i], equal_nan=True), i
+    assert res[0][5] == res[1][5]                                   # work totals (solves, RHS, steps, early stops ...)
+    samples, s2, acc, draws = res[0][:4]
+    oob = np.isnan(draws[:, 3])
+    assert 0.15 < oob.mean() < 0.9 and 0 < acc.mean() < 1
+    for ch in (0, 127, 128, 9000, c - 1):
+        chain_o, s2_o, acc_o, _ = orc.chain_replay_nd(om, data, q0, lo, hi, 3, ns, draws[:, :3, ch],
+                                                      np.nan_to_num(draws[:, 3, ch], nan=0.5), draws[:, 4, ch])
+        assert np.array_equal(acc[:, ch], acc_o), ch
+        assert np.array_equal(samples[:, :, ch], chain_o[1:]), ch
+        assert np.allclose(s2[:, ch], s2_o[1:], rtol=1e-8, atol=0)
