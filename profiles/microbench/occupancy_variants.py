@@ -21,7 +21,6 @@ block = int(sys.argv[2])
 names = sys.argv[3].split(",") if len(sys.argv) > 3 else ["cfg3", "cfg5"]
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 100
 spec = int(sys.argv[5]) if len(sys.argv) > 5 else 0
-compaction = sys.argv[6] if len(sys.argv) > 6 else "auto"
 for name in names:
     w = dict(bench.WORKLOADS[name]); w["name"] = name
     d, cpg = w["d"], w["chains"]
@@ -31,7 +30,6 @@ for name in names:
     data = model.evaluate()[2]
     model.a, model.b = 0.011, 0.014
     model.block_threads = block
-    model.compaction = compaction
     cfg = model.to_cfg()
     cfg.n_params, cfg.n_prior_len, cfg.spec_depth = d, 3, spec
     per = 200 if name == "cfg2" else 10
@@ -53,7 +51,7 @@ for name in names:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / max(1, iters // per)
-    print(f"{os.path.basename(sys.argv[1])} block={block} {name} compaction={compaction} spec={spec} (depth {lib.rsfm_spec_depth(h)}): {ms:.2f} ms per {per}-iteration launch "
+    print(f"{os.path.basename(sys.argv[1])} block={block} {name} spec={spec} (depth {lib.rsfm_spec_depth(h)}): {ms:.2f} ms per {per}-iteration launch "
           f"(checksum {float(samples.sum()):.12e})", flush=True)
     tot = (C.c_uint64 * 9)()
     lib.rsfm_get_totals(h, tot, None)

@@ -1,6 +1,15 @@
 """Which steps does the stiff variant's 'presumed wild' rule (rsfm_device.cuh, rsf_interval_general) cover that the
 exact arithmetic accepts?  Debug build only (-DRSFM_DEBUG_COUNT -> librsfm_dbg.so): in stiff_exact mode every step
-that starts inside half the fast ranges, leaves them at a stage and is ACCEPTED by the general-range stages is recorded."""
+that starts inside half the fast ranges, leaves them at a stage and is ACCEPTED by the general-range stages is recorded.
+
+Build of the counting library (next to the product's, never loaded by it):
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared -DRSFM_DEBUG_COUNT \
+         -I include -I bayesian-markov-chain-monte-carlo_b200/csrc \
+         -o bayesian-markov-chain-monte-carlo_b200/librsfm_dbg.so bayesian-markov-chain-monte-carlo_b200/csrc/rsfm_kernels.cu
+Round-2 result (before the rule got its load condition): one such step per velocity jump -- the first step behind a
+jump that the accumulated output times put a few ulp inside an interval whose frame is the old level (t = 90.000132,
+h = 6.5e-4, err = 4.6e-13 at Dc = 2) -- and 1.3e-6 of the trajectory between the rule and the exact arithmetic; with
+the load condition the two give the same bits (tests/test_gpu_forward.py::test_stiff_rule_changes_no_decision)."""
 import ctypes as C, importlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
