@@ -2,7 +2,7 @@
 
 65,536 chains (cfg 3) are 2,048 warps and 131,072 (cfg 5) are 4,096; at 168 registers 12 warps fit an SM = 1,776 on
 148 SMs, i.e. 1.15 and 2.31 waves: the last, nearly empty wave runs latency-bound and costs almost a full one.
-Builds capped at 128 registers (-DRSFM_MCMC_LB_T=64 -DRSFM_MCMC_LB_B=7/8) hold 16 warps per SM = 2,368: 0.86 and
+Builds capped at 128 registers (`__launch_bounds__(64, 7)` on rsf_mcmc_kernel, an experiment build) hold 16 warps per SM = 2,368: 0.86 and
 1.73 waves.  This script times rsfm_run for both shapes with a given library and block size.
 
 usage: python profiles/microbench/occupancy_variants.py <lib.so> <block_threads> [cfg3,cfg5,cfg2] [iters] [spec_depth]"""
