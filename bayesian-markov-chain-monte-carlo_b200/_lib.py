@@ -20,7 +20,8 @@ CHAIN_OK, CHAIN_NMAX, CHAIN_HSMALL, CHAIN_NONFINITE = 0, 2, 3, 4
 OBS_ACC, OBS_MU = 0, 1
 VARIANT_AUTO, VARIANT_DEFAULT, VARIANT_STIFF = 0, 1, 2
 POOL_GROUP, POOL_ROWS = 1024, 16
-ABI_VERSION = 3
+PARAM_DC, PARAM_K1 = 0, 1
+ABI_VERSION = 4
 
 # every symbol include/rsfm.h declares (tests check the library exports them all)
 EXPORTED_SYMBOLS = (
@@ -52,6 +53,7 @@ class RsfmCfg(C.Structure):
         ("observable", C.c_int32), ("solver_variant", C.c_int32), ("stiff_exact", C.c_int32),
         ("block_threads", C.c_int32), ("chain_groups", C.c_int32), ("round_packing", C.c_int32),
         ("state_law", C.c_int32), ("n_load_table", C.c_int32), ("load_dt", C.c_double), ("load_table_dev", C.c_void_p),
+        ("sampled_param", C.c_int32), ("dc_fixed", C.c_double),
     ]
 
 

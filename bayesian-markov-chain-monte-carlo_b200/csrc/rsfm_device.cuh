@@ -51,6 +51,7 @@ struct ModelK {
     int load_n;                        // RSFM_LOAD_TABLE: entries of load_tab
     double load_dt;                    //   spacing of the table (first entry at t_start)
     const double *load_tab;            //   device pointer, V_l/V_ref - 1
+    double dc_fixed;                   // RSFM_PARAM_K1: the per-chain scalar is k1 and Dc is this constant
 };
 
 // ---------------------------------------------------------------------------
@@ -1239,7 +1240,10 @@ __device__ __noinline__ void rsf_interval_plain(const ModelK *Mp, const ChainCon
 // first); the lane stops integrating there (`out.status |= RSFM_CHAIN_EARLY`, sse = partial > limit).
 // The accept/reject decision is exactly the one the full solve would give.  A warp leaves the
 // output loop when all its lanes are finished (resident series only: no block barriers pending).
-template <bool PARITY, bool VS, bool ISO>
+// K1P (RSFM_PARAM_K1, extension): the per-chain scalar passed as `dc` is the radiation-damping coefficient k1
+// (RateStateModel.py:171, 349-353) and Dc is the model's constant M.dc_fixed -- separate instantiations, so that k1
+// stays a kernel-uniform constant of the fast-interval block everywhere else.
+template <bool PARITY, bool VS, bool ISO, bool K1P = false>
 __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, double b, double dc, bool active,
                                                     SeriesStage &series, const LoadScratch &ls, double *acc_out,
                                                     const double *acc_ref, size_t acc_stride, double fd_den,
@@ -1249,7 +1253,21 @@ __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, do
     double *const wbase = ls.tab + (threadIdx.x >> 5) * LTAB_STRIDE;
     double *wtab = wbase;                  // current buffer (wbase or wbase + 16)
     double *ptab = ls.priv + threadIdx.x;
-    const ChainConst cc = make_chain_const(M, a, b, dc);
+    const double k1_chain = dc;                        // (K1P only)
+    if constexpr (K1P) dc = M.dc_fixed;
+    const ChainConst cc = [&] {
+        ChainConst c_ = make_chain_const(M, a, b, dc);
+        if constexpr (K1P) {
+            c_.k1e = M.damping ? k1_chain : 0.0;
+            // The fast stage takes the damping correction of the stage in flight to first order,
+            // e^(A + delta) - 1 = u + delta (1 + u) with delta = (h/a) a_sj k1 V' (rsf_stage_fast): 1e-16 at the
+            // reference's k1 = 1e-7, but delta^2/2 ~ 4e-10 at k1 = 1e-3.  Away from the reference's value the steps
+            // are therefore scored by the general-range stages (the reference's formulas, exact in k1), selected the
+            // way the slip law selects them: an infinite range scale, no instruction in the fast stage.
+            if (!(fabs(c_.k1e) <= 4.0e-7)) c_.qscale = INFINITY;
+        }
+        return c_;
+    }();
     const bool have_data = series.g != nullptr;
     constexpr bool parity = PARITY;      // compile-time: keeps the fast interval one branch-free block
     const double uround = 2.3e-16;
@@ -1430,7 +1448,7 @@ __device__ __forceinline__ SolveOut rsf_solve_mode(const ModelK &M, double a, do
 }
 
 // integration mode is a kernel-uniform run-time choice; each mode is its own instantiation
-template <bool VS, bool ISO = false>
+template <bool VS, bool ISO = false, bool K1P = false>
 __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double b, double dc, bool active,
                                                SeriesStage &series, const LoadScratch &ls, double *acc_out,
                                                const double *acc_ref, size_t acc_stride, double fd_den,
@@ -1438,9 +1456,9 @@ __device__ __forceinline__ SolveOut rsf_solve(const ModelK &M, double a, double 
                                                double sse_limit = INFINITY)
 {
     if (M.integ_mode == RSFM_INTEG_PARITY)
-        return rsf_solve_mode<true, VS, ISO>(M, a, b, dc, active, series, ls, acc_out, acc_ref, acc_stride, fd_den, xtx_out, t_out,
+        return rsf_solve_mode<true, VS, ISO, K1P>(M, a, b, dc, active, series, ls, acc_out, acc_ref, acc_stride, fd_den, xtx_out, t_out,
                                     sse_limit);
-    return rsf_solve_mode<false, VS, ISO>(M, a, b, dc, active, series, ls, acc_out, acc_ref, acc_stride, fd_den, xtx_out, t_out,
+    return rsf_solve_mode<false, VS, ISO, K1P>(M, a, b, dc, active, series, ls, acc_out, acc_ref, acc_stride, fd_den, xtx_out, t_out,
                                  sse_limit);
 }
 

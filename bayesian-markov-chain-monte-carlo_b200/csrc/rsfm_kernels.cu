@@ -129,6 +129,14 @@ static int check_cfg(const rsfm_cfg *c)
     if (c->round_packing < 0 || c->round_packing > 1) return set_err(RSFM_ERR_INVALID, "round_packing must be 0 (auto) or 1 (off)%s", "");
     if (c->chain_groups < 0 || c->chain_groups > RSFM_MAX_GROUPS)
         return set_err(RSFM_ERR_INVALID, "chain_groups must be in [0, 4]%s", "");
+    if (c->sampled_param != RSFM_PARAM_DC && c->sampled_param != RSFM_PARAM_K1)
+        return set_err(RSFM_ERR_INVALID, "bad sampled_param selector%s", "");
+    if (c->sampled_param == RSFM_PARAM_K1) {
+        if (c->n_params != 1) return set_err(RSFM_ERR_INVALID, "RSFM_PARAM_K1 samples one scalar: n_params must be 1%s", "");
+        if (!(c->dc_fixed > 0.0)) return set_err(RSFM_ERR_INVALID, "RSFM_PARAM_K1 needs dc_fixed > 0%s", "");
+        if (c->solver_variant == RSFM_VARIANT_STIFF)
+            return set_err(RSFM_ERR_INVALID, "RSFM_PARAM_K1 runs the default solver variant only%s", "");
+    }
     return RSFM_OK;
 }
 
@@ -148,6 +156,7 @@ static ModelK make_model(const rsfm_cfg *c)
     M.observable = c->observable;
     M.state_law = c->state_law;
     if (c->loading == RSFM_LOAD_TABLE) { M.load_n = c->n_load_table; M.load_dt = c->load_dt; M.load_tab = c->load_table_dev; }
+    if (c->sampled_param == RSFM_PARAM_K1) M.dc_fixed = c->dc_fixed;
     return M;
 }
 
@@ -160,6 +169,7 @@ static ModelK make_model(const rsfm_cfg *c)
 static bool stiff_variant(const rsfm_cfg *c)
 {
     if (c->solver_variant == RSFM_VARIANT_DEFAULT) return false;
+    if (c->sampled_param == RSFM_PARAM_K1) return false;    // k1 chains exist as default-variant kernels only
     if (c->solver_variant == RSFM_VARIANT_STIFF) return true;
     return c->loading == RSFM_LOAD_VSTEP;
 }
@@ -348,7 +358,8 @@ extern "C" int rsfm_trim(void)
 // ---------------------------------------------------------------------------
 // MB = resident blocks per SM the register budget is sized for: 3 (<= 168 registers) pays at saturating
 // batch sizes (+5 %), 1 (no cap) is 8 % faster when the batch is small and the kernel latency-bound.
-template <int MB, bool VS>
+// K1P: dc_in holds the per-chain k1 (RSFM_PARAM_K1), Dc = M.dc_fixed
+template <int MB, bool VS, bool K1P = false>
 __global__ void __launch_bounds__(128, VS ? 1 : MB)
 rsf_forward_kernel(const __grid_constant__ ModelK M, int C, double a0, double b0, const double *__restrict__ dc_in,
                    const double *__restrict__ a_in, const double *__restrict__ b_in,
@@ -372,8 +383,8 @@ rsf_forward_kernel(const __grid_constant__ ModelK M, int C, double a0, double b0
     SeriesStage series;
     series.begin(s_tile, s_bar, data, M.n_out);
     series.start_solve();
-    SolveOut o = rsf_solve<VS>(M, a, b, dc, active, series, lscr, acc_out ? acc_out + cc : nullptr, nullptr, (size_t)C,
-                           1.0, nullptr, t_out ? t_out + cc : nullptr);
+    SolveOut o = rsf_solve<VS, false, K1P>(M, a, b, dc, active, series, lscr, acc_out ? acc_out + cc : nullptr, nullptr,
+                                           (size_t)C, 1.0, nullptr, t_out ? t_out + cc : nullptr);
     if (active) {
         if (sse_out) sse_out[c] = o.sse;
         if (status_out) status_out[c] = o.status;
@@ -412,7 +423,11 @@ extern "C" int rsfm_forward_batch(const rsfm_cfg *cfg, int32_t C, const double *
     rsf_forward_kernel<MB, VS><<<VS ? vgrid : grid, VS ? STIFF_BLOCK : block, 0, (cudaStream_t)stream>>>(            \
         M, C, cfg->a, cfg->b, dc_dev, a_dev, b_dev, sse_out_dev ? data_dev : nullptr, acc_out_dev, t_out_dev,         \
         sse_out_dev, status_dev, filled_dev, (unsigned long long *)nrhs_dev, (unsigned long long *)nstep_dev, nom)
-    if (vs) RSFM_FWD(1, true);
+    if (cfg->sampled_param == RSFM_PARAM_K1)
+        rsf_forward_kernel<1, false, true><<<grid, block, 0, (cudaStream_t)stream>>>(
+            M, C, cfg->a, cfg->b, dc_dev, a_dev, b_dev, sse_out_dev ? data_dev : nullptr, acc_out_dev, t_out_dev,
+            sse_out_dev, status_dev, filled_dev, (unsigned long long *)nrhs_dev, (unsigned long long *)nstep_dev, nom);
+    else if (vs) RSFM_FWD(1, true);
     else if (C <= 148 * 4 * 32 * 2) RSFM_FWD(1, false);
     else RSFM_FWD(3, false);
 #undef RSFM_FWD
@@ -602,7 +617,7 @@ extern "C" int64_t rsfm_iteration(const rsfm_sampler *s) { return s ? s->iterati
 // pass j = 1..d: solve at q0 with parameter j-1 scaled by (1 + 1e-6); accumulates
 //                the column products needed for X'X.  d = 1 keeps everything in
 //                one pass; d = 3 stores the three sensitivity columns.
-template <int D, bool VS>
+template <int D, bool VS, bool K1P = false>
 __global__ void __launch_bounds__(128)
 rsf_init_kernel(const __grid_constant__ ModelK M, int C, int pass, double a0, double b0, int n_prior_len, SamplerDev S,
                 double *__restrict__ scratch /* [(1+ (D>1?D:0))][n_out][C] */)
@@ -638,7 +653,7 @@ rsf_init_kernel(const __grid_constant__ ModelK M, int C, int pass, double a0, do
     //   pass j, d = 3   : trajectory -> scratch plane j (combined by rsf_init_finish_kernel)
     double *wr = (pass == 0) ? scratch + cc : (D == 1 ? nullptr : scratch + (size_t)pass * plane + cc);
     const double *rd = (pass > 0 && D == 1) ? scratch + cc : nullptr;
-    SolveOut o = rsf_solve<VS>(M, a, b, dc, active, series, lscr, wr, rd, (size_t)C, fd_den, &xtx);
+    SolveOut o = rsf_solve<VS, false, K1P>(M, a, b, dc, active, series, lscr, wr, rd, (size_t)C, fd_den, &xtx);
     if (active) {
         if (pass == 0) {
             S.sse[c] = o.sse;
@@ -748,7 +763,10 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
 #define RSFM_INIT(D, VS)                                                                                              \
     rsf_init_kernel<D, VS><<<VS ? (C + STIFF_BLOCK - 1) / STIFF_BLOCK : grid, VS ? STIFF_BLOCK : block, 0, stream>>>( \
         M, C, pass, s->cfg.a, s->cfg.b, s->cfg.n_prior_len, s->d, s->scratch)
-        if (d == 1) { if (stiff_variant(&s->cfg)) RSFM_INIT(1, true); else RSFM_INIT(1, false); }
+        if (s->cfg.sampled_param == RSFM_PARAM_K1)
+            rsf_init_kernel<1, false, true><<<grid, block, 0, stream>>>(M, C, pass, s->cfg.a, s->cfg.b, s->cfg.n_prior_len,
+                                                                        s->d, s->scratch);
+        else if (d == 1) { if (stiff_variant(&s->cfg)) RSFM_INIT(1, true); else RSFM_INIT(1, false); }
         else { if (stiff_variant(&s->cfg)) RSFM_INIT(3, true); else RSFM_INIT(3, false); }
 #undef RSFM_INIT
         CUDA_TRY(cudaGetLastError());
@@ -805,11 +823,13 @@ struct RunArgs {
 // most in-bounds proposals has (8.2 of the 10 iterations of a launch, against 5 on average at cfg 3).  The solver is
 // untouched: a thread solves for the proposal it was handed and the result goes back to the owner through shared
 // memory, so chains are bit-identical with and without packing.
-template <int D, bool DET, bool VS, bool PACK = false>
+// K1P (d = 1): the chain's scalar is k1 (RSFM_PARAM_K1), Dc = M.dc_fixed; everything but the solve is unchanged.
+template <int D, bool DET, bool VS, bool PACK = false, bool K1P = false>
 __global__ void __launch_bounds__(128, VS ? 1 : 3)
 rsf_mcmc_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunArgs A)
 {
     static_assert(!PACK || (D == 3 && !DET && !VS), "packing: the Philox-driven d = 3 kernel of the default variant");
+    static_assert(!K1P || (D == 1 && !VS), "k1 chains: d = 1, default variant");
     __shared__ double s_job[PACK ? 4 * 128 : 1];        // (a, b, Dc, rejection threshold) of the packed proposals
     __shared__ double s_res[PACK ? 128 : 1];            // sum of squares of the finished solve, by owner
     __shared__ int s_own[PACK ? 128 : 1], s_resi[PACK ? 3 * 128 : 1], s_wc[PACK ? 4 : 1];
@@ -1025,8 +1045,8 @@ rsf_mcmc_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunArgs A
             const double pb = (D == 3) ? qn[1] : A.b0;
             const double pdc = solve ? qn[D - 1] : q[D - 1];
             series.start_solve();
-            SolveOut o = rsf_solve<VS>(M, solve ? pa : ((D == 3) ? q[0] : A.a0), solve ? pb : ((D == 3) ? q[1] : A.b0), pdc,
-                                   solve, series, lscr, nullptr, nullptr, Cz, 1.0, nullptr, nullptr, sse_limit);
+            SolveOut o = rsf_solve<VS, false, K1P>(M, solve ? pa : ((D == 3) ? q[0] : A.a0), solve ? pb : ((D == 3) ? q[1] : A.b0),
+                                                   pdc, solve, series, lscr, nullptr, nullptr, Cz, 1.0, nullptr, nullptr, sse_limit);
             // ---- accept / reject (MCMC.py:327-331) ----
             bool acc = false;
             if (solve) {
@@ -1367,6 +1387,7 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
 static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
 {
     if (A.deterministic) return 0;
+    if (s->cfg.sampled_param == RSFM_PARAM_K1) return 0;   // k1 chains: one-thread-per-chain kernel only
     if (s->cfg.adapt_mode == RSFM_ADAPT_COMPAT && s->cfg.n_params != 1) return 0;
     if (s->cfg.n_out > 2 * SERIES_TILE) return 0;          // streamed series: block barriers, no speculation
     const int want = s->cfg.spec_depth;
@@ -1418,6 +1439,7 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
     // Chain groups: Philox-driven launches of the one-thread-per-chain kernel go to the sampler's own streams, one
     // launch per group, and are NOT joined here -- the caller's stream is ordered behind them by the next call on
     // this sampler that needs their results (rsfm_pooled_partials and every getter / setter; rsfm_join).
+    const bool k1p = s->cfg.sampled_param == RSFM_PARAM_K1;
     if (s->n_groups > 1 && g < 2 && !A.deterministic && !vs) {
         int rc = fork_groups(s, stream);
         if (rc) return rc;
@@ -1425,7 +1447,8 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
         const bool pack = s->cfg.n_params == 3 && block == 128 && s->cfg.round_packing != 1;
         for (int k = 0; k < s->n_groups; k++) {
             A.c_begin = k * per; A.c_end = (k + 1) * per;
-            if (s->cfg.n_params == 1) rsf_mcmc_kernel<1, false, false><<<ggrid, block, 0, s->gstream[k]>>>(M, C, s->d, A);
+            if (k1p) rsf_mcmc_kernel<1, false, false, false, true><<<ggrid, block, 0, s->gstream[k]>>>(M, C, s->d, A);
+            else if (s->cfg.n_params == 1) rsf_mcmc_kernel<1, false, false><<<ggrid, block, 0, s->gstream[k]>>>(M, C, s->d, A);
             else if (pack) rsf_mcmc_kernel<3, false, false, true><<<ggrid, block, 0, s->gstream[k]>>>(M, C, s->d, A);
             else rsf_mcmc_kernel<3, false, false><<<ggrid, block, 0, s->gstream[k]>>>(M, C, s->d, A);
         }
@@ -1453,6 +1476,9 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
         if (s->cfg.n_params == 1 && s->cfg.adapt_mode == RSFM_ADAPT_COMPAT) RSFM_SPEC(1, true)
         else if (s->cfg.n_params == 1) RSFM_SPEC(1, false)
         else RSFM_SPEC(3, false)
+    } else if (k1p) {
+        if (A.deterministic) rsf_mcmc_kernel<1, true, false, false, true><<<grid, block, 0, stream>>>(M, C, s->d, A);
+        else rsf_mcmc_kernel<1, false, false, false, true><<<grid, block, 0, stream>>>(M, C, s->d, A);
     } else if (s->cfg.n_params == 1) {
         if (A.deterministic) RSFM_SEQ(1, true) else RSFM_SEQ(1, false)
     } else {

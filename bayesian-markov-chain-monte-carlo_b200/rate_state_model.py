@@ -120,10 +120,12 @@ class RateStateModel:
         return torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
 
     # -- batched forward solve (extension) -------------------------------
-    def evaluate_batch(self, dc, a=None, b=None, data=None, want_acc=True, want_t=False):
+    def evaluate_batch(self, dc, a=None, b=None, data=None, want_acc=True, want_t=False, k1=None):
         """Solve for many parameter sets in one launch.
 
         dc, a, b: 1-D array-likes / CUDA tensors of equal length C (a, b optional).
+        k1 (extension): a 1-D array of radiation-damping coefficients (RateStateModel.py:171, 351); the
+        batch axis is then k1, ``dc`` must be ONE value (the common Dc) and a, b stay the model's scalars.
         Returns a dict of CUDA tensors: ``acc`` [n_out, C] (time-major; the observable: acceleration, or
         mu when ``self.observable == "mu"``), ``t``,
         ``sse`` [C] (when ``data`` is given), ``status``, ``filled``, ``nrhs``, ``nstep``.
@@ -138,6 +140,13 @@ class RateStateModel:
             return torch.as_tensor(x, dtype=torch.float64).to(dev).contiguous().reshape(-1)
 
         dc_t, a_t, b_t, data_t = as_dev(dc), as_dev(a), as_dev(b), as_dev(data)
+        cfg = self.to_cfg()
+        if k1 is not None:
+            if dc_t.numel() != 1 or a_t is not None or b_t is not None:
+                raise ValueError("with k1 given, dc must be one value and a, b the model's scalars")
+            cfg.sampled_param = _lib.PARAM_K1
+            cfg.dc_fixed = float(dc_t.item())
+            dc_t = as_dev(k1)                       # the library's per-chain scalar is k1 now (rsfm.h: sampled_param)
         cn = dc_t.numel()
         n_out = self.num_outputs()
         if data_t is not None and data_t.numel() != n_out:
@@ -154,7 +163,6 @@ class RateStateModel:
             "nrhs": torch.empty(cn, dtype=torch.int64, device=dev),
             "nstep": torch.empty(cn, dtype=torch.int64, device=dev),
         }
-        cfg = self.to_cfg()
         with torch.cuda.device(dev):
             rc = lib.rsfm_forward_batch(C.byref(cfg), cn, _lib.ptr(dc_t), _lib.ptr(a_t), _lib.ptr(b_t),
                                         _lib.ptr(data_t), _lib.ptr(out["acc"]), _lib.ptr(out["t"]),

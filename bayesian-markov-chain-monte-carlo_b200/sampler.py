@@ -16,7 +16,8 @@ adaptation) runs inside one CUDA kernel (``rsf_mcmc_kernel`` in librsfm) for all
 chains and all iterations; nothing is sampled or integrated on the CPU.
 
 Extensions (keyword-only; defaults reproduce the reference): ``n_chains``,
-``seed``, ``device``, ``param_names`` (("Dc",) or ("a", "b", "Dc")), ``bounds``,
+``seed``, ``device``, ``param_names`` (("Dc",), ("a", "b", "Dc") or ("k1",): the radiation-damping
+coefficient with ``model.Dc`` held fixed), ``bounds``,
 ``deterministic_inputs``, ``compat_adapt``, ``adapt`` ("pooled" = Haario-style
 covariance pooled over chains and ranks), ``shard`` (split chains over
 torch.distributed ranks).
@@ -105,8 +106,8 @@ class MCMC:
         self.chain_id0 = int(chain_id0)        # global id of chain 0 when not sharding (Philox counter)
         self.spec_depth = int(spec_depth)      # speculation tree depth: 0 auto, 1 off, 2..5 forced
         self.resume = resume                   # checkpoint dict / JSON file from MCMC.checkpoint()
-        if self.param_names not in (("Dc",), ("a", "b", "Dc")):
-            raise ValueError("param_names must be ('Dc',) or ('a', 'b', 'Dc')")
+        if self.param_names not in (("Dc",), ("a", "b", "Dc"), ("k1",)):
+            raise ValueError("param_names must be ('Dc',), ('a', 'b', 'Dc') or ('k1',)")
         if compat_adapt is None:
             # reference behaviour follows the container type of qpriors (q2 / q3)
             compat_adapt = hasattr(qpriors, "keys") and adapt is None
@@ -177,6 +178,14 @@ class MCMC:
 
         cfg = self.model.to_cfg()
         cfg.n_params = d
+        sample_k1 = self.param_names == ("k1",)
+        if sample_k1:
+            # the chain's scalar is model.k1 (RateStateModel.py:171, 351) instead of model.Dc (MCMC.py:381);
+            # Dc is what the caller left on the model
+            if self.model.Dc is None:
+                raise TypeError("param_names=('k1',) needs model.Dc set (the fixed critical slip distance)")
+            cfg.sampled_param = _lib.PARAM_K1
+            cfg.dc_fixed = float(np.ravel(np.asarray(self.model.Dc, dtype=np.float64))[0])
         lo, hi = self._bounds(d)
         for j in range(d):
             cfg.lo[j], cfg.hi[j] = lo[j], hi[j]
@@ -314,7 +323,11 @@ class MCMC:
                         print(i, bool(accept_h[0, i]))
                         print("Generated Sample ---- ", dr[i, d - 1] if d == 1 else dr[i, :d])
                 # the reference leaves model.Dc at the last evaluated proposal, a 1-element array (q6)
-                self.model.Dc = np.array([last if last is not None else float(np.ravel(self.qstart)[-1])])
+                left = np.array([last if last is not None else float(np.ravel(self.qstart)[-1])])
+                if sample_k1:
+                    self.model.k1 = float(left[0])
+                else:
+                    self.model.Dc = left
             if self.verbose:
                 print("acceptance ratio:", self.acceptance_ratio[0])      # MCMC.py:530
             self.std2 = np.ascontiguousarray(std2_h[0])                    # MCMC.py:533

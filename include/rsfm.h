@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RSFM_ABI_VERSION 3
+#define RSFM_ABI_VERSION 4
 #define RSFM_MAX_PARAMS 3
 #define RSFM_MAX_GROUPS 4
 
@@ -68,6 +68,11 @@ enum { RSFM_ADAPT_NONE = 0,        /* list-typed priors: update silently dead (q
 enum { RSFM_OBS_ACC = 0,           /* backward-difference acceleration, RateStateModel.py:388 (reference) */
        RSFM_OBS_MU = 1 };          /* friction coefficient mu_k = y[0], RateStateModel.py:385 (extension:
                                       the series the reference integrates and stores but never compares) */
+
+/* which model constant the scalar (d = 1) chain samples ("named parameters (a, b, Dc, k1 ...)") */
+enum { RSFM_PARAM_DC = 0,          /* Dc: what MCMC.SSqcalc sets on the model, MCMC.py:381 (reference) */
+       RSFM_PARAM_K1 = 1 };        /* the radiation-damping coefficient k1 (RateStateModel.py:171, 349-353), with
+                                      Dc = cfg->dc_fixed for every chain (extension) */
 
 /* which instantiation of the solver kernels runs */
 enum { RSFM_VARIANT_AUTO = 0,      /* stiff variant for RSFM_LOAD_VSTEP, default one otherwise */
@@ -122,6 +127,11 @@ typedef struct rsfm_cfg {
     int32_t n_load_table;                /* RSFM_LOAD_TABLE: entries (>= 2), spacing and DEVICE pointer of the table; */
     double  load_dt;                     /*   read by every call that gets this cfg and by rsfm_init, which tabulates */
     const double *load_table_dev;        /*   it for the sampler: keep it valid and unchanged while they run */
+    int32_t sampled_param;               /* RSFM_PARAM_*.  RSFM_PARAM_K1 (n_params = 1, default solver variant only):
+                                            every per-chain scalar this header calls "dc" -- dc_dev of
+                                            rsfm_forward_batch, q / q0 / proposals / samples of the sampler, lo[0], hi[0]
+                                            -- is k1, and Dc is dc_fixed */
+    double  dc_fixed;                    /* RSFM_PARAM_K1 only: the common Dc (> 0) */
 } rsfm_cfg;
 
 typedef struct rsfm_sampler rsfm_sampler;   /* opaque; owns per-chain device state */

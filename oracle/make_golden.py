@@ -14,6 +14,8 @@ so parity is pinned on outputs of the reference itself, imported from
   G3  sse_grid.json   SSE(Dc) on a grid for the seeded data set (MCMC.py:387).
   G4  rhs_values.json   the nested RHS ``friction(t, y)`` (RateStateModel.py:277-355) at fixed states
         (``python oracle/make_golden.py rhs``).
+  G5  forward_k1.json   trajectories and SSE(k1) with the model attribute ``k1`` varied
+        (``python oracle/make_golden.py k1``).
 
 Everything is written in the reference's own ``__ndarray__`` JSON wire format
 (json_save_load.py:37-38).  Versions of numpy/scipy are stamped into each file:
@@ -201,9 +203,42 @@ def make_rhs_values(rsm):
             "rows": np.array(rows)}
 
 
+def make_k1_values(rsm):
+    """G5 forward_k1.json: RateStateModel.evaluate()[1] of the unmodified reference with its public attribute ``k1``
+    (RateStateModel.py:171, used at :351) moved away from the module default, and the sum of squares against a seeded
+    data set on a k1 grid -- what pins the oracle (and through it the CUDA path) for chains that sample k1."""
+    cases = []
+    for dc in (100.0, 1000.0, 1350.0):
+        for k1 in (0.0, 1e-7, 1e-5, 1e-3, 3e-3, 8e-3):
+            m = rsm.RateStateModel(number_time_steps=500)
+            m.Dc = dc
+            m.k1 = k1
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                t, acc, _ = m.evaluate()
+            cases.append({"Dc": dc, "k1": k1, "N": 500, "acc": acc, "t_last": float(t[-1])})
+    # seeded data set at (Dc, k1) = (1000, 3e-3); SSE(k1) as MCMC.SSqcalc forms it (MCMC.py:387), model.k1 set instead of model.Dc
+    m = rsm.RateStateModel(number_time_steps=500)
+    m.Dc = 1000.0
+    m.k1 = 3e-3
+    np.random.seed(4242)
+    _, _, data = m.evaluate()
+    grid = np.array([1e-4, 5e-4, 1e-3, 2e-3, 2.5e-3, 3e-3, 3.5e-3, 4e-3, 6e-3, 9e-3])
+    sse = []
+    for k1 in grid:
+        m.k1 = float(k1)
+        acc = m.evaluate()[1]
+        sse.append(float(np.sum((acc - data) ** 2, axis=0)))
+    return {"cases": cases, "data": data, "data_Dc": 1000.0, "data_k1": 3e-3, "data_seed": 4242,
+            "k1_grid": grid, "sse": np.array(sse)}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     rsm, mcm = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "k1":
+        dump("forward_k1.json", make_k1_values(rsm))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "rhs":
         dump("rhs_values.json", make_rhs_values(rsm))
         return

@@ -22,6 +22,8 @@ OBS_ACC = 0
 OBS_MU = 1
 LAW_AGING = 0
 LAW_SLIP = 1
+PARAM_DC = 0
+PARAM_K1 = 1
 
 
 class OrcModel(C.Structure):
@@ -39,6 +41,7 @@ class OrcModel(C.Structure):
         ("observable", C.c_int),
         ("state_law", C.c_int),
         ("load_table", C.POINTER(C.c_double)), ("n_load_table", C.c_int), ("load_dt", C.c_double),
+        ("sampled_param", C.c_int),
     ]
 
 

@@ -46,6 +46,7 @@ void orc_model_defaults(orc_model *m)
     m->observable = ORC_OBS_ACC;
     m->state_law = ORC_LAW_AGING;
     m->load_table = 0; m->n_load_table = 0; m->load_dt = 0.1;
+    m->sampled_param = ORC_PARAM_DC;
 }
 
 /* load-point velocity.  SINE_DECAY is the reference (RateStateModel.py:327-329);
@@ -335,6 +336,16 @@ double orc_sse(const double *acc, const double *data, int n)
     return pairwise_sq(acc, data, n);
 }
 
+/* the scalar the sampler varies: model.Dc in the reference (MCMC.py:245, 251, 381), k1 with ORC_PARAM_K1 */
+static void set_scalar(orc_model *m, double q)
+{
+    if (m->sampled_param == ORC_PARAM_K1) m->k1 = q; else m->Dc = q;
+}
+static double get_scalar(const orc_model *m)
+{
+    return m->sampled_param == ORC_PARAM_K1 ? m->k1 : m->Dc;
+}
+
 /* batch of independent solves over pthreads (gcc here has no libgomp) */
 typedef struct {
     const orc_model *m; const double *dc; int C; const double *data; int n;
@@ -350,7 +361,7 @@ static void *batch_worker(void *arg)
         int c = atomic_fetch_add(&j->next, 1);
         if (c >= j->C) break;
         orc_model mm = *j->m;
-        mm.Dc = j->dc[c];
+        set_scalar(&mm, j->dc[c]);
         orc_stats st;
         double *acc = j->acc_out ? j->acc_out + (size_t)c * j->n : scratch;
         int ns = orc_observe(&mm, acc, &st);
@@ -401,22 +412,22 @@ int orc_chain_replay(const orc_model *m0, const double *data, int n,
     double *acc_dq = (double *)malloc(sizeof(double) * n);
     int64_t solves = 0;
     /* compute_initial_covariance, MCMC.py:245-266 */
-    m.Dc = qstart;
+    set_scalar(&m, qstart);
     if (orc_observe(&m, acc, 0) != n) { free(acc); free(acc_dq); return -1; }
-    m.Dc = m.Dc * (1 + 1e-6);
+    set_scalar(&m, get_scalar(&m) * (1 + 1e-6));
     orc_observe(&m, acc_dq, 0);
     solves += 2;
     s2[0] = orc_sse(acc, data, n) / (n - n_prior_len);        /* :261 */
     double xtx = 0.0;
     {
         /* X'X via np.dot on an (1,N)x(N,1) product; plain accumulation here */
-        double den = m.Dc * 1e-6;
+        double den = get_scalar(&m) * 1e-6;
         for (int i = 0; i < n; i++) { double x = (acc_dq[i] - acc[i]) / den; xtx += x * x; }
     }
     double V = s2[0] * (1.0 / xtx);                           /* :265-266 */
     if (vstart_out) *vstart_out = V;
     /* SSqprev = SSqcalc(qstart), :468 */
-    m.Dc = qstart;
+    set_scalar(&m, qstart);
     orc_observe(&m, acc, 0);
     solves++;
     double ss = orc_sse(acc, data, n);
@@ -426,7 +437,7 @@ int orc_chain_replay(const orc_model *m0, const double *data, int n,
         double qn = compat_adapt ? q + sqrt(V) * proposals[i] : proposals[i];   /* :497 */
         int ok = (qn > lo) && (qn < hi);                      /* :318-320, strict */
         if (ok) {
-            m.Dc = qn;
+            set_scalar(&m, qn);
             orc_observe(&m, acc, 0);              /* :324 */
             solves++;
             double ssn = orc_sse(acc, data, n);
@@ -462,7 +473,7 @@ int orc_chain_replay(const orc_model *m0, const double *data, int n,
 static void set_params(orc_model *m, int d, const double *q)
 {
     if (d == 3) { m->a = q[0]; m->b = q[1]; m->Dc = q[2]; }
-    else m->Dc = q[0];
+    else set_scalar(m, q[0]);
 }
 
 int orc_chain_replay_nd(const orc_model *m0, const double *data, int n, int d,

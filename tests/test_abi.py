@@ -24,7 +24,7 @@ def test_header_symbols_all_exported(built_lib, pkg):
 
 
 def test_abi_version_and_defaults(built_lib, pkg):
-    assert built_lib.rsfm_abi_version() == 3
+    assert built_lib.rsfm_abi_version() == 4
     cfg = pkg._lib.default_cfg()
     # RateStateModel.py:5-11 / :374 / MCMC.py:97
     assert (cfg.a, cfg.b, cfg.mu_ref, cfg.V_ref, cfg.k1) == (0.011, 0.014, 0.6, 1.0, 1e-7)
@@ -32,6 +32,7 @@ def test_abi_version_and_defaults(built_lib, pkg):
     assert (cfg.rtol, cfg.atol, cfg.nmax, cfg.n0) == (1e-6, 1e-10, 500, 0.01)
     assert cfg.radiation_damping == 1 and cfg.loading == 0 and cfg.integ_mode == 0
     assert cfg.spec_depth == 0 and cfg.adapt_interval == 10
+    assert cfg.sampled_param == 0 and cfg.dc_fixed == 0.0            # the chain samples Dc (MCMC.py:381)
 
 
 def test_sass_is_sm100a_with_tma_bulk_copy(built_lib, pkg):

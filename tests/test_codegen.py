@@ -43,10 +43,10 @@ def _one(hot_blocks, prefix):
 
 @pytest.mark.parametrize("prefix, max_cycles", [
     ("_Z20rsf_mcmc_spec_kernelILi1ELb0ELb0EE", 2020),      # bench config (cfg 2): 1,924 in the round-1 build
-    ("_Z15rsf_mcmc_kernelILi1ELb0ELb0ELb0EE", 2180),           # saturating sizes / cfg 5: 2,072
-    ("_Z15rsf_mcmc_kernelILi3ELb0ELb0ELb0EE", 2160),          # cfg 3 without round packing: 2,052
-    ("_Z15rsf_mcmc_kernelILi3ELb0ELb0ELb1EE", 2160),           # cfg 3: 2,052
-    ("_Z18rsf_forward_kernelILi1ELb0EE", 2000),            # forward batches: 1,903
+    ("_Z15rsf_mcmc_kernelILi1ELb0ELb0ELb0ELb0EE", 2180),           # saturating sizes / cfg 5: 2,072
+    ("_Z15rsf_mcmc_kernelILi3ELb0ELb0ELb0ELb0EE", 2160),          # cfg 3 without round packing: 2,052
+    ("_Z15rsf_mcmc_kernelILi3ELb0ELb0ELb1ELb0EE", 2160),           # cfg 3: 2,052
+    ("_Z18rsf_forward_kernelILi1ELb0ELb0EE", 2000),            # forward batches: 1,903
 ])
 def test_fast_interval_block_schedule_and_no_spills(hot_blocks, prefix, max_cycles):
     n, cycles, local = _one(hot_blocks, prefix)
@@ -58,9 +58,13 @@ def test_fast_interval_block_schedule_and_no_spills(hot_blocks, prefix, max_cycl
 def test_both_variants_of_every_solver_kernel_are_built(hot_blocks):
     for stem in ("rsf_forward_kernelILi1E", "rsf_init_kernelILi1E", "rsf_init_kernelILi3E",
                  "rsf_mcmc_kernelILi1ELb0E", "rsf_mcmc_kernelILi3ELb0E", "rsf_mcmc_spec_kernelILi1ELb0E"):
-        # (the template arguments end in the variant flag VS; rsf_mcmc_kernel has the packing flag PACK behind it)
+        # (the template arguments are ..., VS[, PACK], K1P, except for the speculative kernel, which ends in VS)
         names = []
         for n in (k.split("EEv")[0] for k in hot_blocks if stem in k):
+            if "rsf_mcmc_spec_kernelI" not in n:
+                if n.endswith("ELb1"):
+                    continue                                   # the k1 instantiation (d = 1, default variant only)
+                n = n[:-4]
             if "rsf_mcmc_kernelI" in n:
                 if n.endswith("ELb1"):
                     continue                                   # the packing instantiation (d = 3, default variant only)
@@ -68,3 +72,12 @@ def test_both_variants_of_every_solver_kernel_are_built(hot_blocks):
             names.append(n)
         names.sort()
         assert len(names) == 2 and names[0].endswith("Lb0") and names[1].endswith("Lb1"), (stem, names)
+
+
+def test_k1_instantiations_are_built_beside_the_tuned_kernels(hot_blocks):
+    """RSFM_PARAM_K1 lives in its own instantiations (forward, init, the d = 1 one-thread-per-chain kernel with Philox
+    and with host-supplied draws), so the per-chain k1 register never enters the tuned kernels."""
+    for name in ("_Z18rsf_forward_kernelILi1ELb0ELb1EE", "_Z15rsf_init_kernelILi1ELb0ELb1EE",
+                 "_Z15rsf_mcmc_kernelILi1ELb0ELb0ELb0ELb1EE", "_Z15rsf_mcmc_kernelILi1ELb1ELb0ELb0ELb1EE"):
+        n, cycles, local = _one(hot_blocks, name)
+        assert 900 <= n <= 1100 and local == 0

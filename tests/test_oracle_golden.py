@@ -205,3 +205,77 @@ def test_rhs_matches_reference_friction(orc):
         out = orc.rhs(m, row[2], row[3:6])
         worst = max(worst, float(np.max(np.abs(out - row[6:9]) / rhs_term_scales(row))))
     assert worst <= 1e-15, worst
+
+
+# ---- k1 as the varied constant (SURVEY 8f.4 "named parameters"): golden from the unmodified reference with its
+# ---- public attribute model.k1 changed (oracle/make_golden.py k1) ----
+def test_forward_with_k1_matches_reference(orc):
+    g = load_golden("forward_k1.json")
+    n_exact = 0
+    for case in g["cases"]:
+        m = orc.make_model(Dc=case["Dc"], k1=case["k1"], number_time_steps=case["N"])
+        t, acc, st = orc.forward(m)
+        ref = case["acc"]
+        assert np.max(np.abs(acc - ref)) <= TRAJ_RTOL * np.max(np.abs(ref)), (case["Dc"], case["k1"])
+        assert t[-1] == case["t_last"]
+        n_exact += int(np.array_equal(acc, ref))
+    assert n_exact >= 12
+    # k1 matters: the largest value roughly quarters the response
+    big = [c for c in g["cases"] if c["Dc"] == 1000.0]
+    assert np.max(np.abs(big[-1]["acc"])) < 0.3 * np.max(np.abs(big[0]["acc"]))
+
+
+def test_sse_on_a_k1_grid_matches_reference(orc):
+    """ORC_PARAM_K1: the batch axis (and the chain's scalar) is k1, Dc stays fixed."""
+    g = load_golden("forward_k1.json")
+    m = orc.make_model(Dc=g["data_Dc"], sampled_param=orc.PARAM_K1)
+    sse, _, _ = orc.forward_batch(m, g["k1_grid"], data=g["data"])
+    assert np.allclose(sse, g["sse"], rtol=1e-11, atol=0)
+    assert g["k1_grid"][int(np.argmin(g["sse"]))] in (2.5e-3, 3e-3, 3.5e-3)     # truth 3e-3
+
+
+def test_scipy_port_with_k1_bit_exact():
+    from oracle import scipy_port
+    g = load_golden("forward_k1.json")
+    case = [c for c in g["cases"] if c["Dc"] == 1350.0 and c["k1"] == 3e-3][0]
+    m = scipy_port.PortModel()
+    m.Dc, m.k1 = 1350.0, 3e-3
+    assert np.array_equal(m.evaluate()[1], case["acc"])
+
+
+def test_k1_replay_is_the_dc_replay_with_the_attribute_swapped(orc):
+    """orc_chain_replay with ORC_PARAM_K1 against a plain Python loop over orc.forward (MCMC.py:245-266, 494-521 with
+    model.k1 in the place of model.Dc)."""
+    g = load_golden("forward_k1.json")
+    data = g["data"]
+    rng = np.random.default_rng(7)
+    ns, q0, lo, hi = 12, 2e-3, 0.0, 0.01
+    z, u, gam = rng.standard_normal(ns), rng.random(ns), rng.gamma(0.5 * (0.01 + 500), size=ns)
+    m = orc.make_model(Dc=1000.0, sampled_param=orc.PARAM_K1)
+    chain, s2, acc, vstart, nsolves = orc.chain_replay(m, data, q0, lo, hi, 3, ns, z, u, gam, compat_adapt=True)
+
+    def sse_of(k1):
+        return orc.sse(orc.forward(orc.make_model(Dc=1000.0, k1=k1))[1], data)
+    base = orc.forward(orc.make_model(Dc=1000.0, k1=q0))[1]
+    pert = orc.forward(orc.make_model(Dc=1000.0, k1=q0 * (1 + 1e-6)))[1]
+    s2_0 = orc.sse(base, data) / (500 - 3)
+    x = (pert - base) / (q0 * (1 + 1e-6) * 1e-6)
+    v = s2_0 / float(np.sum(x * x))
+    assert vstart == pytest.approx(v, rel=1e-12)
+    q, ss, s2_i = q0, sse_of(q0), s2_0
+    for i in range(ns):
+        qn = q + np.sqrt(v) * z[i]
+        ok = lo < qn < hi
+        if ok:
+            ssn = sse_of(qn)
+            ok = min(0.0, 0.5 * (ss - ssn) / s2_i) > np.log(u[i])
+            if ok:
+                q, ss = qn, ssn
+        assert bool(acc[i]) == bool(ok)
+        assert chain[i + 1] == q
+        s2_i = 1 / (gam[i] * (1 / (0.5 * (0.01 * s2_i + ss))))
+        assert s2[i + 1] == pytest.approx(s2_i, rel=1e-13)
+        if (i + 1) % 10 == 0:                                        # MCMC.py:523-527, 200-204 (dict-prior form)
+            vnew = 2.38 ** 2 / 2.0 * np.var(chain[i + 2 - 10:i + 2], ddof=1)
+            if vnew > 0:
+                v = np.sqrt(vnew)
