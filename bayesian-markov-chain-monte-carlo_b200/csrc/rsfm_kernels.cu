@@ -445,6 +445,7 @@ struct SamplerDev {
     double *chol;       // [d(d+1)/2][C]; d = 1: proposal variance (as the reference stores it)
     double *ring;       // [adapt_interval][C] last samples, COMPAT adaptation (d = 1)
     double *suff;       // [d + d(d+1)/2][C] per-chain sums for POOLED adaptation
+    double *fit;        // [SPEC_FIT][C] predictor state of the speculative kernel (d = 1, few chains), else unused
     double *data;       // [n_out] padded to an even count
     double *nom;        // [n_out][NOM_STRIDE] nominal loading table (loading_table_kernel)
     unsigned int *accepted;        // [C]
@@ -489,6 +490,12 @@ struct rsfm_sampler {
 };
 
 static int tri(int d) { return d * (d + 1) / 2; }
+
+// Predictor state of rsf_mcmc_spec_kernel per chain: moments S0..S4 of x and T0..T2 of x^k y (0-7), coefficients
+// c0..c2 (8-10), mean squared residual (11), "fit valid" (12), "residual known" (13), centre 1/q_c, SS_c and scale
+// of the fit variables (14-16), state (17: 0 = not set up, 1 = in use, -1 = not usable for this chain).
+static const int SPEC_FIT = 18;
+static const int SPEC_MAX_CHAINS = 148 * 4 * 32 * 2 / 4;      // most chains the speculative kernel is chosen for
 
 // ---------------------------------------------------------------------------
 // chain groups
@@ -546,6 +553,8 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     const size_t o_q = take(sizeof(double) * d * Cz), o_sse = take(sizeof(double) * Cz), o_s2 = take(sizeof(double) * Cz);
     const size_t o_chol = take(sizeof(double) * tri(d) * Cz), o_ring = take(sizeof(double) * (cfg->adapt_mode == RSFM_ADAPT_COMPAT ? cfg->adapt_interval : 1) * Cz);
     const size_t o_suff = take(sizeof(double) * (d + tri(d)) * Cz), o_data = take(sizeof(double) * ((size_t)cfg->n_out + 2));
+    const bool want_fit = d == 1 && C <= SPEC_MAX_CHAINS;
+    const size_t o_fit = take(sizeof(double) * (want_fit ? SPEC_FIT * Cz : 1));
     const size_t o_nom = take(sizeof(double) * NOM_STRIDE * (size_t)cfg->n_out);
     const size_t o_acc = take(sizeof(unsigned int) * Cz), o_status = take(sizeof(int) * Cz);
     size_t o_cnt[7];
@@ -561,6 +570,7 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     char *b = s->slab;
     s->d.q = (double *)(b + o_q); s->d.sse = (double *)(b + o_sse); s->d.sigma2 = (double *)(b + o_s2);
     s->d.chol = (double *)(b + o_chol); s->d.ring = (double *)(b + o_ring); s->d.suff = (double *)(b + o_suff);
+    s->d.fit = want_fit ? (double *)(b + o_fit) : nullptr;
     s->d.data = (double *)(b + o_data); s->nom_buf = (double *)(b + o_nom); s->d.nom = s->nom_buf;
     s->d.accepted = (unsigned int *)(b + o_acc); s->d.status = (int *)(b + o_status);
     s->d.nrhs = (unsigned long long *)(b + o_cnt[0]); s->d.nstep = (unsigned long long *)(b + o_cnt[1]);
@@ -750,6 +760,7 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     CUDA_TRY(cudaMemsetAsync(s->d.urhs, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.ustep, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * (d + tri(d)) * (size_t)C, stream));
+    if (s->d.fit) CUDA_TRY(cudaMemsetAsync(s->d.fit, 0, sizeof(double) * SPEC_FIT * (size_t)C, stream));
     const int block = pick_block(C, &s->cfg), grid = (C + block - 1) / block;
     const ModelK M = make_model(&s->cfg);
     // nominal load table of this sampler (a tabulated load is read HERE: the table must not change afterwards); the
@@ -1139,24 +1150,43 @@ rsf_mcmc_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunArgs A
 
 
 // ---------------------------------------------------------------------------
-// speculative ("prefetching") Metropolis for small chain counts
+// speculative ("prefetching") Metropolis for small chain counts, with a predictor
 // ---------------------------------------------------------------------------
 // With C chains on a 148-SM part, one thread per chain leaves most SMSPs idle while every chain
 // waits a full solve latency per iteration (the loop of MCMC.py:494 is strictly sequential).  Here
-// G = 2^g lanes serve one chain: lanes 1..G-1 are the nodes of the binary tree of the next g
-// iterations.  Node j at depth l evaluates the proposal iteration it+l-1 would make if the earlier
-// iterations of the round had the accept (1) / reject (0) outcomes spelled by the bits of j below its
-// leading one (children of j: 2j after a reject, 2j+1 after an accept).  All solves of the tree run
-// concurrently; afterwards every lane of the group walks the realised path with the tree's sums of
-// squares, applying exactly the reference's accept rule and sigma^2 update in order.  Random draws
-// are Philox values keyed by (chain, iteration), so the chain is the one the sequential kernel
-// produces, bit for bit; only the wall time per iteration changes (up to g times shorter).
+// G = 2^g lanes serve one chain: every lane evaluates one NODE of the binary tree of the chain's
+// possible futures.  A node at depth l is reached by a path of l-1 accept / reject outcomes of the
+// round's earlier iterations and evaluates the proposal iteration it+l-1 would make after them
+// (its accept child proposes from that proposal, its reject child from the state before).  All
+// solves of the tree run concurrently; afterwards every lane of the group walks the realised path
+// with the tree's sums of squares, applying exactly the reference's accept rule and sigma^2 update in
+// order.  Random draws are Philox values keyed by (chain, iteration), so the chain is the one the
+// sequential kernel produces, bit for bit; only the wall time per iteration changes.
 //
-// Early stopping: the root knows its exact threshold SS - 2 s2 ln U.  A deeper node does not know
-// the state it will be judged against, so it stops at a generous bound H = SS + 100 s2; at
-// resolution time a stopped node counts as rejected only if H >= the true threshold (then rejection
-// is certain), otherwise it is unresolved and the round ends before it -- that iteration becomes the
-// root of the next round.  Exactness never depends on H.
+// WHICH G nodes are evaluated is chosen anew every round, best first by the probability that the
+// realised path reaches them (round 2; "predictive prefetching").  The root has probability 1, the
+// children of a node with estimated acceptance probability p have reach p and 1 - p times the
+// node's; the open child with the largest reach is added G - 1 times (one argmax over the group per
+// node; the lane that receives the node computes its proposal from the parent's state handed over by
+// shuffles).  The estimate p never enters a result -- a wrong guess only ends the round earlier:
+//   * d = 1 (Dc): the sum of squares is, to ~1e-2 sigma^2 over the whole posterior, a quadratic in
+//     1/Dc (the response scales with k' = 0.1/Dc, RateStateModel.py:324), so a three-coefficient
+//     least-squares fit through the completed solves of the last few rounds -- every node of every
+//     tree is an exact sample of SS(q), used or not -- predicts SS' of a proposal, and with the
+//     acceptance uniform and the gamma draws of the coming iterations known in advance (Philox) the
+//     decision SS' < SS - 2 s2 ln U itself: p = Phi((threshold - SS'_fit) / rms residual of the fit).
+//     On the bench workload 99 % of the decisions are predicted and a 16-lane group advances ~15
+//     iterations per round where the balanced tree of round 1 advanced 4.
+//   * otherwise (d = 3, no fit yet): p = the running acceptance rate of the launch; p = 0.5 gives
+//     back the balanced tree.
+//
+// Early stopping: a node whose path holds no accept is judged against the state the round started
+// with, so its threshold SS - 2 s2 ln U is known exactly (s2 follows from the gamma draws alone)
+// and is its stopping bound, like the root's.  Any other node stops at a generous bound
+// H = SS + 100 s2; at resolution time a stopped node counts as rejected only if its bound is at
+// least the true threshold (then rejection is certain), otherwise it is unresolved and the round
+// ends before it -- that iteration becomes the root of the next round.  Exactness never depends on
+// the bounds.
 //
 // COMPAT = true (d = 1, the reference's dict-prior adaptation): the proposal scale changes after every
 // adapt_interval-th sample, so a round never looks past that boundary; the writer lane keeps the
@@ -1169,20 +1199,24 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ double s_ltab[4 * LTAB_STRIDE];
     __shared__ double s_lpriv[11 * 128];
+    // the fit of SS(q), one slot per group (<= 32 groups per block, g >= 2): moments S0..S4 of x and T0..T2 of
+    // x^k y, coefficients c0..c2, mean squared residual, "fit valid", "residual known", and the centre / scale of the
+    // fit variables (kept here, not in registers: nothing of the predictor is live across the solve)
+    __shared__ double s_sur[32 * SPEC_FIT];
     LoadScratch lscr;
     lscr.tab = s_ltab; lscr.priv = s_lpriv; lscr.nom = S.nom;
     constexpr int T = D * (D + 1) / 2;
     const int G = 1 << g;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int chain = tid >> g;
-    const int node = tid & (G - 1);                    // 0: idle helper lane; 1..G-1: tree nodes
     const bool chain_ok = chain < C;
     const int cc = chain_ok ? chain : C - 1;
     const int lane = threadIdx.x & 31;
     const int gbase = lane & ~(G - 1);
+    const int li = lane - gbase;                       // this lane's slot in its group: it receives the li-th node
     const size_t Cz = (size_t)C;
-    const int depth = node > 0 ? 32 - __clz(node) : 0; // level of this node (1 = root)
-    const bool writer = chain_ok && node == 1;
+    const bool writer = chain_ok && li == 0;
+    double *const sur = s_sur + (threadIdx.x >> g) * SPEC_FIT;
 
     double q[D], L[T], sq[D], sqq[T];
 #pragma unroll
@@ -1199,58 +1233,132 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
     SeriesStage series;
     series.begin(s_tile, s_bar, S.data, M.n_out);
 
+    // fit variable x = (1/q' - 1/q_c) q_c^2 / (proposal s.d.), y = SS' - SS_c, centred on the state at launch
+    // (the fit lives in the sampler between launches, SamplerDev::fit, and in shared memory during one)
+    if (li == 0) {
+        const bool kept = (D == 1) && S.fit && S.fit[17 * Cz + cc] != 0.0;
+        if (kept) {
+#pragma unroll
+            for (int k = 0; k < SPEC_FIT; k++) sur[k] = S.fit[k * Cz + cc];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 14; k++) sur[k] = 0.0;
+            const double xs = (D == 1) ? q[0] * q[0] / sqrt(L[0]) : 0.0;
+            sur[14] = 1.0 / q[0]; sur[15] = ss; sur[16] = xs;
+            sur[17] = ((D == 1) && q[0] > 0.0 && xs > 0.0 && xs < 1e300) ? 1.0 : -1.0;
+        }
+    }
+    __syncwarp();
+
     int it = 0;
     while (__any_sync(FULL_MASK, chain_ok && it < A.n_iters)) {
         const bool live = chain_ok && it < A.n_iters;
-        int rmax = live ? min(g, A.n_iters - it) : 0;
+        int rmax = live ? min(G, A.n_iters - it) : 0;
         if (COMPAT) rmax = min(rmax, A.adapt_interval - (int)((A.iter0 + it) % A.adapt_interval));
-        const bool mine = live && node > 0 && depth <= rmax;
-        // ---- proposal of this node: replay the path encoded in `node` ----
-        double qn[D], cur[D];
+        // ---- draws of iteration it + li (slot li of the group): the tree below reads them by shuffle ----
+        double dz[D], dlnu = 0.0, dgam = 1.0;
 #pragma unroll
-        for (int j = 0; j < D; j++) { cur[j] = q[j]; qn[j] = q[j]; }
-        bool reachable = mine;
-        for (int m = 1; m <= depth; m++) {
-            const unsigned int giter = (unsigned int)(A.iter0 + it + m - 1);
-            double z[D];
+        for (int j = 0; j < D; j++) dz[j] = 0.0;
+        if (li < rmax) {
+            const unsigned int giter = (unsigned int)(A.iter0 + it + li);
             double z0, z1;
             philox_normal2(key, gid, giter, 0u, z0, z1);
-            z[0] = z0;
-            if (D > 1) z[1] = z1;
-            if (D > 2) { philox_normal2(key, gid, giter, 1u, z0, z1); z[2] = z0; }
-            if (D == 1) {
-                qn[0] = cur[0] + sqrt(L[0]) * z[0];
-            } else {
-                qn[0] = cur[0] + L[0] * z[0];
-                qn[1] = cur[1] + L[1] * z[0] + L[2] * z[1];
-                qn[2] = cur[2] + L[3] * z[0] + L[4] * z[1] + L[5] * z[2];
+            dz[0] = z0;
+            if (D > 1) dz[1] = z1;
+            if (D > 2) { philox_normal2(key, gid, giter, 1u, z0, z1); dz[2] = z0; }
+            dlnu = log(philox_uniform(key, gid, giter, 2u));
+            dgam = philox_gamma(key, gid, giter, gshape);
+        }
+        // ---- predictor of this round ----
+        const bool have_fit = sur[17] > 0.0 && sur[12] != 0.0 && sur[13] != 0.0;
+        const double fc0 = sur[8], fc1 = sur[9], fc2 = sur[10];
+        const double rqc = sur[14], ss0 = sur[15], xs = sur[16];
+        const double rtau = have_fit ? rsqrt(2.0 * fmax(sur[11], 1e-300)) : 0.0;
+        const double p0 = fmin(fmax(((double)n_acc + 1.0) / ((double)nsolve + 2.0), 0.05), 0.95);
+        // ---- the tree: slot r of the group receives the r-th node, best first by reach probability ----
+        bool have = false, n_inb = false, n_exact = false;
+        int n_depth = 0, cA = -1, cR = -1;
+        double n_cur[D], qn[D], n_ssc = ss, n_s2c = s2, n_reach = 0.0, n_p = 0.0, n_sshat = ss, n_gam = 1.0;
+        double vA = -1.0, vR = -1.0, limit = INFINITY;
+#pragma unroll
+        for (int j = 0; j < D; j++) { n_cur[j] = q[j]; qn[j] = q[j]; }
+#pragma unroll 1
+        for (int r = 0; r < G; r++) {
+            // the open child with the largest reach (ties: lowest lane)
+            double bv = have ? fmax(vA, vR) : -1.0;
+            int bl = lane;
+            for (int off = 1; off < G; off <<= 1) {
+                const double ov = __shfl_xor_sync(FULL_MASK, bv, off);
+                const int ol = __shfl_xor_sync(FULL_MASK, bl, off);
+                if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
             }
-            if (m < depth) {
-                const bool took_accept = (node >> (depth - m - 1)) & 1;
-                if (took_accept) {
-                    bool inb_a = true;
+            const bool root_step = r == 0;
+            const bool take = root_step ? rmax >= 1 : bv > 0.0;
+            // what every lane would hand to its better child; the winner's offer is read by shuffle
+            const bool pickA = vA >= vR;
+            const double o_ssc = pickA ? n_sshat : n_ssc;
+            double o_s2;
+            {
+                const double bval = 0.5 * (A.n0 * n_s2c + o_ssc);
+                const double scale = 1.0 / bval;
+                o_s2 = 1.0 / (n_gam * scale);
+            }
+            double t_cur[D];
 #pragma unroll
-                    for (int j = 0; j < D; j++) inb_a = inb_a && (qn[j] > A.lo[j]) && (qn[j] < A.hi[j]);
-                    if (!inb_a) reachable = false;         // an out-of-bounds ancestor cannot have been accepted
+            for (int j = 0; j < D; j++) t_cur[j] = __shfl_sync(FULL_MASK, pickA ? qn[j] : n_cur[j], bl);
+            double t_ssc = __shfl_sync(FULL_MASK, o_ssc, bl);
+            double t_s2 = __shfl_sync(FULL_MASK, o_s2, bl);
+            int t_depth = __shfl_sync(FULL_MASK, n_depth + 1, bl);
+            bool t_exact = __shfl_sync(FULL_MASK, (!pickA && n_exact) ? 1 : 0, bl) != 0;
+            if (root_step) {
 #pragma unroll
-                    for (int j = 0; j < D; j++) cur[j] = qn[j];
+                for (int j = 0; j < D; j++) t_cur[j] = q[j];
+                t_ssc = ss; t_s2 = s2; t_depth = 1; t_exact = true; bv = 1.0;
+            }
+            if (!root_step && take && lane == bl) {
+                if (pickA) { vA = -1.0; cA = gbase + r; } else { vR = -1.0; cR = gbase + r; }
+            }
+            // draws of the new node's iteration
+            const int dsrc = gbase + min(max(t_depth, 1), G) - 1;
+            double zz[D];
+#pragma unroll
+            for (int j = 0; j < D; j++) zz[j] = __shfl_sync(FULL_MASK, dz[j], dsrc);
+            const double lnu_m = __shfl_sync(FULL_MASK, dlnu, dsrc);
+            const double gam_m = __shfl_sync(FULL_MASK, dgam, dsrc);
+            if (take && li == r) {
+                have = true;
+#pragma unroll
+                for (int j = 0; j < D; j++) n_cur[j] = t_cur[j];
+                n_ssc = t_ssc; n_s2c = t_s2; n_depth = t_depth; n_reach = bv; n_exact = t_exact; n_gam = gam_m;
+                if (D == 1) {
+                    qn[0] = n_cur[0] + sqrt(L[0]) * zz[0];       // L[0] is the proposal variance for d = 1
+                } else {
+                    qn[0] = n_cur[0] + L[0] * zz[0];
+                    qn[1] = n_cur[1] + L[1] * zz[0] + L[2] * zz[1];
+                    qn[2] = n_cur[2] + L[3] * zz[0] + L[4] * zz[1] + L[5] * zz[2];
                 }
-            }
-        }
-        bool inb = true;
+                n_inb = true;
 #pragma unroll
-        for (int j = 0; j < D; j++) inb = inb && (qn[j] > A.lo[j]) && (qn[j] < A.hi[j]);
-        const bool solve = reachable && inb;
-        // ---- stopping bound: exact for the root, generous for speculative nodes ----
-        double limit = INFINITY;
-        if (solve) {
-            if (node == 1) {
-                const double u = philox_uniform(key, gid, (unsigned int)(A.iter0 + it), 2u);
-                limit = ss - 2.0 * s2 * log(u);
-            } else {
-                limit = ss + 100.0 * s2;
+                for (int j = 0; j < D; j++) n_inb = n_inb && (qn[j] > A.lo[j]) && (qn[j] < A.hi[j]);
+                const double thr = n_ssc - 2.0 * n_s2c * lnu_m;
+                n_sshat = n_ssc;
+                if (!n_inb) {
+                    n_p = 0.0;                                   // an out-of-bounds proposal is never accepted
+                } else if (have_fit && qn[0] > 0.0) {
+                    const double x = (1.0 / qn[0] - rqc) * xs;
+                    n_sshat = ss0 + fma(x, fma(x, fc2, fc1), fc0);
+                    n_p = fmin(fmax(0.5 * erfc(-(thr - n_sshat) * rtau), 0.02), 0.98);
+                } else {
+                    n_p = p0;
+                }
+                const bool kids = n_depth < rmax;
+                vA = kids ? n_reach * n_p : -1.0;
+                vR = kids ? n_reach * (1.0 - n_p) : -1.0;
+                limit = n_inb ? (n_exact ? thr : ss + 100.0 * s2) : INFINITY;
             }
         }
+        const bool inb = have && n_inb;
+        const bool solve = inb;
         const double pa = (D == 3) ? qn[0] : A.a0;
         const double pb = (D == 3) ? qn[1] : A.b0;
         series.start_solve();
@@ -1269,11 +1377,59 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
         const int oflags = (inb ? 1 : 0) | (solve ? 2 : 0) | ((o.status & RSFM_CHAIN_EARLY) ? 4 : 0) |
                            ((o.status & ~RSFM_CHAIN_EARLY) << 4);
 
+        // ---- the fit learns from every solve of the tree that ran to the end ----
+        // (two groups of one warp may be in different states: every shuffle and warp barrier below is executed by all
+        //  lanes, only the arithmetic in between is conditional)
+        if (D == 1) {
+            const bool use = sur[17] > 0.0;
+            const bool pt = use && solve && o.status == 0 && qn[0] > 0.0 && o.sse < 1e300;
+            const bool had_fit = sur[12] != 0.0;
+            const double x = pt ? (1.0 / qn[0] - sur[14]) * sur[16] : 0.0, y = pt ? o.sse - sur[15] : 0.0;
+            const double res = (pt && had_fit) ? y - fma(x, fma(x, sur[10], sur[9]), sur[8]) : 0.0;
+            double mo[10] = {pt ? 1.0 : 0.0, x, x * x, x * x * x, (x * x) * (x * x), y, x * y, (x * x) * y,
+                             res * res, (pt && had_fit) ? 1.0 : 0.0};
+            for (int off = 1; off < G; off <<= 1) {
+#pragma unroll
+                for (int k = 0; k < 10; k++) mo[k] += __shfl_xor_sync(FULL_MASK, mo[k], off);
+            }
+            // (the sums are the same bits in every lane of the group: each butterfly level adds the same two numbers)
+            const double n_round = mo[0];
+#pragma unroll
+            for (int k = 0; k < 8; k++) mo[k] += 0.7 * sur[k];                   // the fit forgets older rounds
+            double tau2 = sur[11], has_tau = sur[13];
+            if (mo[9] > 0.0) {
+                const double msr = mo[8] / mo[9];
+                tau2 = has_tau != 0.0 ? 0.7 * tau2 + 0.3 * msr : msr;
+                has_tau = 1.0;
+            }
+            // normal equations [[S0 S1 S2] [S1 S2 S3] [S2 S3 S4]] c = (T0 T1 T2) by elimination
+            const double l10 = mo[1] / mo[0], l20 = mo[2] / mo[0];
+            const double a11 = mo[2] - l10 * mo[1], a12 = mo[3] - l10 * mo[2], b1 = mo[6] - l10 * mo[5];
+            const double a22 = mo[4] - l20 * mo[2], b2 = mo[7] - l20 * mo[5];
+            const double l21 = a12 / a11;
+            const double a22p = a22 - l21 * a12, b2p = b2 - l21 * b1;
+            const double c2 = b2p / a22p, c1 = (b1 - a12 * c2) / a11, c0 = (mo[5] - mo[1] * c1 - mo[2] * c2) / mo[0];
+            const bool valid = mo[0] >= 6.0 && a11 > 1e-9 * mo[2] && a22p > 1e-9 * mo[4] && c2 > 0.0 &&
+                               fabs(c0) < 1e300 && fabs(c1) < 1e300 && c2 < 1e300;
+            // first fit: no residual against an earlier fit exists; take the in-sample one (n - 3 degrees of freedom)
+            const double r0 = (pt && valid) ? y - fma(x, fma(x, c2, c1), c0) : 0.0;
+            double rr = r0 * r0;
+            for (int off = 1; off < G; off <<= 1) rr += __shfl_xor_sync(FULL_MASK, rr, off);
+            if (has_tau == 0.0 && valid && n_round > 3.5) { tau2 = rr / (n_round - 3.0); has_tau = 1.0; }
+            __syncwarp();
+            if (use && li == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) sur[k] = mo[k];
+                sur[8] = c0; sur[9] = c1; sur[10] = c2; sur[11] = tau2; sur[12] = valid ? 1.0 : 0.0; sur[13] = has_tau;
+            }
+            __syncwarp();
+        }
+
         // ---- resolution: every lane of the group walks the realised path (identical arithmetic) ----
-        int j = 1, ndone = 0;
-        bool stopped = !live;
-        for (int m = 1; m <= g; m++) {
-            const int src = gbase + (j & (G - 1));
+        int cl = gbase, ndone = 0;
+        bool stopped = !live || rmax < 1;
+        for (int m = 1; m <= G; m++) {
+            const int src = cl >= 0 ? cl : lane;
             double pq[D];
 #pragma unroll
             for (int jj = 0; jj < D; jj++) pq[jj] = __shfl_sync(FULL_MASK, qn[jj], src);
@@ -1281,6 +1437,7 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
             const double plim = __shfl_sync(FULL_MASK, limit, src);
             const int pf = __shfl_sync(FULL_MASK, oflags, src);
             const unsigned int prhs = __shfl_sync(FULL_MASK, o.nrhs, src), pstep = __shfl_sync(FULL_MASK, o.nstep, src);
+            const int pcA = __shfl_sync(FULL_MASK, cA, src), pcR = __shfl_sync(FULL_MASK, cR, src);
             if (stopped || m > rmax) { stopped = true; continue; }
             const unsigned int giter = (unsigned int)(A.iter0 + it + m - 1);
             const bool p_inb = pf & 1, p_early = pf & 4;
@@ -1338,8 +1495,9 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
                     for (int b = 0; b <= a; b++) sqq[t++] += q[a] * q[b];
             }
             if (COMPAT && writer) S.ring[(size_t)((A.iter0 + it + m) % A.adapt_interval) * Cz + chain] = q[0];
-            j = acc ? 2 * j + 1 : 2 * j;
+            cl = acc ? pcA : pcR;                           // the node the realised outcome leads to, if it is in the tree
             ndone++;
+            if (cl < 0) stopped = true;
         }
         it += ndone;
         if (COMPAT) {
@@ -1361,12 +1519,16 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
                 const double vnew = 2.38 * 2.38 / 2.0 * v;
                 if (vnew > 0.0) lnew = sqrt(vnew);
             }
-            L[0] = __shfl_sync(FULL_MASK, lnew, gbase + 1);
+            L[0] = __shfl_sync(FULL_MASK, lnew, gbase);
         }
     }
 
     if (writer) {
         const int c = chain;
+        if (D == 1 && S.fit) {
+#pragma unroll
+            for (int k = 0; k < SPEC_FIT; k++) S.fit[k * Cz + c] = sur[k];
+        }
 #pragma unroll
         for (int j = 0; j < D; j++) S.q[j * Cz + c] = q[j];
         S.sse[c] = ss; S.sigma2[c] = s2;
@@ -1383,7 +1545,7 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
     }
 }
 
-// depth of the speculation tree for C chains: the largest g with C 2^g threads <= one warp per SMSP
+// lanes per chain (2^g) of the speculative kernel for C chains; 0 = the one-thread-per-chain kernel
 static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
 {
     if (A.deterministic) return 0;
@@ -1395,12 +1557,18 @@ static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
     if (want >= 2 && want <= 5) return want;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-    const long long cap = (long long)sms * 4 * 32;            // one warp per SMSP (measured optimum)
+    // The largest tree that leaves at most two warps per SM sub-partition (all the 255-register kernel can hold).
+    // Round 1 (balanced trees, a round advanced g iterations with 2^g lanes) stopped at one warp: the second warp of a
+    // sub-partition only shares its FP64 pipe.  With the predictor a round advances nearly as many iterations as the
+    // group has lanes, so the second warp's lanes pay (profiles/microbench/spec_predict.py: 1,024 chains 16.6 -> 17.9 M
+    // chain-iterations/s from near starts, 10.4 -> 16.7 M from the prior's width; 2,048: 18.1 -> 20.9 M; 4,096: 19.0 -> 22.9 M).
+    // Without the fit (d = 3) the trees follow the acceptance rate only and the round-1 rule stands: one warp per
+    // sub-partition, except that four lanes per chain still pay at two.
+    const long long one = (long long)sms * 4 * 32;
+    const long long cap = s->cfg.n_params == 1 ? 2 * one : one;
     int g = 0;
     while (g < 5 && ((long long)s->C << (g + 1)) <= cap) g++;
-    // measured: a 3-node tree (4 lanes per chain) still pays at up to two warps per sub-partition
-    // (C = 8,192: 13.0 M vs 9.1 M solves/s), deeper trees do not
-    if (g < 2 && ((long long)s->C << 2) <= 2 * cap) g = 2;
+    if (g < 2 && ((long long)s->C << 2) <= 2 * one) g = 2;
     return g >= 2 ? g : 0;
 }
 
@@ -1555,6 +1723,8 @@ extern "C" int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double
     if (sse_dev) CUDA_TRY(cudaMemcpyAsync(s->d.sse, sse_dev, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
     if (sigma2_dev) CUDA_TRY(cudaMemcpyAsync(s->d.sigma2, sigma2_dev, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
     if (chol_dev) CUDA_TRY(cudaMemcpyAsync(s->d.chol, chol_dev, sizeof(double) * tri(d) * C, cudaMemcpyDeviceToDevice, st));
+    // the predictor of the speculative kernel starts over around the new state (it never affects results)
+    if (s->d.fit) CUDA_TRY(cudaMemsetAsync(s->d.fit, 0, sizeof(double) * SPEC_FIT * C, st));
     if (iteration >= 0) s->iteration = iteration;
     return RSFM_OK;
 }

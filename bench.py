@@ -306,6 +306,7 @@ class Bench:
         cfg.n_params, cfg.n_prior_len = d, 3
         cfg.adapt_mode = pkg._lib.ADAPT_POOLED if pooled else pkg._lib.ADAPT_NONE
         cfg.adapt_interval = interval
+        cfg.spec_depth = args.spec_depth
         for j in range(d):
             cfg.lo[j], cfg.hi[j] = w["lo"][j], w["hi"][j]
         stream = pkg._lib.current_stream(torch, dev)
@@ -417,7 +418,8 @@ class Bench:
                 out = mc = None                         # the previous job's host arrays are consumed, not kept
                 t0 = time.perf_counter()
                 common = dict(nsamples=K * iters, verbose=False, seed=args.seed, device=dev, param_names=names, bounds=bounds,
-                              adapt=w["adapt"], adapt_start=w.get("adapt_start", 100), adapt_interval=interval)
+                              adapt=w["adapt"], adapt_start=w.get("adapt_start", 100), adapt_interval=interval,
+                              spec_depth=args.spec_depth)
                 if world > 1 and pooled:                # chains sharded over the ranks, statistics pooled by NCCL
                     mc = pkg.MCMC(model, pinned.numpy(), w["truth"][2], ["Uniform", w["lo"][-1], w["hi"][-1]],
                                   start_values(w, total_chains, (0, total_chains)), n_chains=total_chains, shard=True, **common)
@@ -595,6 +597,8 @@ def main():
                          "never affects results")
     ap.add_argument("--round-packing", type=int, default=0, help="d = 3 kernel: 0 auto (on), 1 off; never affects results")
     ap.add_argument("--block-threads", type=int, default=0, help="threads per block of the one-thread-per-chain kernels (0 auto)")
+    ap.add_argument("--spec-depth", type=int, default=0,
+                    help="few-chain workloads: lanes per chain of the speculative kernel = 2^depth (0 auto, 1 off, 2..5); never affects results")
     ap.add_argument("--seed", type=int, default=20240)
     ap.add_argument("--e2e-steps", type=int, default=2, help="timed public-API calls (each = the whole job)")
     ap.add_argument("--cpu-iters", type=int, default=12, help="iterations per chain in the cpu_baseline sample")
