@@ -1426,10 +1426,22 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
         }
 
         // ---- resolution: every lane of the group walks the realised path (identical arithmetic) ----
+        // the acceptance uniform and the gamma draw of iteration it + li once more, one iteration per lane (not kept
+        // across the solve: registers), read by shuffle below instead of being drawn by every lane at every level
+        double du = 0.5, dlnu2 = 0.0, dgam2 = 1.0;
+        if (li < rmax) {
+            const unsigned int giter = (unsigned int)(A.iter0 + it + li);
+            du = philox_uniform(key, gid, giter, 2u);
+            dlnu2 = log(du);
+            dgam2 = philox_gamma(key, gid, giter, gshape);
+        }
         int cl = gbase, ndone = 0;
         bool stopped = !live || rmax < 1;
         for (int m = 1; m <= G; m++) {
             const int src = cl >= 0 ? cl : lane;
+            const int dsrc = gbase + m - 1;
+            const double u_m = __shfl_sync(FULL_MASK, du, dsrc), lnu_m = __shfl_sync(FULL_MASK, dlnu2, dsrc);
+            const double g0 = __shfl_sync(FULL_MASK, dgam2, dsrc);
             double pq[D];
 #pragma unroll
             for (int jj = 0; jj < D; jj++) pq[jj] = __shfl_sync(FULL_MASK, qn[jj], src);
@@ -1444,8 +1456,8 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
             bool acc = false;
             double u = nan("");
             if (p_inb) {
-                u = philox_uniform(key, gid, giter, 2u);
-                const double lnu = log(u);
+                u = u_m;
+                const double lnu = lnu_m;
                 const double thr = ss - 2.0 * s2 * lnu;
                 // a node stopped at its bound is decided only if that bound is at least the threshold
                 // (the root's bound IS its threshold; m > 1 also guarantees progress if the state is NaN)
@@ -1464,7 +1476,6 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
                     n_acc++;
                 }
             }
-            const double g0 = philox_gamma(key, gid, giter, gshape);
             {
                 const double bval = 0.5 * (A.n0 * s2 + ss);
                 const double scale = 1.0 / bval;
