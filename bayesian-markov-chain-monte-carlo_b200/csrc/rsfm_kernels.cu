@@ -495,7 +495,7 @@ static int tri(int d) { return d * (d + 1) / 2; }
 // c0..c2 (8-10), mean squared residual (11), "fit valid" (12), "residual known" (13), centre 1/q_c, SS_c and scale
 // of the fit variables (14-16), state (17: 0 = not set up, 1 = in use, -1 = not usable for this chain).
 static const int SPEC_FIT = 18;
-static const int SPEC_MAX_CHAINS = 148 * 4 * 32 * 2 / 4;      // most chains the speculative kernel is chosen for
+static const int SPEC_MAX_CHAINS = 148 * 4 * 32 * 2 / 2;      // most chains the speculative kernel is chosen for
 
 // ---------------------------------------------------------------------------
 // chain groups
@@ -1199,7 +1199,7 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ double s_ltab[4 * LTAB_STRIDE];
     __shared__ double s_lpriv[11 * 128];
-    // the fit of SS(q), one slot per group (<= 32 groups per block, g >= 2): moments S0..S4 of x and T0..T2 of
+    // the fit of SS(q), one slot per group (one-warp blocks: <= 16 groups per block): moments S0..S4 of x and T0..T2 of
     // x^k y, coefficients c0..c2, mean squared residual, "fit valid", "residual known", and the centre / scale of the
     // fit variables (kept here, not in registers: nothing of the predictor is live across the solve)
     __shared__ double s_sur[32 * SPEC_FIT];
@@ -1562,7 +1562,7 @@ static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
     if (A.deterministic) return 0;
     if (s->cfg.sampled_param == RSFM_PARAM_K1) return 0;   // k1 chains: one-thread-per-chain kernel only
     if (s->cfg.adapt_mode == RSFM_ADAPT_COMPAT && s->cfg.n_params != 1) return 0;
-    if (s->cfg.n_out > 2 * SERIES_TILE) return 0;          // streamed series: block barriers, no speculation
+    // (a streamed series, n_out > 1,024, is fine: the kernel runs one-warp blocks, its tile barriers are warp-wide)
     const int want = s->cfg.spec_depth;
     if (want == 1) return 0;
     if (want >= 2 && want <= 5) return want;
@@ -1579,8 +1579,10 @@ static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
     const long long cap = s->cfg.n_params == 1 ? 2 * one : one;
     int g = 0;
     while (g < 5 && ((long long)s->C << (g + 1)) <= cap) g++;
-    if (g < 2 && ((long long)s->C << 2) <= 2 * one) g = 2;
-    return g >= 2 ? g : 0;
+    if (g < 2 && s->cfg.n_params != 1 && ((long long)s->C << 2) <= 2 * one) g = 2;
+    // d = 1: two lanes per chain (root + its likelier child) still pay -- the one-thread-per-chain kernel is latency
+    // bound at one warp per sub-partition (9,473 .. 18,944 chains; cfg 4: 16,384)
+    return (g >= 2 || (g == 1 && s->cfg.n_params == 1)) ? g : 0;
 }
 
 extern "C" int rsfm_chain_groups(const rsfm_sampler *s) { return s ? s->n_groups : -1; }
@@ -1619,7 +1621,7 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
     // launch per group, and are NOT joined here -- the caller's stream is ordered behind them by the next call on
     // this sampler that needs their results (rsfm_pooled_partials and every getter / setter; rsfm_join).
     const bool k1p = s->cfg.sampled_param == RSFM_PARAM_K1;
-    if (s->n_groups > 1 && g < 2 && !A.deterministic && !vs) {
+    if (s->n_groups > 1 && g < 1 && !A.deterministic && !vs) {
         int rc = fork_groups(s, stream);
         if (rc) return rc;
         const int per = C / s->n_groups, ggrid = (per + block - 1) / block;
@@ -1642,9 +1644,11 @@ static int launch_run(rsfm_sampler *s, RunArgs &A, cudaStream_t stream)
         if (rc) return rc;
         s->need_fork = 1;                 // this launch writes the state on the caller's stream
     }
-    if (g >= 2) {
+    if (g >= 1) {
         const long long threads = (long long)C << g;
-        const int sblock = threads <= 148 * 32 * 4 ? 32 : 128;
+        // one-warp blocks: up to 1,184 warps (two per sub-partition) are spread evenly over the SMs -- 128-thread
+        // blocks put two blocks on 108 SMs and one on 40 at 1,024 warps, and the launch waits for the full ones
+        const int sblock = 32;
         const int sgrid = (int)((threads + sblock - 1) / sblock);
 #define RSFM_SPEC(D, CO)                                                                                              \
     { if (vs) rsf_mcmc_spec_kernel<D, CO, true><<<sgrid, sblock, 0, stream>>>(M, C, s->d, A, g);                      \

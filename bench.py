@@ -459,14 +459,14 @@ class Bench:
         # 8 B sigma^2 + 1 B flag per chain, and the 8 N B series once per block
         per_launch_iters = interval if pooled else iters
         n_kernel_launches = K * (iters // per_launch_iters if pooled else 1)
-        threads = cpg << spec_g if spec_g >= 2 else cpg
+        threads = cpg << spec_g if spec_g >= 1 else cpg
         block = 32 if (w["loading"] == "vstep" or threads <= 148 * 32) else 64 if threads <= 148 * 128 else 128
-        if spec_g >= 2:
+        if spec_g >= 1:
             block = 32 if threads <= 148 * 32 * 4 else 128
         nblocks = (threads + block - 1) // block
         alg_bytes = cpg * 64.0 + per_launch_iters * cpg * (8.0 * d + 9.0) + nblocks * 8.0 * w["n_out"]
         launch_s = kern_s / n_kernel_launches
-        if spec_g >= 2:
+        if spec_g >= 1:
             kernel = f"rsf_mcmc_spec_kernel<{d},false,{'true' if w['loading'] == 'vstep' else 'false'}> (speculation depth {spec_g}: {1 << spec_g} lanes per chain)"
         else:
             kernel = f"rsf_mcmc_kernel<{d},false,{'true' if w['loading'] == 'vstep' else 'false'}> (one thread per chain)"

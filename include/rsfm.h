@@ -107,8 +107,8 @@ typedef struct rsfm_cfg {
     int32_t n_prior_len;                 /* len(qpriors): 3 list form, 2 dict form, MCMC.py:261 (q5) */
     int32_t adapt_interval;              /* MCMC.py:58 */
     int32_t adapt_mode;                  /* RSFM_ADAPT_* */
-    int32_t spec_depth;                  /* speculation tree depth of rsfm_run: 0 auto (by chain count),
-                                            1 off, 2..5 forced; results never depend on it */
+    int32_t spec_depth;                  /* speculative kernel of rsfm_run, 2^spec_depth lanes per chain: 0 auto (by
+                                            chain count), 1 off, 2..5 forced; results never depend on it */
     int32_t observable;                  /* RSFM_OBS_* */
     int32_t solver_variant;              /* RSFM_VARIANT_* (tests / tuning; results agree within the parity gates) */
     int32_t stiff_exact;                 /* stiff variant: score every step that left the fast ranges with the
@@ -201,9 +201,10 @@ int rsfm_run(rsfm_sampler *s, int32_t n_iters,
 int rsfm_chain_groups(const rsfm_sampler *s);
 int rsfm_join(rsfm_sampler *s, void *stream);
 
-/* Depth g of the speculation tree rsfm_run will use for this sampler (0 = plain
- * one-thread-per-chain kernel; g >= 2: 2^g lanes per chain evaluate the next g
- * iterations' proposals concurrently).  Never affects results. */
+/* log2 of the lanes per chain rsfm_run will use for this sampler (0 = plain one-thread-per-chain
+ * kernel; g >= 1: 2^g lanes evaluate 2^g nodes of the tree of the chain's next iterations
+ * concurrently, chosen best-first by a predictor of the accept / reject decisions).  Never
+ * affects results. */
 int rsfm_spec_depth(const rsfm_sampler *s);
 
 /* Same loop with host-supplied randomness:

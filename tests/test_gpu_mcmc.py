@@ -936,3 +936,42 @@ def test_round_packing_gives_the_same_chains(cuda, pkg, orc):
         assert np.array_equal(acc[:, ch], acc_o), ch
         assert np.array_equal(samples[:, :, ch], chain_o[1:]), ch
         assert np.allclose(s2[:, ch], s2_o[1:], rtol=1e-8, atol=0)
+
+
+@pytest.mark.parametrize("n_steps, t_end, c, loading", [(40, 4.0, 9600, "sine_decay"), (1100, 110.0, 6, "sine_decay"),
+                                                       (2100, 210.0, 9500, "vstep")])
+def test_two_lane_groups_and_streamed_series_in_the_speculative_kernel(cuda, pkg, n_steps, t_end, c, loading):
+    """Round 2 widened the speculative kernel: two lanes per chain (9,473 .. 18,944 chains, where the one-thread-per-
+    chain kernel runs one latency-bound warp per sub-partition) and a streamed series (n_out > 1,024; one-warp blocks,
+    the tile barriers are warp-wide).  Chains must be those of the sequential kernel bit for bit."""
+    model = pkg.RateStateModel(number_time_steps=n_steps, end_time=t_end)
+    if loading == "vstep":
+        model.loading, model.vstep_period, model.vstep_factor = "vstep", 50.0, 10.0
+        truth, q0, lo, hi = 0.5, np.random.default_rng(2).uniform(0.3, 0.9, c), 0.05, 5.0
+    else:
+        truth, q0, lo, hi = 1325.0, np.random.default_rng(2).uniform(900.0, 2000.0, c), 0.0, 1e4
+    model.Dc = truth
+    np.random.seed(7)
+    _, _, data = model.evaluate()
+    outs = []
+    for depth in (1, 0):
+        mc = pkg.MCMC(model, data, truth, ["Uniform", lo, hi], q0, nsamples=8, n_chains=c, verbose=False, seed=5,
+                      spec_depth=depth)
+        out = mc.sample(False)
+        outs.append((out, mc.std2.copy(), mc.accepts.copy(), mc.stats))
+    assert outs[0][3]["nsolves_executed"] == outs[0][3]["nsolves"]
+    assert outs[1][3]["nsolves_executed"] > outs[1][3]["nsolves"]            # the speculative kernel did run
+    if loading == "vstep":
+        # Stiff variant: whether a lane's step is scored by the fast or by the general-range stages depends on its
+        # warp-mates (rsf_interval_general tries the fast step when ANY lane starts in range), the two agree to
+        # rounding, and the stability-limited solve amplifies that to ~1e-6 .. 1e-4 of the sum of squares (DESIGN 5).
+        # So the two kernels agree chain by chain at the level of decisions, not of bits.
+        same = (outs[0][2] == outs[1][2]).all(axis=1)
+        assert same.mean() > 0.98
+        assert np.array_equal(outs[0][0][same], outs[1][0][same])
+        assert np.allclose(outs[0][1][same], outs[1][1][same], rtol=1e-3, atol=0)
+    else:
+        assert outs[1][3]["nsolves"] == outs[0][3]["nsolves"]
+        for a, b in zip(outs[0][:3], outs[1][:3]):
+            assert np.array_equal(a, b)
+    assert 0 < outs[0][2].mean() < 1
