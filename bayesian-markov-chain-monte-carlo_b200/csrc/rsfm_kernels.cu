@@ -1560,6 +1560,7 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
 static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
 {
     if (A.deterministic) return 0;
+    if (A.n_iters == 1) return 0;                          // nothing to look ahead to (rsfm_spec_depth asks with 0)
     if (s->cfg.sampled_param == RSFM_PARAM_K1) return 0;   // k1 chains: one-thread-per-chain kernel only
     if (s->cfg.adapt_mode == RSFM_ADAPT_COMPAT && s->cfg.n_params != 1) return 0;
     // (a streamed series, n_out > 1,024, is fine: the kernel runs one-warp blocks, its tile barriers are warp-wide)

@@ -17,7 +17,9 @@ steps of a workload are its stated number of iterations, started from the start 
     cfg2   configs[1]: 1,024 chains, Dc posterior, no adaptation (list priors as main.py), 10 x 200 iterations
     cfg4r  configs[3] reduced: velocity-step loading x10 every 1,000 s, stiff regime (Dc ~ 0.05), 16,384 chains,
            series of 20,000 points (2,000 s: one velocity step; the stated 100,000 points are a parity test and
-           profiles/ record, 5.5 s of latency per solve), 4 x 1 iterations
+           profiles/ record, 4-5 s of latency per solve), 4 x 1 iterations (a launch of one iteration has nothing
+           to look ahead to and runs the one-thread-per-chain kernel; longer launches use two lanes per chain,
+           +25 %: profiles/r2/pred/)
 At N = 1 the line is the cfg3 record and carries cfg2 / cfg5 (one shard) / cfg4r as `sub_records`, each with its own
 roofline (flops from ITS counters over ITS kernel time) and its own `traffic` (ncu capture of the same launch,
 profiles/ncu_traffic.json).  `--workload X` runs one workload alone as the headline.
@@ -462,7 +464,7 @@ class Bench:
         threads = cpg << spec_g if spec_g >= 1 else cpg
         block = 32 if (w["loading"] == "vstep" or threads <= 148 * 32) else 64 if threads <= 148 * 128 else 128
         if spec_g >= 1:
-            block = 32 if threads <= 148 * 32 * 4 else 128
+            block = 32                                   # the speculative kernel runs one-warp blocks
         nblocks = (threads + block - 1) // block
         alg_bytes = cpg * 64.0 + per_launch_iters * cpg * (8.0 * d + 9.0) + nblocks * 8.0 * w["n_out"]
         launch_s = kern_s / n_kernel_launches

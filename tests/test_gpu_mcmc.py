@@ -975,3 +975,17 @@ def test_two_lane_groups_and_streamed_series_in_the_speculative_kernel(cuda, pkg
         for a, b in zip(outs[0][:3], outs[1][:3]):
             assert np.array_equal(a, b)
     assert 0 < outs[0][2].mean() < 1
+
+
+def test_predictor_keeps_the_speculative_work_on_the_realised_path(cuda, pkg):
+    """Regression guard for the round-2 predictor: with the quadratic-in-1/Dc fit of the sum of squares,
+    nearly every node of a chain's 32-lane tree lies on the path the chain then takes.  The balanced trees of round 1
+    executed 6.2 solves per decided one at 32 lanes (3.6 at 16); the gate leaves a wide margin."""
+    g = load_golden("sse_grid.json")
+    model = pkg.RateStateModel()
+    c = 64
+    q0 = np.random.default_rng(4).uniform(300.0, 4000.0, c)
+    mc = pkg.MCMC(model, g["data"], 1350.0, ["Uniform", 0.0, 1e4], q0, nsamples=400, n_chains=c, verbose=False, seed=3)
+    mc.sample(False)
+    assert mc.stats["nsolves_executed"] < 1.5 * mc.stats["nsolves"], mc.stats
+    assert 0.05 < float(np.mean(mc.acceptance_ratio)) < 0.95
