@@ -104,6 +104,35 @@ def test_facade_constructor_mirrors_reference(pkg):
         pkg.MCMC(m, data, 1.0, [0, 0, 1], 1.0, param_names=("x",))
     with pytest.raises(TypeError):
         m.evaluate()                                       # Dc not set
+    # named parameters of the build: Dc, (a, b, Dc), k1 -- nothing else, and the reference's windowed
+    # adaptation exists for one parameter only
+    for names in (("Dc",), ("a", "b", "Dc"), ("k1",)):
+        assert pkg.MCMC(m, data, 1.0, ["Uniform", 0.0, 1.0], 1.0, param_names=names).param_names == names
+    with pytest.raises(ValueError):
+        pkg.MCMC(m, data, 1.0, ["Uniform", 0.0, 1.0], 1.0, param_names=("k1", "Dc"))
+    with pytest.raises(ValueError):
+        pkg.MCMC(m, data, 1.0, {1: 0.0, 2: 1.0}, 1.0, param_names=("a", "b", "Dc"))
+    assert pkg.MCMC(m, data, 1.0, {1: 0.0, 2: 0.01}, 1e-3, param_names=("k1",)).compat_adapt
+
+
+def test_cfg_struct_matches_the_header(pkg):
+    """The ctypes mirror of struct rsfm_cfg names every field of include/rsfm.h, in order (a drifted mirror would
+    silently shift every later field)."""
+    import os
+    import re
+    from conftest import ROOT
+    src = open(os.path.join(ROOT, "include", "rsfm.h")).read()
+    body = src[src.index("typedef struct rsfm_cfg {"):src.index("} rsfm_cfg;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for stmt in body.split(";"):
+        stmt = stmt.replace("typedef struct rsfm_cfg {", "").strip()
+        if not stmt:
+            continue
+        decl = stmt.split(None, 1)[1] if not stmt.startswith("const") else stmt.split("*", 1)[1]
+        for n in decl.split(","):
+            names.append(re.sub(r"\[.*\]", "", n).replace("*", "").strip())
+    assert names == [f[0] for f in pkg._lib.RsfmCfg._fields_]
 
 
 def test_qstart_shapes(pkg):
