@@ -367,6 +367,8 @@ class Bench:
         # the timed job starts from the start values: K steps = the first K*iters iterations of every chain
         handle, pool = make_sampler()
         spec_g = int(lib.rsfm_spec_depth(handle))
+        if (interval if pooled else iters) == 1:
+            spec_g = 0                                  # a launch of one iteration runs the one-thread-per-chain kernel
         n_groups = int(lib.rsfm_chain_groups(handle))
         tot0 = totals(handle)
         launches[0] = launches[1] = 0
