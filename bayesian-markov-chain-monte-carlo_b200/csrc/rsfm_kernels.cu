@@ -508,6 +508,8 @@ static int pick_groups(const rsfm_cfg *c, int C, uint64_t chain_id0)
     if (c->adapt_mode != RSFM_ADAPT_POOLED || c->chain_groups == 1) return 1;
     if (stiff_variant(c) || c->n_out > 2 * SERIES_TILE) return 1;
     if (chain_id0 % RSFM_POOL_GROUP != 0) return 1;
+    // samplers the speculative kernel serves (it runs on the caller's stream) have no groups
+    if (c->spec_depth >= 2 || (c->spec_depth == 0 && c->n_params == 1 && C <= SPEC_MAX_CHAINS)) return 1;
     int g = c->chain_groups >= 2 ? c->chain_groups : 4;
     while (g > 1 && (C % (g * RSFM_POOL_GROUP) != 0 || C / g < 8192)) g--;
     return g;
@@ -1451,7 +1453,6 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
             const unsigned int prhs = __shfl_sync(FULL_MASK, o.nrhs, src), pstep = __shfl_sync(FULL_MASK, o.nstep, src);
             const int pcA = __shfl_sync(FULL_MASK, cA, src), pcR = __shfl_sync(FULL_MASK, cR, src);
             if (stopped || m > rmax) { stopped = true; continue; }
-            const unsigned int giter = (unsigned int)(A.iter0 + it + m - 1);
             const bool p_inb = pf & 1, p_early = pf & 4;
             bool acc = false;
             double u = nan("");
@@ -1984,6 +1985,8 @@ static int install_factor(rsfm_sampler *s, int slot, cudaStream_t st)
 {
     const int T = tri(s->cfg.n_params);
     if (s->n_groups > 1) {
+        // iterations that ran on the caller's stream (host-supplied draws) must be over before a group installs
+        { int rc_ = fork_groups(s, st); if (rc_) return rc_; }
         const int per = s->C / s->n_groups;
         for (int g = 0; g < s->n_groups; g++) {
             CUDA_TRY(cudaStreamWaitEvent(s->gstream[g], s->fac_event[slot], 0));

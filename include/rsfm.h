@@ -118,6 +118,8 @@ typedef struct rsfm_cfg {
     int32_t chain_groups;                /* RSFM_ADAPT_POOLED only: serve the chains by this many launches on the
                                             sampler's own streams (0 auto: up to 4 when >= 8,192 chains each, group
                                             boundaries on multiples of RSFM_POOL_GROUP; 1 off); see rsfm_join.
+                                            A sampler the speculative kernel serves (spec_depth >= 2, or auto with
+                                            n_params = 1 and <= 18,944 chains) has one group.
                                             Results never depend on it */
     int32_t round_packing;               /* d = 3 one-thread-per-chain kernel: pack the in-bounds proposals of a block into
                                             its lowest threads at the start of every solve round (0 auto = on for

@@ -843,6 +843,7 @@ def test_rsfm_join_orders_the_callers_stream_behind_the_chain_groups(cuda, pkg):
     for groups, use_side in ((1, False), (2, False), (2, True)):
         cfg = pkg.RateStateModel().to_cfg()
         cfg.adapt_mode, cfg.chain_groups = pkg._lib.ADAPT_POOLED, groups
+        cfg.spec_depth = 1            # one thread per chain (16,384 chains would get two lanes each, and then no groups)
         st = torch.cuda.Stream() if use_side else torch.cuda.current_stream()
         with torch.cuda.stream(st):
             h = lib.rsfm_create(C.byref(cfg), c, 3, 0)
