@@ -445,7 +445,7 @@ struct SamplerDev {
     double *chol;       // [d(d+1)/2][C]; d = 1: proposal variance (as the reference stores it)
     double *ring;       // [adapt_interval][C] last samples, COMPAT adaptation (d = 1)
     double *suff;       // [d + d(d+1)/2][C] per-chain sums for POOLED adaptation
-    double *fit;        // [SPEC_FIT][C] predictor state of the speculative kernel (d = 1, few chains), else unused
+    double *fit;        // [SPEC_FIT or SPEC_FIT3][C] predictor state of the speculative kernel (few chains), else unused
     double *data;       // [n_out] padded to an even count
     double *nom;        // [n_out][NOM_STRIDE] nominal loading table (loading_table_kernel)
     unsigned int *accepted;        // [C]
@@ -487,6 +487,7 @@ struct rsfm_sampler {
     double *fac_buf[2];            // proposal factor of the pooled update, double-buffered for the group installs
     int fac_parity;
     int staged;                    // slot of a factor formed by rsfm_pooled_update(install = 2) and not installed yet, or -1
+    int fit_rows;                  // rows of d.fit (SPEC_FIT, SPEC_FIT3, or 0 when the sampler keeps no predictor state)
 };
 
 static int tri(int d) { return d * (d + 1) / 2; }
@@ -495,6 +496,10 @@ static int tri(int d) { return d * (d + 1) / 2; }
 // c0..c2 (8-10), mean squared residual (11), "fit valid" (12), "residual known" (13), centre 1/q_c, SS_c and scale
 // of the fit variables (14-16), state (17: 0 = not set up, 1 = in use, -1 = not usable for this chain).
 static const int SPEC_FIT = 18;
+// d = 3: the fit is a full quadratic in t = (1/a, b/a, 1/Dc) (centred, scaled): normal matrix P (55 entries, upper
+// triangle by rows; 0-54), right-hand side R (55-64), coefficients (65-74), mean squared residual (75), "fit valid"
+// (76), "residual known" (77), centre (78-80) and scale (81-83) of t, SS_c (84), state as above (85), padding.
+static const int SPEC_FIT3 = 88;
 static const int SPEC_MAX_CHAINS = 148 * 4 * 32 * 2 / 2;      // most chains the speculative kernel is chosen for
 
 // ---------------------------------------------------------------------------
@@ -555,8 +560,9 @@ extern "C" rsfm_sampler *rsfm_create(const rsfm_cfg *cfg, int32_t C, uint64_t se
     const size_t o_q = take(sizeof(double) * d * Cz), o_sse = take(sizeof(double) * Cz), o_s2 = take(sizeof(double) * Cz);
     const size_t o_chol = take(sizeof(double) * tri(d) * Cz), o_ring = take(sizeof(double) * (cfg->adapt_mode == RSFM_ADAPT_COMPAT ? cfg->adapt_interval : 1) * Cz);
     const size_t o_suff = take(sizeof(double) * (d + tri(d)) * Cz), o_data = take(sizeof(double) * ((size_t)cfg->n_out + 2));
-    const bool want_fit = d == 1 && C <= SPEC_MAX_CHAINS;
-    const size_t o_fit = take(sizeof(double) * (want_fit ? SPEC_FIT * Cz : 1));
+    const bool want_fit = (d == 1 && C <= SPEC_MAX_CHAINS) || (d == 3 && C <= SPEC_MAX_CHAINS / 2);
+    s->fit_rows = want_fit ? (d == 1 ? SPEC_FIT : SPEC_FIT3) : 0;
+    const size_t o_fit = take(sizeof(double) * (want_fit ? s->fit_rows * Cz : 1));
     const size_t o_nom = take(sizeof(double) * NOM_STRIDE * (size_t)cfg->n_out);
     const size_t o_acc = take(sizeof(unsigned int) * Cz), o_status = take(sizeof(int) * Cz);
     size_t o_cnt[7];
@@ -762,7 +768,7 @@ extern "C" int rsfm_init(rsfm_sampler *s, const double *q0_dev, const double *da
     CUDA_TRY(cudaMemsetAsync(s->d.urhs, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.ustep, 0, sizeof(unsigned long long) * C, stream));
     CUDA_TRY(cudaMemsetAsync(s->d.suff, 0, sizeof(double) * (d + tri(d)) * (size_t)C, stream));
-    if (s->d.fit) CUDA_TRY(cudaMemsetAsync(s->d.fit, 0, sizeof(double) * SPEC_FIT * (size_t)C, stream));
+    if (s->d.fit) CUDA_TRY(cudaMemsetAsync(s->d.fit, 0, sizeof(double) * s->fit_rows * (size_t)C, stream));
     const int block = pick_block(C, &s->cfg), grid = (C + block - 1) / block;
     const ModelK M = make_model(&s->cfg);
     // nominal load table of this sampler (a tabulated load is read HERE: the table must not change afterwards); the
@@ -1204,7 +1210,7 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
     // the fit of SS(q), one slot per group (one-warp blocks: <= 16 groups per block): moments S0..S4 of x and T0..T2 of
     // x^k y, coefficients c0..c2, mean squared residual, "fit valid", "residual known", and the centre / scale of the
     // fit variables (kept here, not in registers: nothing of the predictor is live across the solve)
-    __shared__ double s_sur[32 * SPEC_FIT];
+    __shared__ double s_sur[(D == 3) ? 8 * SPEC_FIT3 : 32 * SPEC_FIT];    // (d = 3 runs >= 4 lanes per chain: <= 8 groups)
     LoadScratch lscr;
     lscr.tab = s_ltab; lscr.priv = s_lpriv; lscr.nom = S.nom;
     constexpr int T = D * (D + 1) / 2;
@@ -1218,7 +1224,7 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
     const int li = lane - gbase;                       // this lane's slot in its group: it receives the li-th node
     const size_t Cz = (size_t)C;
     const bool writer = chain_ok && li == 0;
-    double *const sur = s_sur + (threadIdx.x >> g) * SPEC_FIT;
+    double *const sur = s_sur + (threadIdx.x >> g) * ((D == 3) ? SPEC_FIT3 : SPEC_FIT);
 
     double q[D], L[T], sq[D], sqq[T];
 #pragma unroll
@@ -1237,7 +1243,27 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
 
     // fit variable x = (1/q' - 1/q_c) q_c^2 / (proposal s.d.), y = SS' - SS_c, centred on the state at launch
     // (the fit lives in the sampler between launches, SamplerDev::fit, and in shared memory during one)
-    if (li == 0) {
+    if (D == 3 && li == 0) {
+        // d = 3: t = ((1/a' - 1/a_c) a_c^2/sd_a, (b'/a' - b_c/a_c) a_c/sd_b, (1/Dc' - 1/Dc_c) Dc_c^2/sd_Dc) with the
+        // marginal proposal s.d. of the factor in force at the first launch
+        const bool kept = S.fit && S.fit[85 * Cz + cc] != 0.0;
+        if (kept) {
+#pragma unroll 1
+            for (int k = 0; k < SPEC_FIT3; k++) sur[k] = S.fit[k * Cz + cc];
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < SPEC_FIT3; k++) sur[k] = 0.0;
+            const double sda = fabs(L[0]), sdb = sqrt(L[1 % T] * L[1 % T] + L[2 % T] * L[2 % T]);
+            const double sdd = sqrt(L[3 % T] * L[3 % T] + L[4 % T] * L[4 % T] + L[5 % T] * L[5 % T]);
+            const double a_c = q[0], b_c = q[1 % D], d_c = q[2 % D];
+            sur[78] = 1.0 / a_c; sur[79] = b_c / a_c; sur[80] = 1.0 / d_c;
+            sur[81] = a_c * a_c / sda; sur[82] = a_c / sdb; sur[83] = d_c * d_c / sdd; sur[84] = ss;
+            const bool ok = a_c > 0.0 && d_c > 0.0 && sur[81] > 0.0 && sur[81] < 1e300 && sur[82] > 0.0 && sur[82] < 1e300 &&
+                            sur[83] > 0.0 && sur[83] < 1e300;
+            sur[85] = ok ? 1.0 : -1.0;
+        }
+    }
+    if (D != 3 && li == 0) {
         const bool kept = (D == 1) && S.fit && S.fit[17 * Cz + cc] != 0.0;
         if (kept) {
 #pragma unroll
@@ -1272,10 +1298,11 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
             dgam = philox_gamma(key, gid, giter, gshape);
         }
         // ---- predictor of this round ----
-        const bool have_fit = sur[17] > 0.0 && sur[12] != 0.0 && sur[13] != 0.0;
+        const bool have_fit = (D == 3) ? (sur[85] > 0.0 && sur[76] != 0.0 && sur[77] != 0.0)
+                                       : (sur[17] > 0.0 && sur[12] != 0.0 && sur[13] != 0.0);
         const double fc0 = sur[8], fc1 = sur[9], fc2 = sur[10];
         const double rqc = sur[14], ss0 = sur[15], xs = sur[16];
-        const double rtau = have_fit ? rsqrt(2.0 * fmax(sur[11], 1e-300)) : 0.0;
+        const double rtau = have_fit ? rsqrt(2.0 * fmax((D == 3) ? sur[75] : sur[11], 1e-300)) : 0.0;
         const double p0 = fmin(fmax(((double)n_acc + 1.0) / ((double)nsolve + 2.0), 0.05), 0.95);
         // ---- the tree: slot r of the group receives the r-th node, best first by reach probability ----
         bool have = false, n_inb = false, n_exact = false;
@@ -1346,7 +1373,14 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
                 n_sshat = n_ssc;
                 if (!n_inb) {
                     n_p = 0.0;                                   // an out-of-bounds proposal is never accepted
-                } else if (have_fit && qn[0] > 0.0) {
+                } else if (D == 3 && have_fit && qn[0] > 0.0 && qn[D - 1] > 0.0) {
+                    const double ra = 1.0 / qn[0];
+                    const double t0 = (ra - sur[78]) * sur[81], t1 = (qn[1 % D] * ra - sur[79]) * sur[82];
+                    const double t2 = (1.0 / qn[D - 1] - sur[80]) * sur[83];
+                    n_sshat = sur[84] + sur[65] + t0 * (sur[66] + t0 * sur[69] + t1 * sur[70] + t2 * sur[71]) +
+                              t1 * (sur[67] + t1 * sur[72] + t2 * sur[73]) + t2 * (sur[68] + t2 * sur[74]);
+                    n_p = fmin(fmax(0.5 * erfc(-(thr - n_sshat) * rtau), 0.02), 0.98);
+                } else if (D == 1 && have_fit && qn[0] > 0.0) {
                     const double x = (1.0 / qn[0] - rqc) * xs;
                     n_sshat = ss0 + fma(x, fma(x, fc2, fc1), fc0);
                     n_p = fmin(fmax(0.5 * erfc(-(thr - n_sshat) * rtau), 0.02), 0.98);
@@ -1423,6 +1457,115 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
 #pragma unroll
                 for (int k = 0; k < 8; k++) sur[k] = mo[k];
                 sur[8] = c0; sur[9] = c1; sur[10] = c2; sur[11] = tau2; sur[12] = valid ? 1.0 : 0.0; sur[13] = has_tau;
+            }
+            __syncwarp();
+        }
+
+        if (D == 3) {
+            // Ten-coefficient fit: features f = (1, t0, t1, t2, t0^2, t0 t1, t0 t2, t1^2, t1 t2, t2^2).  The group sums
+            // f f^T and f y of this round's completed solves entry by entry (rolled loops, f on the stack), slot 0 of
+            // the group keeps the normal equations in shared memory (older rounds forgotten by 0.7) and solves them by
+            // Cholesky; the other lanes wait at the warp barrier.  Every shuffle is executed by all lanes.
+            const bool use = sur[85] > 0.0;
+            const bool pt = use && solve && o.status == 0 && qn[0] > 0.0 && qn[D - 1] > 0.0 && o.sse < 1e300;
+            double f[10];
+            {
+                const double ra = pt ? 1.0 / qn[0] : 0.0;
+                const double t0 = pt ? (ra - sur[78]) * sur[81] : 0.0, t1 = pt ? (qn[1 % D] * ra - sur[79]) * sur[82] : 0.0;
+                const double t2 = pt ? (1.0 / qn[D - 1] - sur[80]) * sur[83] : 0.0;
+                f[0] = pt ? 1.0 : 0.0; f[1] = t0; f[2] = t1; f[3] = t2; f[4] = t0 * t0; f[5] = t0 * t1; f[6] = t0 * t2;
+                f[7] = t1 * t1; f[8] = t1 * t2; f[9] = t2 * t2;
+            }
+            const double y = pt ? o.sse - sur[84] : 0.0;
+            const bool had_fit = sur[76] != 0.0;
+            double pred = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < 10; k++) pred += f[k] * sur[65 + k];
+            const double res = (pt && had_fit) ? y - pred : 0.0;
+            double rs = res * res, rn = (pt && had_fit) ? 1.0 : 0.0, n_round = f[0];
+            for (int off = 1; off < G; off <<= 1) {
+                rs += __shfl_xor_sync(FULL_MASK, rs, off);
+                rn += __shfl_xor_sync(FULL_MASK, rn, off);
+                n_round += __shfl_xor_sync(FULL_MASK, n_round, off);
+            }
+            __syncwarp();                                   // the old coefficients have been read by every lane
+            int idx = 0;
+#pragma unroll 1
+            for (int i = 0; i < 10; i++) {
+#pragma unroll 1
+                for (int j = i; j <= 10; j++) {             // j = 10: the right-hand side f_i y
+                    double v = f[i] * (j < 10 ? f[j] : y);
+                    for (int off = 1; off < G; off <<= 1) v += __shfl_xor_sync(FULL_MASK, v, off);
+                    const int at = j < 10 ? idx++ : 55 + i;
+                    if (use && li == 0) sur[at] = 0.7 * sur[at] + v;
+                }
+            }
+            if (use && li == 0) {
+                // P c = R by Cholesky (P = U^T U, upper triangle by rows), a relative ridge of 1e-10 on the diagonal
+                double U[55], c[10];
+                bool ok = sur[0] >= 20.0;
+                int p0i = 0;
+#pragma unroll 1
+                for (int i = 0; i < 10 && ok; i++) {
+                    // row i of U: U_ii = sqrt(P_ii - sum_k<i U_ki^2), U_ij = (P_ij - sum_k<i U_ki U_kj) / U_ii
+#pragma unroll 1
+                    for (int j = i; j < 10; j++) {
+                        double a = sur[p0i + (j - i)] * (j == i ? 1.0 + 1e-10 : 1.0);
+                        int pk = 0;
+#pragma unroll 1
+                        for (int k = 0; k < i; k++) { a -= U[pk + (i - k)] * U[pk + (j - k)]; pk += 10 - k; }
+                        if (j == i) {
+                            if (!(a > 1e-12 * sur[p0i]) || !(a < 1e300)) { ok = false; break; }
+                            U[p0i] = sqrt(a);
+                        } else {
+                            U[p0i + (j - i)] = a / U[p0i];
+                        }
+                    }
+                    p0i += 10 - i;
+                }
+                if (ok) {
+                    // U^T w = R, then U c = w
+                    int pi = 0;
+#pragma unroll 1
+                    for (int i = 0; i < 10; i++) {
+                        double a = sur[55 + i];
+                        int pk = 0;
+#pragma unroll 1
+                        for (int k = 0; k < i; k++) { a -= U[pk + (i - k)] * c[k]; pk += 10 - k; }
+                        c[i] = a / U[pi];
+                        pi += 10 - i;
+                    }
+#pragma unroll 1
+                    for (int i = 9; i >= 0; i--) {
+                        int pi2 = 0;
+                        for (int k = 0; k < i; k++) pi2 += 10 - k;
+                        double a = c[i];
+#pragma unroll 1
+                        for (int j = i + 1; j < 10; j++) a -= U[pi2 + (j - i)] * c[j];
+                        c[i] = a / U[pi2];
+                        if (!(fabs(c[i]) < 1e300)) ok = false;
+                    }
+                }
+                if (ok) {
+#pragma unroll 1
+                    for (int k = 0; k < 10; k++) sur[65 + k] = c[k];
+                }
+                sur[76] = ok ? 1.0 : 0.0;
+            }
+            __syncwarp();
+            // residual scale: against the previous fit when there was one, else in-sample (n - 10 degrees of freedom)
+            const bool valid = sur[76] != 0.0;
+            double pred2 = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < 10; k++) pred2 += f[k] * sur[65 + k];
+            const double r0 = (pt && valid) ? y - pred2 : 0.0;
+            double rr = r0 * r0;
+            for (int off = 1; off < G; off <<= 1) rr += __shfl_xor_sync(FULL_MASK, rr, off);
+            if (use && li == 0) {
+                double tau2 = sur[75], has_tau = sur[77];
+                if (rn > 0.0) { const double msr = rs / rn; tau2 = has_tau != 0.0 ? 0.7 * tau2 + 0.3 * msr : msr; has_tau = 1.0; }
+                if (has_tau == 0.0 && valid && n_round > 10.5) { tau2 = rr / (n_round - 10.0); has_tau = 1.0; }
+                sur[75] = tau2; sur[77] = has_tau;
             }
             __syncwarp();
         }
@@ -1541,6 +1684,10 @@ rsf_mcmc_spec_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunA
 #pragma unroll
             for (int k = 0; k < SPEC_FIT; k++) S.fit[k * Cz + c] = sur[k];
         }
+        if (D == 3 && S.fit) {
+#pragma unroll 1
+            for (int k = 0; k < SPEC_FIT3; k++) S.fit[k * Cz + c] = sur[k];
+        }
 #pragma unroll
         for (int j = 0; j < D; j++) S.q[j * Cz + c] = q[j];
         S.sse[c] = ss; S.sigma2[c] = s2;
@@ -1575,13 +1722,12 @@ static int pick_spec_depth(const rsfm_sampler *s, const RunArgs &A)
     // sub-partition only shares its FP64 pipe.  With the predictor a round advances nearly as many iterations as the
     // group has lanes, so the second warp's lanes pay (profiles/microbench/spec_predict.py: 1,024 chains 16.6 -> 17.9 M
     // chain-iterations/s from near starts, 10.4 -> 16.7 M from the prior's width; 2,048: 18.1 -> 20.9 M; 4,096: 19.0 -> 22.9 M).
-    // Without the fit (d = 3) the trees follow the acceptance rate only and the round-1 rule stands: one warp per
-    // sub-partition, except that four lanes per chain still pay at two.
+    // (d = 3 has its own fit, ten coefficients in (1/a, b/a, 1/Dc), and follows the same rule:
+    //  profiles/microbench/spec_predict3.py)
     const long long one = (long long)sms * 4 * 32;
-    const long long cap = s->cfg.n_params == 1 ? 2 * one : one;
+    const long long cap = 2 * one;
     int g = 0;
     while (g < 5 && ((long long)s->C << (g + 1)) <= cap) g++;
-    if (g < 2 && s->cfg.n_params != 1 && ((long long)s->C << 2) <= 2 * one) g = 2;
     // d = 1: two lanes per chain (root + its likelier child) still pay -- the one-thread-per-chain kernel is latency
     // bound at one warp per sub-partition (9,473 .. 18,944 chains; cfg 4: 16,384)
     return (g >= 2 || (g == 1 && s->cfg.n_params == 1)) ? g : 0;
@@ -1741,7 +1887,7 @@ extern "C" int rsfm_set_state(rsfm_sampler *s, const double *q_dev, const double
     if (sigma2_dev) CUDA_TRY(cudaMemcpyAsync(s->d.sigma2, sigma2_dev, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
     if (chol_dev) CUDA_TRY(cudaMemcpyAsync(s->d.chol, chol_dev, sizeof(double) * tri(d) * C, cudaMemcpyDeviceToDevice, st));
     // the predictor of the speculative kernel starts over around the new state (it never affects results)
-    if (s->d.fit) CUDA_TRY(cudaMemsetAsync(s->d.fit, 0, sizeof(double) * SPEC_FIT * C, st));
+    if (s->d.fit) CUDA_TRY(cudaMemsetAsync(s->d.fit, 0, sizeof(double) * s->fit_rows * C, st));
     if (iteration >= 0) s->iteration = iteration;
     return RSFM_OK;
 }
