@@ -1185,8 +1185,10 @@ rsf_mcmc_kernel(const __grid_constant__ ModelK M, int C, SamplerDev S, RunArgs A
 //     decision SS' < SS - 2 s2 ln U itself: p = Phi((threshold - SS'_fit) / rms residual of the fit).
 //     On the bench workload 99 % of the decisions are predicted and a 16-lane group advances ~15
 //     iterations per round where the balanced tree of round 1 advanced 4.
-//   * otherwise (d = 3, no fit yet): p = the running acceptance rate of the launch; p = 0.5 gives
-//     back the balanced tree.
+//   * d = 3 (a, b, Dc): the same with a full quadratic (ten coefficients) in (1/a, b/a, 1/Dc), whose
+//     normal equations one lane of the group keeps in shared memory and solves by Cholesky.
+//   * no fit yet: p = the running acceptance rate of the launch; p = 0.5 gives back the balanced
+//     tree.
 //
 // Early stopping: a node whose path holds no accept is judged against the state the round started
 // with, so its threshold SS - 2 s2 ln U is known exactly (s2 follows from the gamma draws alone)
