@@ -147,3 +147,129 @@ def speculative_chain(model, data, q0, var, lo, hi, z, u, gam, lanes, use_fit=Tr
             tau2 = float(sum((y - (coef[0] + x * (coef[1] + x * coef[2]))) ** 2 for x, y in pts)) / (len(pts) - 3.0)
     stats = dict(rounds=rounds, advance=n / rounds, evaluated=evaluated, predicted=predicted / max(1, decided))
     return np.array(chain), np.array(acc), stats
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# joint (a, b, Dc) posterior: the same policy with a ten-coefficient quadratic in t = (1/a, b/a, 1/Dc)
+# ---------------------------------------------------------------------------------------------------------------
+class _SS3:
+    def __init__(self, data):
+        self.data, self.cache = np.ascontiguousarray(data), {}
+
+    def many(self, qs):
+        out = []
+        for q in qs:
+            k = tuple(float(x) for x in q)
+            if k not in self.cache:
+                self.cache[k] = orc.sse(orc.forward(orc.make_model(Dc=k[2], a=k[0], b=k[1]))[1], self.data)
+            out.append(self.cache[k])
+        return out
+
+
+def _features(q, qc, sc):
+    t = np.array([1.0 / q[0] - 1.0 / qc[0], q[1] / q[0] - qc[1] / qc[0], 1.0 / q[2] - 1.0 / qc[2]]) * sc
+    return np.array([1.0, t[0], t[1], t[2], t[0] * t[0], t[0] * t[1], t[0] * t[2], t[1] * t[1], t[1] * t[2], t[2] * t[2]])
+
+
+def chain_abdc(data, q0, sd, lo, hi, z, u, gam, lanes=0, use_fit=True, forget=0.7):
+    """Joint (a, b, Dc) chain with independent proposal s.d. ``sd`` [3] and draws z [n, 3], u [n], gam [n]:
+    ``lanes = 0`` runs the sequential loop, otherwise rounds of ``lanes`` tree nodes.  Returns (chain [n+1, 3], accepts
+    [n], stats)."""
+    ss_of = _SS3(data)
+    lo, hi, sd = np.asarray(lo, float), np.asarray(hi, float), np.asarray(sd, float)
+    n = len(u)
+    q = np.array(q0, dtype=float)
+    ss = ss_of.many([q])[0]
+    s2 = ss / (len(data) - 3)
+    chain, acc = [q.copy()], []
+    if lanes == 0:
+        for i in range(n):
+            qn = q + sd * z[i]
+            ok = bool(np.all(qn > lo) and np.all(qn < hi))
+            if ok:
+                ssn = ss_of.many([qn])[0]
+                ok = min(0.0, 0.5 * (ss - ssn) / s2) > math.log(u[i])
+                if ok:
+                    q, ss = qn, ssn
+            acc.append(ok)
+            chain.append(q.copy())
+            s2 = 1.0 / (gam[i] * (1.0 / (0.5 * (N0 * s2 + ss))))
+        return np.array(chain), np.array(acc), dict(rounds=n, advance=1.0, evaluated=n, predicted=0.0)
+    qc, ss0 = q.copy(), ss
+    sc = np.array([qc[0] ** 2 / sd[0], qc[0] / sd[1], qc[2] ** 2 / sd[2]])
+    pm, rv, coef, tau2 = np.zeros((10, 10)), np.zeros(10), None, None
+    it = rounds = evaluated = predicted = decided = 0
+    while it < n:
+        rmax = min(lanes, n - it)
+        fit = use_fit and coef is not None and tau2 is not None
+        p_prior = min(max((sum(acc) + 1.0) / (decided + 2.0), 0.05), 0.95)
+
+        def node(cur, ssc, s2c, depth, reach):
+            m = it + depth - 1
+            qn = cur + sd * z[m]
+            inb = bool(np.all(qn > lo) and np.all(qn < hi))
+            thr = ssc - 2.0 * s2c * math.log(u[m])
+            sshat, p = ssc, p_prior
+            if not inb:
+                p = 0.0
+            elif fit:
+                sshat = ss0 + float(_features(qn, qc, sc) @ coef)
+                p = min(max(0.5 * math.erfc(-(thr - sshat) / math.sqrt(2.0 * max(tau2, 1e-300))), 0.02), 0.98)
+            kids = depth < rmax
+            return dict(cur=cur, ssc=ssc, s2c=s2c, depth=depth, reach=reach, qn=qn, inb=inb, p=p, sshat=sshat, g=gam[m],
+                        vA=reach * p if kids else -1.0, vR=reach * (1.0 - p) if kids else -1.0, cA=-1, cR=-1)
+
+        nodes = [node(q, ss, s2, 1, 1.0)]
+        for _ in range(1, lanes):
+            best, bi, bc = 0.0, -1, None
+            for i, nd in enumerate(nodes):
+                for c in ("A", "R"):
+                    if nd["v" + c] > best:
+                        best, bi, bc = nd["v" + c], i, c
+            if bi < 0:
+                break
+            par = nodes[bi]
+            par["v" + bc], par["c" + bc] = -1.0, len(nodes)
+            ssc = par["sshat"] if bc == "A" else par["ssc"]
+            s2n = 1.0 / (par["g"] * (1.0 / (0.5 * (N0 * par["s2c"] + ssc))))
+            nodes.append(node(par["qn"] if bc == "A" else par["cur"], ssc, s2n, par["depth"] + 1,
+                              par["reach"] * (par["p"] if bc == "A" else 1.0 - par["p"])))
+        vals = ss_of.many([nd["qn"] for nd in nodes if nd["inb"]])
+        evaluated += len(vals)
+        k = 0
+        for nd in nodes:
+            if nd["inb"]:
+                nd["sse"], k = vals[k], k + 1
+        cl = done = 0
+        while cl >= 0 and done < rmax:
+            nd, m = nodes[cl], it + done
+            ok = False
+            if nd["inb"]:
+                ok = min(0.0, 0.5 * (ss - nd["sse"]) / s2) > math.log(u[m])
+                decided += 1
+                predicted += int(ok == (nd["p"] > 0.5))
+                if ok:
+                    q, ss = nd["qn"], nd["sse"]
+            acc.append(ok)
+            chain.append(q.copy())
+            s2 = 1.0 / (gam[m] * (1.0 / (0.5 * (N0 * s2 + ss))))
+            done += 1
+            cl = nd["cA"] if ok else nd["cR"]
+        it += done
+        rounds += 1
+        pts = [(_features(nd["qn"], qc, sc), nd["sse"] - ss0) for nd in nodes if nd["inb"]]
+        if coef is not None and pts:
+            msr = float(np.mean([(y - f @ coef) ** 2 for f, y in pts]))
+            tau2 = msr if tau2 is None else 0.7 * tau2 + 0.3 * msr
+        pm = forget * pm + sum((np.outer(f, f) for f, _ in pts), np.zeros((10, 10)))
+        rv = forget * rv + sum((f * y for f, y in pts), np.zeros(10))
+        coef = None
+        if pm[0, 0] >= 20.0:
+            try:
+                coef = np.linalg.solve(pm + 1e-10 * np.diag(np.diag(pm)), rv)
+            except np.linalg.LinAlgError:
+                coef = None
+        if coef is not None and tau2 is None and len(pts) > 10:
+            tau2 = float(sum((y - f @ coef) ** 2 for f, y in pts)) / (len(pts) - 10.0)
+    stats = dict(rounds=rounds, advance=n / rounds, evaluated=evaluated, predicted=predicted / max(1, decided))
+    return np.array(chain), np.array(acc), stats

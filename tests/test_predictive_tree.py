@@ -50,3 +50,23 @@ def test_sum_of_squares_is_quadratic_in_the_reciprocal_of_dc(orc, problem):
         return np.max(np.abs(ss - np.polyval(np.polyfit(x, ss, 2), x))) / s2
     assert resid(1.0 / qs) < 0.05
     assert resid(qs) > 1.0
+
+
+def test_joint_posterior_trees_with_the_ten_coefficient_fit(orc, problem):
+    """d = 3: the policy with the quadratic in (1/a, b/a, 1/Dc): the sequential chain whatever the tree, most nodes
+    on the realised path."""
+    from oracle import predictive_tree as pt
+    rng = np.random.default_rng(9)
+    n = 200
+    z, u, gam = rng.standard_normal((n, 3)), rng.random(n), rng.gamma(0.5 * (0.01 + 500), size=n)
+    args = (problem["data"], [0.0105, 0.0145, 1200.0], [2e-4, 3e-4, 40.0], [0.005, 0.005, 0.0], [0.02, 0.03, 1e4], z, u, gam)
+    ref_chain, ref_acc, _ = pt.chain_abdc(*args, lanes=0)
+    assert 0.1 < ref_acc.mean() < 0.9
+    res = {}
+    for use_fit in (False, True):
+        chain, acc, st = pt.chain_abdc(*args, lanes=16, use_fit=use_fit)
+        assert np.array_equal(chain, ref_chain) and np.array_equal(acc, ref_acc)
+        res[use_fit] = st
+    assert res[False]["advance"] < 6.5
+    assert res[True]["advance"] > 8.5 and res[True]["predicted"] > 0.9
+    assert res[True]["evaluated"] < 0.6 * res[False]["evaluated"]
